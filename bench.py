@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the vectorised env-step path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c3] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one `vector_step` over the rank's shard: ONE launch of the fused CUDA kernel (physics x frame_skip +
+states + termination + reward + observation + in-kernel Philox reset of truncated envs).  Prints ONE JSON line
+(rank 0).  `value` is device-timed (CUDA events on the launching stream, inputs resident in HBM, L2 flushed between
+timed steps); `e2e` is the same metric through the C-ABI host-buffer entry point (`dsim_step_host`: pinned host
+actions -> H2D -> kernel -> D2H obs/reward/truncated) timed on the host clock.  `roofline` is the step kernel
+against the MEASURED HBM peak; `cpu_baseline` is the FP64 C oracle (OpenMP) on the box's host cores.
+`--impl reference` times that CPU implementation alone (the reference's own Python + MuJoCo cannot run on the box:
+/root/reference and the mujoco wheel do not exist there).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes per env-step: state read 104 + state/flags write 94 + obs 4*obs_dim (+24 params, +16 per-env ref)
+WORKLOADS = {
+    # BASELINE.json configs[3]: RMA domain randomisation, 1M envs over 8 GPUs = 131072 per GPU (train_RMA.py:66-75)
+    "c4": dict(cls="LocalFrameRPYParamsEnv", reward="distance_energy_reward", envs_per_gpu=131072, alg_bytes=104 + 94 + 88 + 24,
+               cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True),
+               name="C4: LocalFrameRPYParamsEnv(22 obs)+distance_energy_reward, per-env randomised params, 131072 envs/GPU (1M over 8 GPUs)"),
+    # configs[1]: BaseDroneEnv, 4096 envs, default (hover-at-reference) reward, raw 33-float obs
+    "c2": dict(cls="BaseDroneEnv", reward="default_reward_fcn", envs_per_gpu=4096, alg_bytes=104 + 94 + 132,
+               cfg=dict(), name="C2: BaseDroneEnv(33 obs)+default_reward_fcn, base_config, 4096 envs"),
+    # configs[2]: moving-reference tracking, 65536 envs, per-env joystick-style setpoints
+    "c3": dict(cls="LocalFrameRPYEnv", reward="distance_reward_fcn", envs_per_gpu=65536, alg_bytes=104 + 94 + 64 + 16,
+               cfg=dict(per_env_reference=True), name="C3: LocalFrameRPYEnv(16 obs)+distance_reward_fcn, per-env moving setpoints, 65536 envs"),
+    # C4 env at the per-GPU size of configs[4] (4M envs over 8 GPUs): working set > L2
+    "c4x4": dict(cls="LocalFrameRPYParamsEnv", reward="distance_energy_reward", envs_per_gpu=524288, alg_bytes=104 + 94 + 88 + 24,
+                 cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True),
+                 name="C4 env at 524288 envs/GPU (the per-GPU env count of config 5)"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = float(f[1])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[0]))
+                    for k, nm in enumerate(names):
+                        if f[3 + k].lower().startswith("active"):
+                            reasons.add(nm)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_env(wl, n, rank_offset, device, auto_reset=True):
+    import mujoco_drone_b200 as M
+    cls = M.BaseDroneEnv if wl["cls"] == "BaseDroneEnv" else getattr(M.observation_wrappers, wl["cls"])
+    cfg = dict(M.base_config)
+    cfg.update(wl["cfg"])
+    cfg.update(num_drones=n, reward_fcn=getattr(M.rewards, wl["reward"]), env_id_offset=rank_offset, device=device, auto_reset=auto_reset)
+    return cls(cfg)
+
+
+def cpu_baseline(wl, threads, target_seconds=12.0, n=8192):
+    """FP64 C oracle (oracle/dsim_oracle.c, OpenMP over envs) on a bounded sample of the same workload."""
+    from oracle import oracle as O
+    import mujoco_drone_b200 as M
+    rng = np.random.default_rng(0)
+    cfgd = dict(M.base_config)
+    cfgd.update(wl["cfg"])
+    pd = cfgd["param_difficulty"] if cfgd.get("random_params", True) else 0.0
+    c = np.array([1, 0.17, 7, 0.01, 1.2, 0.3])
+    hw = np.array([0.1, 0.02, 1, 0.0025, 0.2, 0.05])
+    params = c + rng.uniform(-1, 1, size=(n, 6)) * hw * pd
+    env = O.CpuVecEnv(params, True, 100.0, 1, True)
+    sd = cfgd["state_difficulty"]
+    rc = O.make_reset_cfg([0, 0, 15, 0], sd * 2, [0, 0], [sd] * 3, [sd] * 3, [0.5 * sd] * 2, [0.5 * sd] * 2, True, True)
+    for i in range(n):
+        env.qpos[i], env.qvel[i] = O.sample_state(rc, 42, i, 0)
+    rid, oid = O.REWARD_IDS[wl["reward"]], O.OBS_IDS[wl["cls"]]
+    ref = np.array([0, 0, 15.0, 0])
+    if cfgd.get("per_env_reference"):
+        ref = np.tile(ref, (n, 1))
+    acts = rng.uniform(0, 1, size=(n, 4))
+    env.step(acts, ref, rid, oid, 4.0, 10 ** 9, nthreads=threads)       # warm-up
+    steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < target_seconds:
+        env.step(acts, ref, rid, oid, 4.0, 10 ** 9, nthreads=threads)
+        steps += 1
+    dt = time.perf_counter() - t0
+    return dict(value=n * steps / dt, unit="env-steps/s", cores=threads, kind="port",
+                sample=f"{steps} vector_steps x {n} envs of the same workload in {dt:.1f} s (FP64 C restatement of mj_step + obs/reward, OpenMP)")
+
+
+def run_reference_arm(args, wl, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = O.max_threads()
+    n = 8192
+    # each "step" = one vector_step over a bounded sample of n envs
+    from oracle import oracle as O2  # noqa: F401
+    import mujoco_drone_b200 as M
+    rng = np.random.default_rng(0)
+    cfgd = dict(M.base_config)
+    cfgd.update(wl["cfg"])
+    pd = cfgd["param_difficulty"] if cfgd.get("random_params", True) else 0.0
+    params = np.array([1, 0.17, 7, 0.01, 1.2, 0.3]) + rng.uniform(-1, 1, size=(n, 6)) * np.array([0.1, 0.02, 1, 0.0025, 0.2, 0.05]) * pd
+    env = O.CpuVecEnv(params, True, 100.0, 1, True)
+    env.qpos[:, 2] = 15.0
+    rid, oid = O.REWARD_IDS[wl["reward"]], O.OBS_IDS[wl["cls"]]
+    ref = np.tile(np.array([0, 0, 15.0, 0]), (n, 1)) if cfgd.get("per_env_reference") else np.array([0, 0, 15.0, 0])
+    acts = rng.uniform(0, 1, size=(n, 4))
+    for _ in range(args.warmup):
+        env.step(acts, ref, rid, oid, 4.0, 10 ** 9, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        env.step(acts, ref, rid, oid, 4.0, 10 ** 9, nthreads=threads)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    sample = f"each step = one vector_step over a {n}-env sample of the workload; FP64 C restatement (oracle port), {threads} OpenMP threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": wl["name"], "cpu_sample_envs": n},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference Python + mujoco wheel are not installable/present on the GPU box; this is the oracle port of the same path",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads / hot-L2 measurements")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mujoco_drone_b200 as M
+    from mujoco_drone_b200 import dist as ddist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = wl["envs_per_gpu"]                                    # weak scaling: fixed envs per GPU
+    env = make_env(wl, n, rank * n, local_rank)
+    env.reset_tensor()
+    nbank = 8
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    bank = torch.rand((nbank, n, 4), device=dev, generator=g)   # synthetic random actions ~U[0,1]^4, resident in HBM
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    axes = None
+    if wl["cfg"].get("per_env_reference"):
+        axes = (torch.rand((4, n), device=dev, generator=g) * 2 - 1).mul(100).round().div(100)   # joystick.py:36 rounds to 2 decimals
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run_steps(k, timed, do_flush):
+        evs = []
+        for i in range(k):
+            if do_flush and flush is not None:
+                flush.fill_(float(i))
+            if axes is not None and i % 50 == 0:
+                env.control_reference_tensor(axes)
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            env.step_tensor(bank[i % nbank])
+            if timed:
+                e1.record()
+                evs.append((e0, e1))
+        return evs
+
+    run_steps(max(args.warmup, 3), False, True)
+    barrier()
+    l0 = env.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.time()
+    evs = run_steps(args.steps, True, True)
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    launches = env.launch_count() - l0
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    stats = ddist.allreduce_episode_stats(env.episode_stats(), device=dev)     # the path's only collective
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = world * n * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the C-ABI host-buffer entry point (pinned host memory, copies inside the timed region)
+    h_act = torch.rand((nbank, n, 4)).pin_memory()
+    h_obs = torch.empty((n, env.obs_dim)).pin_memory()
+    h_rew = torch.empty((n,)).pin_memory()
+    h_tr = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    e2e_steps = max(10, min(args.steps, 50))
+    for i in range(3):
+        env.step_host(h_act[i % nbank].numpy(), h_obs.numpy(), h_rew.numpy(), h_tr.numpy())
+    barrier()
+    t0e = time.perf_counter()
+    for i in range(e2e_steps):
+        env.step_host(h_act[i % nbank].numpy(), h_obs.numpy(), h_rew.numpy(), h_tr.numpy())
+    barrier()
+    dte = torch.tensor([time.perf_counter() - t0e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dte, op=dist.ReduceOp.MAX)
+    e2e = world * n * e2e_steps / float(dte.item())
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        # same workload with L2 left hot (state stays L2-resident between steps, as in a tight rollout loop)
+        run_steps(5, False, False)
+        torch.cuda.synchronize(dev)
+        evh = run_steps(min(args.steps, 100), True, False)
+        torch.cuda.synchronize(dev)
+        msh = sum(a.elapsed_time(b) for a, b in evh)
+        extras["hot_l2"] = {"value": n * len(evh) / (msh * 1e-3), "ms_per_step": msh / len(evh), "note": "no L2 flush between steps (1 GPU, rank 0)"}
+    if world > 1:
+        dist.barrier()
+
+    peak, peak_src = measured_peaks()
+    k_ms = ms / args.steps
+    achieved = wl["alg_bytes"] * n / (k_ms * 1e-3) / 1e9
+    line = {
+        "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "envs_per_gpu": n, "total_envs": n * world, "frame_skip": 1, "timestep": 0.01,
+                   "actions": "random U[0,1]^4 from an HBM-resident bank", "auto_reset": "in-kernel Philox",
+                   "l2": "flushed between timed steps (256 MiB fill)" if flush is not None else "not flushed",
+                   "parallelism": f"env-sharded x{world}, no data-path collective"},
+        "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * (4 * env.obs_dim + 4 + 1),
+                "steps": e2e_steps, "api": "dsim_step_host (C ABI) with pinned host buffers"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "step_kernel<float,true>", "algorithmic_bytes_per_env_step": wl["alg_bytes"], "peak_source": peak_src},
+        "clocks": clocks,
+        "episode_stats": {k: stats[k] for k in ("n_episodes", "mean_return", "mean_length", "n_nonfinite", "n_near_ground")},
+    }
+    if extras:
+        line["extras"] = extras
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        line["cpu_baseline"] = cpu_baseline(wl, O.max_threads())
+    if rank == 0:
+        print(json.dumps(line))
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

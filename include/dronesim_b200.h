@@ -1,0 +1,142 @@
+/*
+ * dronesim_b200.h — C ABI of libdronesim_b200.so: the B200-native replacement for the vectorised
+ * env-step path of TichyTech/mujoco-drone.
+ *
+ * The reference has NO native FFI (it is pure Python on top of the `mujoco` wheel); the boundary this
+ * library is bound behind is the RLlib VectorEnv surface of environments/BaseDroneEnv.py.  Each entry
+ * point cites the reference interface it replaces.  Plain pointers and sizes only; no torch types, no
+ * exceptions.  Every int-returning function returns DSIM_OK (0) or a negative DSIM_E* code and leaves a
+ * message retrievable with dsim_last_error().  One handle = one shard of envs on one GPU, one caller
+ * thread, one stream at a time (reference threading model: one env object per Ray worker process,
+ * BaseDroneEnv.py:53).
+ *
+ * Device memory layout (all buffers owned by the handle, valid until dsim_destroy):
+ *   state   [DSIM_NSTATE_ROWS][ld]  SoA rows of `real` (float, or double when precision==DSIM_FP64):
+ *           0-2 position OFFSET from start_pos[0:3] | 3-6 quat (w,x,y,z) | 7-8 hinge angles (x,y)
+ *           9-11 world linear velocity | 12-14 body angular velocity | 15-16 hinge rates
+ *           17-20 motor activations `act` | 21-23 accelerometer `sensordata`
+ *           i.e. MuJoCo's qpos[9], qvel[8], act[4], sensordata[3] per drone (BaseDroneEnv.py:367-375).
+ *   ld = num_envs rounded up to a multiple of 32 (every row is 128-byte aligned).
+ */
+#ifndef DRONESIM_B200_H
+#define DRONESIM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSIM_ABI_VERSION 1
+
+enum { DSIM_OK = 0, DSIM_EINVAL = -1, DSIM_ECUDA = -2, DSIM_ENOMEM = -3, DSIM_EUNSUPPORTED = -4, DSIM_ESHAPE = -5 };
+enum { DSIM_FP32 = 0, DSIM_FP64 = 1 };
+enum { DSIM_LAYOUT_ENV_MAJOR = 0 /* [N][D], policy-ready rows */, DSIM_LAYOUT_SOA = 1 /* [D][ld] */ };
+enum { DSIM_NSTATE_ROWS = 24, DSIM_NCONST = 13, DSIM_NPARAM = 6, DSIM_MAX_OBS = 33 };
+
+/* buffer ids for dsim_buffer() */
+enum {
+    DSIM_BUF_STATE = 0,      /* real  [24][ld]                                   data.qpos/qvel/act/sensordata */
+    DSIM_BUF_NUM_STEPS = 1,  /* int32 [N]                                        BaseDroneEnv.num_steps (:110) */
+    DSIM_BUF_OBS = 2,        /* real  [N][obs_dim] or [obs_dim][ld]              vector_step()[0] */
+    DSIM_BUF_REWARD = 3,     /* real  [N]                                        vector_step()[1] */
+    DSIM_BUF_TRUNCATED = 4,  /* uint8 [N]                                        vector_step()[3] */
+    DSIM_BUF_PARAMS = 5,     /* real  [6][ld] raw drone_params                   BaseDroneEnv.drone_params (:117) */
+    DSIM_BUF_CONSTS = 6,     /* real  [13][ld] compiled rigid-body constants     (MjModel of env_gen.py) */
+    DSIM_BUF_REFERENCE = 7,  /* real  [4][ld] per-env setpoint (xyz offset from start_pos, yaw); only if per_env_reference */
+    DSIM_BUF_RESET_COUNT = 8,/* uint32[N] Philox epoch of each env's reset stream */
+    DSIM_BUF_STATES33 = 9,   /* real  [N][33|29] get_drone_states() rows, filled by dsim_compute_states */
+    DSIM_BUF_EP_RETURN = 10, /* real  [N] running return of the current episode */
+    DSIM_BUF_STATS = 11      /* double[8]: sum_return, sum_length, n_episodes, n_nonfinite, n_near_ground, 0,0,0 */
+};
+enum { DSIM_DT_F32 = 0, DSIM_DT_F64 = 1, DSIM_DT_I32 = 2, DSIM_DT_U8 = 3, DSIM_DT_U32 = 4 };
+
+/* observation variants: class names of environments/observation_wrappers.py (ids == oracle OBS_IDS) */
+enum {
+    DSIM_OBS_BASE = 0, DSIM_OBS_GLOBAL_RPY = 1, DSIM_OBS_LOCAL_PRY = 2, DSIM_OBS_LOCAL_FULLSTATE = 3,
+    DSIM_OBS_LOCAL_FULLSTATE_ZVEC = 4, DSIM_OBS_LOCAL_PRY_ACC = 5, DSIM_OBS_LOCAL_PRY_PARAMS = 6,
+    DSIM_OBS_LOCAL_PRY_ACC_PARAMS = 7, DSIM_OBS_LOCAL_RPY_PARAMS = 8, DSIM_OBS_LOCAL_RPY_FAKEPARAMS = 9,
+    DSIM_OBS_LOCAL_RPY = 10, DSIM_OBS_LOCAL_PRY_ACC_NOPEND = 11, DSIM_OBS_LOCAL_PRY_ACC_PARAMS_NOPEND = 12 /* raises in the reference */,
+    DSIM_OBS_LOCAL_RM_PARAMS = 13, DSIM_OBS_LOCAL_ZVEC = 14, DSIM_NUM_OBS = 15
+};
+/* reward functions of environments/rewards.py in file order (ids == oracle REWARD_IDS) */
+enum { DSIM_NUM_REWARDS = 17 };
+
+/* Everything BaseDroneEnv.__init__ reads from `config` (BaseDroneEnv.py:60-106), already resolved to numbers. */
+typedef struct DsimConfig {
+    int32_t struct_size;           /* sizeof(DsimConfig): ABI guard */
+    int32_t abi_version;           /* DSIM_ABI_VERSION */
+    int32_t num_envs;              /* drones on THIS device (config['num_drones'] of this shard) */
+    int32_t precision;             /* DSIM_FP32 | DSIM_FP64 (reference arithmetic is FP64) */
+    int64_t env_id_offset;         /* global id of local env 0: RNG streams are keyed by the global id */
+    uint32_t seed;                 /* config['seed'] */
+    int32_t pendulum;              /* config['pendulum'] */
+    int32_t frame_skip;            /* config['skip_steps'] */
+    int32_t round_precision;       /* 1: apply mjcf precision=5 ("%.5g") to every model attribute (env_gen.py:129) */
+    double frequency;              /* config['frequency'] -> timestep = 1/frequency (env_gen.py:82) */
+    int32_t obs_id, reward_id;     /* wrapper class / config['reward_fcn'] resolved by name */
+    int32_t obs_layout;            /* DSIM_LAYOUT_* */
+    int32_t per_env_reference;     /* 0: one reference shared by all drones (BaseDroneEnv.py:80) */
+    int32_t auto_reset;            /* 1: truncated envs are re-sampled inside the step kernel (native loop) */
+    int32_t random_start_pos, random_params;
+    double reference[4], start_pos[4];
+    double max_distance;
+    int64_t max_steps;
+    double max_pos_offset;         /* state_difficulty * max_random_offset */
+    double angle_sigma[2], vel_sigma[3], ang_vel_sigma[3], pend_rp_sigma[2], pend_vel_sigma[2]; /* already * state_difficulty */
+    double param_center[6], param_halfwidth[6], param_difficulty;   /* *_interval in drone_params order */
+} DsimConfig;
+
+typedef struct DsimHandle DsimHandle;
+
+/* -- lifetime: BaseDroneEnv.__init__ (:55-149) / close() */
+int dsim_abi_version(void);
+int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out);
+void dsim_destroy(DsimHandle *h);
+const char *dsim_last_error(const DsimHandle *h /* NULL: error of the last failed dsim_create */);
+int dsim_obs_dim(int obs_id, int pendulum);     /* observation_space.shape[0] actually EMITTED (Q14: 24 for FullStateZvec) */
+
+/* -- model: generate_drone_params (:180-216) + env_gen.make_sim/mjcf_to_mjmodel (env_gen.py:7-133) */
+int dsim_regen_params(DsimHandle *h, uint32_t epoch, void *stream);             /* Philox draw + compile, on device */
+int dsim_set_params(DsimHandle *h, const double *params_host /*[N][6]*/, void *stream); /* explicit drone_params + compile */
+int dsim_get_params(DsimHandle *h, double *params_host /*[N][6]*/);
+int dsim_get_consts(DsimHandle *h, double *consts_host /*[N][13]*/);
+
+/* -- reset: reset_model (:296-326), vector_reset (:328-332), reset_at (:334-351); set_state -> mj_forward */
+int dsim_reset_all(DsimHandle *h, void *stream);                                /* sample all, num_steps=0, forward, obs */
+int dsim_reset_masked(DsimHandle *h, const uint8_t *mask_dev, void *stream);    /* sample where mask!=0, num_steps=0 (obs untouched: Q1) */
+int dsim_reset_at(DsimHandle *h, int index, void *stream);
+int dsim_forward(DsimHandle *h, int refresh_obs, void *stream);                 /* mj_forward: sensordata (+ obs from current state) */
+int dsim_zero_act(DsimHandle *h, void *stream);                                 /* new MjData on regen: act = 0 (Q3) */
+
+/* -- step: vector_step (:259-294) = ctrl remap + mj_step x frame_skip + states + termination + reward + obs */
+int dsim_step(DsimHandle *h, const void *actions_dev /* real [N][4] */, void *stream);
+/* termination / reward / observation of the CURRENT state for the given raw actions; nothing is advanced, counted or
+ * stored (what `terminated_fcn`, `reward_fcn`, `_get_obs` return when called on `self.states`, :275-284) */
+int dsim_evaluate(DsimHandle *h, const void *actions_dev /* real [N][4] */, void *stream);
+/* same with HOST buffers (pinned or pageable), copies inside: the end-to-end path */
+int dsim_step_host(DsimHandle *h, const float *actions_host /*[N][4]*/, float *obs_host /*[N][obs_dim]*/,
+                   float *reward_host /*[N]*/, uint8_t *truncated_host /*[N]*/, void *stream);
+
+/* -- reference / setpoints: self.reference (:80), control_reference (:151-172) */
+int dsim_set_reference(DsimHandle *h, const double ref[4]);
+int dsim_control_reference(DsimHandle *h, const void *axes_dev /* real [4][ld] joystick axes x,y,z,yaw after sign flips */, void *stream);
+
+/* -- state access for callers that poke MjData (BaseDroneEnv.py:342-346) and for parity tests.
+ *    Host arrays use the reference's drone-major layout: qpos [N][9|7] (ABSOLUTE positions), qvel [N][8|6], act [N][4], sensordata [N][3] */
+int dsim_set_state(DsimHandle *h, const double *qpos, const double *qvel, const double *act, const int32_t *num_steps, void *stream);
+int dsim_get_state(DsimHandle *h, double *qpos, double *qvel, double *act, double *sensordata, int32_t *num_steps);
+int dsim_compute_states(DsimHandle *h, void *stream);                           /* get_drone_states (:357-380) -> DSIM_BUF_STATES33 */
+
+/* -- zero-copy views for the policy */
+int dsim_buffer(DsimHandle *h, int buf_id, void **dev_ptr, int64_t *rows, int64_t *cols, int64_t *ld, int32_t *dtype);
+int dsim_stats(DsimHandle *h, double out[8], int reset);                        /* episode statistics (device sync) */
+int dsim_sync(DsimHandle *h, void *stream);
+
+/* -- instrumentation */
+int64_t dsim_launch_count(const DsimHandle *h);                                 /* kernels launched by this handle */
+int dsim_kernel_info(int which /*0 step fp32, 1 step fp64*/, int32_t *regs, int32_t *local_bytes, int32_t *max_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,409 @@
+// dsim_device.cuh — device-side building blocks of the fused env-step kernel (sm_100a).
+//
+// Everything is templated on the scalar type T: float is the product path, double is the validation
+// instantiation (same source, so a derivation error shows at 1e-12 against the CPU oracle instead of hiding
+// inside FP32 round-off) and the optional FP64 mode (the reference computes in FP64).
+//
+// The dynamics are a HAND-SPECIALISED derivation for the fixed kinematic tree of environments/env_gen.py:7-73
+// (free-floating body B + link C on an x-hinge + pendulum D on a y-hinge), written in the BODY frame:
+// Newton-Euler with the composite-body 6x6 block reduced analytically to one 3x3 SPD solve and the two hinge
+// DOFs eliminated last (Schur complement), so the explicit acceleration (accelerometer, mj_sensorAcc) and the
+// implicit-joint-damping acceleration (mj_EulerSkip) share one factorisation.  It is NOT a transcription of
+// MuJoCo's generic world-frame CRB/RNE (that is what oracle/dsim_oracle.c restates); agreement between the two
+// is the derivation check.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+
+#define DSIM_DEV __device__ __forceinline__
+#define DSIM_HD __host__ __device__ __forceinline__
+
+namespace dsim {
+
+// ------------------------------------------------------------------ model-wide constants (env_gen.py)
+constexpr double kGravity = 9.81;        // MuJoCo default gravity (0,0,-9.81)
+constexpr double kRho = 1.2;             // env_gen.py:83 density
+constexpr double kEta = 0.00002;         // env_gen.py:84 viscosity
+constexpr double kHingeDamping = 0.15;   // env_gen.py:23 default joint damping (hinges only; <freejoint> takes no defaults)
+constexpr double kLinkDrop = 0.025;      // env_gen.py:66 link body at (0,0,-half_body_size/2)
+constexpr double kSenseZ = -0.0125;      // env_gen.py:48 'sense' site at (0,0,-half_body_size/4)
+constexpr double kMassC = 0.01;          // env_gen.py:68 sphere mass
+constexpr double kInertiaC = 0.4 * 0.01 * 0.02 * 0.02;   // solid sphere r = 0.02
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kMinVal = 1e-15;        // mjMINVAL
+
+// rows of the SoA state buffer (include/dronesim_b200.h)
+enum { S_POS = 0, S_QUAT = 3, S_HINGE = 7, S_VEL = 9, S_OMEGA = 12, S_HVEL = 15, S_ACT = 17, S_ACC = 21, S_ROWS = 24 };
+// rows of the compiled-constants buffer
+enum { C_MB = 0, C_CZ, C_IBX, C_IBY, C_IBZ, C_MD, C_ZD, C_IDX, C_IDZ, C_FS, C_F, C_KQ, C_INVTAU, C_ROWS };
+
+// ------------------------------------------------------------------ scalar helpers
+template <typename T> DSIM_DEV T sqrt_(T x) { if constexpr (std::is_same<T, float>::value) return sqrtf(x); else return sqrt(x); }
+template <typename T> DSIM_DEV T rsqrt_(T x) { if constexpr (std::is_same<T, float>::value) return rsqrtf(x); else return 1.0 / sqrt(x); }
+template <typename T> DSIM_DEV T abs_(T x) { if constexpr (std::is_same<T, float>::value) return fabsf(x); else return fabs(x); }
+template <typename T> DSIM_DEV T max_(T a, T b) { if constexpr (std::is_same<T, float>::value) return fmaxf(a, b); else return fmax(a, b); }
+template <typename T> DSIM_DEV T min_(T a, T b) { if constexpr (std::is_same<T, float>::value) return fminf(a, b); else return fmin(a, b); }
+template <typename T> DSIM_DEV T atan2_(T y, T x) { if constexpr (std::is_same<T, float>::value) return atan2f(y, x); else return atan2(y, x); }
+template <typename T> DSIM_DEV T fmod_(T a, T b) { if constexpr (std::is_same<T, float>::value) return fmodf(a, b); else return fmod(a, b); }
+template <typename T> DSIM_DEV T log_(T x) { if constexpr (std::is_same<T, float>::value) return logf(x); else return log(x); }
+template <typename T> DSIM_DEV T cbrt_(T x) { if constexpr (std::is_same<T, float>::value) return cbrtf(x); else return cbrt(x); }
+template <typename T> DSIM_DEV void sincos_(T a, T *s, T *c) { if constexpr (std::is_same<T, float>::value) sincosf(a, s, c); else sincos(a, s, c); }
+template <typename T> DSIM_DEV bool finite_(T x) { return isfinite(x); }
+template <typename T> DSIM_DEV T clamp_(T x, T lo, T hi) { return min_(max_(x, lo), hi); }
+// Python's float % for a positive modulus (rewards.py / observation_wrappers.py heading wrap)
+template <typename T> DSIM_DEV T pymod_(T a, T b) { T r = fmod_(a, b); return (r < T(0)) ? r + b : r; }
+template <typename T> DSIM_DEV T wrap_pi(T a) { return pymod_(a + T(kPi), T(2 * kPi)) - T(kPi); }
+
+template <typename T> struct V3 { T x, y, z; };
+template <typename T> DSIM_DEV V3<T> mk(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
+template <typename T> DSIM_DEV V3<T> operator+(V3<T> a, V3<T> b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> DSIM_DEV V3<T> operator-(V3<T> a, V3<T> b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> DSIM_DEV V3<T> operator*(T s, V3<T> a) { return mk(s * a.x, s * a.y, s * a.z); }
+template <typename T> DSIM_DEV T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> DSIM_DEV V3<T> cross(V3<T> a, V3<T> b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+
+// rotation matrix (row-major, body -> world) of a UNIT quaternion (w,x,y,z)
+template <typename T> struct M3 { T m[9]; };
+template <typename T> DSIM_DEV M3<T> quat_to_mat(T w, T x, T y, T z) {
+    M3<T> R;
+    R.m[0] = w * w + x * x - y * y - z * z; R.m[1] = 2 * (x * y - w * z);           R.m[2] = 2 * (x * z + w * y);
+    R.m[3] = 2 * (x * y + w * z);           R.m[4] = w * w - x * x + y * y - z * z; R.m[5] = 2 * (y * z - w * x);
+    R.m[6] = 2 * (x * z - w * y);           R.m[7] = 2 * (y * z + w * x);           R.m[8] = w * w - x * x - y * y + z * z;
+    return R;
+}
+template <typename T> DSIM_DEV V3<T> mul(const M3<T> &R, V3<T> v) {
+    return mk(R.m[0] * v.x + R.m[1] * v.y + R.m[2] * v.z, R.m[3] * v.x + R.m[4] * v.y + R.m[5] * v.z, R.m[6] * v.x + R.m[7] * v.y + R.m[8] * v.z);
+}
+template <typename T> DSIM_DEV V3<T> tmul(const M3<T> &R, V3<T> v) {
+    return mk(R.m[0] * v.x + R.m[3] * v.y + R.m[6] * v.z, R.m[1] * v.x + R.m[4] * v.y + R.m[7] * v.z, R.m[2] * v.x + R.m[5] * v.y + R.m[8] * v.z);
+}
+// R = Rz(yaw) Ry(pitch) Rx(roll): transformation.py:20-23 + :10-12
+template <typename T> DSIM_DEV M3<T> rpy_to_mat(T roll, T pitch, T yaw) {
+    T sr, cr, sp, cp, sy, cy;
+    sincos_(roll, &sr, &cr); sincos_(pitch, &sp, &cp); sincos_(yaw, &sy, &cy);
+    M3<T> R;
+    R.m[0] = cy * cp; R.m[1] = cy * sp * sr - sy * cr; R.m[2] = cy * sp * cr + sy * sr;
+    R.m[3] = sy * cp; R.m[4] = sy * sp * sr + cy * cr; R.m[5] = sy * sp * cr - cy * sr;
+    R.m[6] = -sp;     R.m[7] = cp * sr;                R.m[8] = cp * cr;
+    return R;
+}
+
+// ------------------------------------------------------------------ per-env state held in registers
+template <typename T> struct EnvState {
+    V3<T> pos;            // OFFSET from start_pos
+    T qw, qx, qy, qz;
+    T hx, hy;             // hinge angles
+    V3<T> vel;            // world frame
+    V3<T> om;             // body frame
+    T hvx, hvy;           // hinge rates
+    T act[4];
+    V3<T> acc;            // accelerometer
+};
+template <typename T> struct EnvConsts { T mB, cz, IBx, IBy, IBz, mD, zD, IDx, IDz, Fs, F, kq, inv_tau; };
+
+// mj_inertiaBoxFluidModel for one body: local angular/linear velocity at the COM in the principal frame ->
+// local force / torque.  Box from (mass, principal inertia).
+template <typename T> struct FluidBox { T fq[3], tq[3], kv, kw; };
+template <typename T> DSIM_DEV FluidBox<T> fluid_box(T mass, T Ix, T Iy, T Iz) {
+    T s = T(6) / mass;
+    T bx = sqrt_(max_(T(kMinVal), Iy + Iz - Ix) * s), by = sqrt_(max_(T(kMinVal), Ix + Iz - Iy) * s), bz = sqrt_(max_(T(kMinVal), Ix + Iy - Iz) * s);
+    T d = (bx + by + bz) * T(1.0 / 3.0);
+    FluidBox<T> f;
+    f.kv = T(3.0 * kPi * kEta) * d;
+    f.kw = T(kPi * kEta) * d * d * d;
+    f.fq[0] = T(0.5 * kRho) * by * bz; f.fq[1] = T(0.5 * kRho) * bx * bz; f.fq[2] = T(0.5 * kRho) * bx * by;
+    T bx2 = bx * bx, by2 = by * by, bz2 = bz * bz;
+    T bx4 = bx2 * bx2, by4 = by2 * by2, bz4 = bz2 * bz2;
+    f.tq[0] = T(kRho / 64.0) * bx * (by4 + bz4); f.tq[1] = T(kRho / 64.0) * by * (bx4 + bz4); f.tq[2] = T(kRho / 64.0) * bz * (bx4 + by4);
+    return f;
+}
+template <typename T> DSIM_DEV void fluid_apply(const FluidBox<T> &b, V3<T> w, V3<T> v, V3<T> &f, V3<T> &t) {
+    f = mk(-b.kv * v.x - b.fq[0] * abs_(v.x) * v.x, -b.kv * v.y - b.fq[1] * abs_(v.y) * v.y, -b.kv * v.z - b.fq[2] * abs_(v.z) * v.z);
+    t = mk(-b.kw * w.x - b.tq[0] * abs_(w.x) * w.x, -b.kw * w.y - b.tq[1] * abs_(w.y) * w.y, -b.kw * w.z - b.tq[2] * abs_(w.z) * w.z);
+}
+
+// symmetric 3x3 SPD solve through LDL^T (factor once, three right-hand sides per substep)
+template <typename T> struct Ldl3 { T l10, l20, l21, id0, id1, id2; };
+template <typename T> DSIM_DEV Ldl3<T> ldl3(T a00, T a10, T a11, T a20, T a21, T a22) {
+    Ldl3<T> f;
+    f.id0 = T(1) / a00;
+    f.l10 = a10 * f.id0; f.l20 = a20 * f.id0;
+    T d1 = a11 - f.l10 * a10;
+    f.id1 = T(1) / d1;
+    f.l21 = (a21 - f.l20 * a10) * f.id1;
+    T d2 = a22 - f.l20 * a20 - f.l21 * f.l21 * d1;
+    f.id2 = T(1) / d2;
+    return f;
+}
+template <typename T> DSIM_DEV V3<T> ldl3_solve(const Ldl3<T> &f, V3<T> b) {
+    T y0 = b.x, y1 = b.y - f.l10 * y0, y2 = b.z - f.l20 * y0 - f.l21 * y1;
+    T z2 = y2 * f.id2;
+    T z1 = y1 * f.id1 - f.l21 * z2;
+    T z0 = y0 * f.id0 - f.l10 * z1 - f.l20 * z2;
+    return mk(z0, z1, z2);
+}
+
+// ------------------------------------------------------------------ one mj_step (Euler, implicit hinge damping)
+// ADVANCE=false evaluates only the forward part (mj_forward: accelerometer refresh after set_state).
+template <typename T, bool PEND, bool ADVANCE>
+DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T h) {
+    // -- kinematics (mj_kinematics normalises the free-joint quaternion)
+    T qn = s.qw * s.qw + s.qx * s.qx + s.qy * s.qy + s.qz * s.qz;
+    T qi = rsqrt_(qn);
+    if (!(qn >= T(1e-30))) { s.qw = T(1); s.qx = s.qy = s.qz = T(0); qi = T(1); }
+    T qw = s.qw * qi, qx = s.qx * qi, qy = s.qy * qi, qz = s.qz * qi;
+    const M3<T> R = quat_to_mat(qw, qx, qy, qz);
+    const V3<T> vb = tmul(R, s.vel);                                         // origin velocity, body coords
+    const V3<T> gb = mk(T(-kGravity) * R.m[6], T(-kGravity) * R.m[7], T(-kGravity) * R.m[8]);   // R^T g
+    const V3<T> om = s.om;
+    const T mC = PEND ? T(kMassC) : T(0), IC = PEND ? T(kInertiaC) : T(0), dl = T(kLinkDrop);
+    const T mD = PEND ? c.mD : T(0);
+    const T mh = mC + mD, mtot = c.mB + mh, inv_m = T(1) / mtot;
+
+    T sx = 0, cx = 1, sy = 0, cy = 1;
+    if (PEND) { sincos_(s.hx, &sx, &cx); sincos_(s.hy, &sy, &cy); }
+    const V3<T> yc = mk(T(0), cx, sx);                                       // hinge-y axis (C frame y) in body coords
+    const V3<T> n = mk(sy, -sx * cy, cx * cy);                               // pendulum axis (D frame z)
+    const V3<T> xd = mk(cy, sx * sy, -cx * sy);                              // D frame x
+    const T mu = mD * c.zD;                                                  // first moment of D about the hinge point
+    const T P = PEND ? c.IDx + mD * c.zD * c.zD : T(0);                      // transverse inertia of D about the hinge
+    const T QmP = PEND ? c.IDz - P : T(0);
+
+    // -- composite body about the origin o of the free joint: first moment H, inertia Io, then about the composite COM
+    const V3<T> H = mk(mu * n.x, mu * n.y, c.mB * c.cz - mh * dl + mu * n.z);
+    const T k12 = c.mB * c.cz * c.cz + IC + mh * dl * dl + P - T(2) * mu * dl * n.z;
+    const T Ixx = c.IBx + k12 + QmP * n.x * n.x, Iyy = c.IBy + k12 + QmP * n.y * n.y, Izz = c.IBz + IC + P + QmP * n.z * n.z;
+    const T Ixy = QmP * n.x * n.y, Ixz = QmP * n.x * n.z + mu * dl * n.x, Iyz = QmP * n.y * n.z + mu * dl * n.y;
+    const Ldl3<T> L = ldl3(Ixx - (H.y * H.y + H.z * H.z) * inv_m, Ixy + H.x * H.y * inv_m, Iyy - (H.x * H.x + H.z * H.z) * inv_m,
+                           Ixz + H.x * H.z * inv_m, Iyz + H.y * H.z * inv_m, Izz - (H.x * H.x + H.y * H.y) * inv_m);
+    const V3<T> com = inv_m * H;
+
+    // -- velocity products (RNE with zero acceleration) and gravity
+    const T oxy2 = om.x * om.x + om.y * om.y;
+    const V3<T> cen = mk(om.x * om.z, om.y * om.z, -oxy2);                   // w x (w x z^) : scale by the z offset
+    // body B: COM at (0,0,cz)
+    const V3<T> FB0 = c.mB * (c.cz * cen - gb);
+    const V3<T> IBw = mk(c.IBx * om.x, c.IBy * om.y, c.IBz * om.z);
+    V3<T> blin = FB0;
+    V3<T> bang = cross(om, IBw) + mk(-c.cz * FB0.y, c.cz * FB0.x, T(0));     // N_B + r_B x F_B
+    T bias_x = 0, bias_y = 0;
+    V3<T> rho = mk(T(0), T(0), T(0)), omD = om, omC = om;
+    if (PEND) {
+        const V3<T> ah0 = (-dl) * cen;                                       // hinge point at (0,0,-dl)
+        omC = mk(om.x + s.hvx, om.y, om.z);
+        omD = omC + s.hvy * yc;
+        const V3<T> aC0 = s.hvx * mk(T(0), om.z, -om.y);                     // hvx * (w x x^)
+        const V3<T> aD0 = aC0 + s.hvy * cross(omC, yc);
+        rho = c.zD * n;
+        const V3<T> accD = ah0 + cross(aD0, rho) + cross(omD, cross(omD, rho));
+        const V3<T> FC0 = mC * (ah0 - gb);
+        const V3<T> FD0 = mD * (accD - gb);
+        const T dI = c.IDz - c.IDx;
+        const V3<T> IDa = c.IDx * aD0 + (dI * dot(n, aD0)) * n;
+        const V3<T> IDw = c.IDx * omD + (dI * dot(n, omD)) * n;
+        const V3<T> TD = IDa + cross(omD, IDw) + cross(rho, FD0);            // about the hinge point
+        const V3<T> NC0 = IC * aC0;
+        const V3<T> Fh = FC0 + FD0;
+        blin = blin + Fh;
+        bang = bang + NC0 + TD + mk(dl * Fh.y, -dl * Fh.x, T(0));            // r_h x F, r_h = (0,0,-dl)
+        bias_x = NC0.x + TD.x;
+        bias_y = dot(yc, TD);
+    }
+
+    // -- applied forces: actuators (site transmission, force = act), fluid, hinge damping
+    const T a0 = s.act[0], a1 = s.act[1], a2 = s.act[2], a3 = s.act[3];
+    V3<T> flin = mk(T(0), T(0), c.F * ((a0 + a1) + (a2 + a3)));
+    V3<T> fang = mk(c.Fs * ((a1 + a2) - (a0 + a3)), c.Fs * ((a2 + a3) - (a0 + a1)), c.kq * ((a0 + a2) - (a1 + a3)));
+    T f_x = 0, f_y = 0;
+    {   // body B: principal frame == body frame (4-fold symmetry)
+        const FluidBox<T> fb = fluid_box(c.mB, c.IBx, c.IBy, c.IBz);
+        V3<T> f, t;
+        fluid_apply(fb, om, vb + mk(om.y * c.cz, -om.x * c.cz, T(0)), f, t);
+        flin = flin + f;
+        fang = fang + t + mk(-c.cz * f.y, c.cz * f.x, T(0));
+    }
+    if (PEND) {
+        const V3<T> vh = vb + mk(-om.y * dl, om.x * dl, T(0));               // w x r_h
+        {   // body C: sphere -> cubic box; frame = Rx(hx)
+            constexpr double bC = 0.030983866769659335;                      // sqrt(6 I_C / m_C)
+            FluidBox<T> fb;
+            fb.kv = T(3.0 * kPi * kEta * bC); fb.kw = T(kPi * kEta * bC * bC * bC);
+            fb.fq[0] = fb.fq[1] = fb.fq[2] = T(0.5 * kRho * bC * bC);
+            fb.tq[0] = fb.tq[1] = fb.tq[2] = T(kRho / 64.0 * bC * 2.0 * bC * bC * bC * bC);
+            const V3<T> vl = mk(vh.x, cx * vh.y + sx * vh.z, -sx * vh.y + cx * vh.z);
+            const V3<T> wl = mk(omC.x, cx * omC.y + sx * omC.z, -sx * omC.y + cx * omC.z);
+            V3<T> fl, tl;
+            fluid_apply(fb, wl, vl, fl, tl);
+            const V3<T> f = mk(fl.x, cx * fl.y - sx * fl.z, sx * fl.y + cx * fl.z);
+            const V3<T> t = mk(tl.x, cx * tl.y - sx * tl.z, sx * tl.y + cx * tl.z);
+            flin = flin + f;
+            fang = fang + t + mk(dl * f.y, -dl * f.x, T(0));
+            f_x += t.x;
+        }
+        {   // body D: frame axes (xd, yc, n), COM at hinge + rho
+            const FluidBox<T> fb = fluid_box(mD, c.IDx, c.IDx, c.IDz);
+            const V3<T> vD = vh + cross(omD, rho);
+            V3<T> fl, tl;
+            fluid_apply(fb, mk(dot(xd, omD), dot(yc, omD), dot(n, omD)), mk(dot(xd, vD), dot(yc, vD), dot(n, vD)), fl, tl);
+            const V3<T> f = fl.x * xd + fl.y * yc + fl.z * n;
+            const V3<T> W = tl.x * xd + tl.y * yc + tl.z * n + cross(rho, f);
+            flin = flin + f;
+            fang = fang + W + mk(dl * f.y, -dl * f.x, T(0));
+            f_x += W.x;
+            f_y += dot(yc, W);
+        }
+        f_x -= T(kHingeDamping) * s.hvx;
+        f_y -= T(kHingeDamping) * s.hvy;
+    }
+
+    // -- forward acceleration: base block via the COM-reduced 3x3, hinges via the Schur complement
+    const V3<T> F = flin - blin, Tq = fang - bang;
+    const V3<T> al0 = ldl3_solve(L, Tq - cross(com, F));
+    const V3<T> ac0 = inv_m * F + cross(com, al0);
+    V3<T> a_e = ac0, al_e = al0, a_i = ac0, al_i = al0;
+    T hax_i = 0, hay_i = 0;
+    if (PEND) {
+        const T rx = f_x - bias_x, ry = f_y - bias_y;
+        const V3<T> px = (-mu * cy) * yc, py = mu * xd;                      // linear momentum per unit hinge rate
+        const V3<T> Lx = mk(IC + P + QmP * n.x * n.x, QmP * n.x * n.y, QmP * n.x * n.z) + mk(dl * px.y, -dl * px.x, T(0));
+        const V3<T> Ly = P * yc + mk(dl * py.y, -dl * py.x, T(0));
+        const V3<T> alx = ldl3_solve(L, Lx - cross(com, px)), acx = inv_m * px + cross(com, alx);
+        const V3<T> aly = ldl3_solve(L, Ly - cross(com, py)), acy = inv_m * py + cross(com, aly);
+        const T Sxx = (IC + P + QmP * n.x * n.x) - (dot(px, acx) + dot(Lx, alx));
+        const T Sxy = -(dot(px, acy) + dot(Lx, aly));
+        const T Syy = P - (dot(py, acy) + dot(Ly, aly));
+        const T r1 = rx - (dot(px, ac0) + dot(Lx, al0)), r2 = ry - (dot(py, ac0) + dot(Ly, al0));
+        {   // explicit (qacc of mj_fwdAcceleration): feeds the accelerometer
+            const T idet = T(1) / (Sxx * Syy - Sxy * Sxy);
+            const T hax = (Syy * r1 - Sxy * r2) * idet, hay = (Sxx * r2 - Sxy * r1) * idet;
+            a_e = ac0 - hax * acx - hay * acy;
+            al_e = al0 - hax * alx - hay * aly;
+        }
+        if (ADVANCE) {  // implicit in joint damping (mj_EulerSkip): (M + h diag(B)) qacc = qfrc_smooth
+            const T hb = h * T(kHingeDamping);
+            const T Sxx2 = Sxx + hb, Syy2 = Syy + hb;
+            const T idet = T(1) / (Sxx2 * Syy2 - Sxy * Sxy);
+            hax_i = (Syy2 * r1 - Sxy * r2) * idet; hay_i = (Sxx2 * r2 - Sxy * r1) * idet;
+            a_i = ac0 - hax_i * acx - hay_i * acy;
+            al_i = al0 - hax_i * alx - hay_i * aly;
+        }
+    }
+
+    // -- accelerometer at site 'sense' (0,0,zs), site frame == body frame; pre-integration state, explicit qacc
+    const T zs = T(kSenseZ);
+    s.acc = a_e - gb + mk(al_e.y * zs, -al_e.x * zs, T(0)) + zs * cen;
+
+    if (ADVANCE) {
+        // mj_advance: activation (dyntype=filter, explicit), velocity, then position with the NEW velocity
+        #pragma unroll
+        for (int k = 0; k < 4; k++) s.act[k] += h * ((ctrl[k] - s.act[k]) * c.inv_tau);
+        s.vel = s.vel + h * mul(R, a_i);
+        s.om = s.om + h * al_i;
+        s.pos = s.pos + h * s.vel;
+        // mju_quatIntegrate: q <- normalize(q) * axisangle(w/|w|, h|w|)
+        const T w2 = dot(s.om, s.om);
+        T rw = T(1), rx_ = T(0), ry_ = T(0), rz_ = T(0);
+        if (w2 >= T(1e-30)) {
+            const T iw = rsqrt_(w2), wn = w2 * iw;
+            T sh, ch;
+            sincos_(T(0.5) * h * wn, &sh, &ch);
+            rw = ch; rx_ = sh * s.om.x * iw; ry_ = sh * s.om.y * iw; rz_ = sh * s.om.z * iw;
+        }
+        s.qw = qw * rw - qx * rx_ - qy * ry_ - qz * rz_;
+        s.qx = qw * rx_ + qx * rw + qy * rz_ - qz * ry_;
+        s.qy = qw * ry_ - qx * rz_ + qy * rw + qz * rx_;
+        s.qz = qw * rz_ + qx * ry_ - qy * rx_ + qz * rw;
+        if (PEND) {
+            s.hvx += h * hax_i; s.hvy += h * hay_i;
+            s.hx += h * s.hvx; s.hy += h * s.hvy;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ transformation.py: quaternion -> (roll, pitch, yaw)
+// scipy Rotation.as_euler('ZYX')[::-1] (quaternion algorithm, gimbal-lock branches, eps 1e-7)
+template <typename T> DSIM_DEV void quat_to_rpy(T w, T x, T y, T z, T &roll, T &pitch, T &yaw) {
+    const T a = w - y, b = x + z, c = y + w, d = z - x;
+    const T hs = atan2_(b, a), hd = atan2_(d, c);
+    T a1 = T(2) * atan2_(sqrt_(c * c + d * d), sqrt_(a * a + b * b));
+    const bool case1 = abs_(a1) <= T(1e-7), case2 = abs_(a1 - T(kPi)) <= T(1e-7);
+    T a0, a2;
+    if (!case1 && !case2) { a2 = hs - hd; a0 = hs + hd; }
+    else { a2 = T(0); a0 = case1 ? T(2) * hs : T(2) * hd; }
+    a1 -= T(kPi / 2);
+    roll = wrap_pi(a2); pitch = wrap_pi(a1); yaw = wrap_pi(a0);
+}
+
+// ------------------------------------------------------------------ Philox4x32-10 and samplers
+struct U4 { uint32_t x, y, z, w; };
+DSIM_DEV U4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    #pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+template <typename T> DSIM_DEV T u01(uint32_t x) { return (T(x >> 8) + T(0.5)) * T(1.0 / 16777216.0); }
+template <typename T> DSIM_DEV void box_muller(uint32_t x0, uint32_t x1, T &z0, T &z1) {
+    const T r = sqrt_(T(-2) * log_(u01<T>(x0)));
+    T s, c;
+    sincos_(T(2 * kPi) * u01<T>(x1), &s, &c);
+    z0 = r * c; z1 = r * s;
+}
+template <typename T> DSIM_DEV T clipn(T z, T sigma) { const T v = z * sigma, lim = T(2) * sigma; return clamp_(v, -lim, lim); }
+
+template <typename T> struct ResetCfg {
+    T start_yaw, max_pos_offset;
+    T angle_sigma[2], vel_sigma[3], ang_vel_sigma[3], pend_rp_sigma[2], pend_vel_sigma[2];
+    int random_start_pos;
+};
+
+// BaseDroneEnv.sample_state (:218-257), same draw order, Philox stream 0 keyed by (seed, global env id, reset_count).
+// Activations `act` are NOT touched (Q3: they persist across episode resets).
+template <typename T, bool PEND>
+DSIM_DEV void sample_state(EnvState<T> &s, const ResetCfg<T> &rc, uint32_t seed, uint32_t env, uint32_t count) {
+    T roll = 0, pitch = 0, yaw = rc.start_yaw;
+    s.pos = mk(T(0), T(0), T(0));
+    s.vel = mk(T(0), T(0), T(0)); s.om = mk(T(0), T(0), T(0));
+    s.hx = s.hy = s.hvx = s.hvy = T(0);
+    if (rc.random_start_pos) {
+        T n0, n1, n2, n3;
+        U4 x = philox4x32(0, count, 0, 0, seed, env);
+        box_muller(x.x, x.y, n0, n1); box_muller(x.z, x.w, n2, n3);
+        const T inn = rsqrt_(n0 * n0 + n1 * n1 + n2 * n2);
+        x = philox4x32(1, count, 0, 0, seed, env);
+        const T r = rc.max_pos_offset * cbrt_(u01<T>(x.x));
+        s.pos = mk(r * (n0 * inn), r * (n1 * inn), r * (n2 * inn));
+        yaw = T(kPi) - T(2 * kPi) * u01<T>(x.y);
+        box_muller(x.z, x.w, n0, n1);
+        roll = clipn(n0, rc.angle_sigma[0]); pitch = clipn(n1, rc.angle_sigma[1]);
+        x = philox4x32(2, count, 0, 0, seed, env);
+        box_muller(x.x, x.y, n0, n1); box_muller(x.z, x.w, n2, n3);
+        s.vel = mk(clipn(n0, rc.vel_sigma[0]), clipn(n1, rc.vel_sigma[1]), clipn(n2, rc.vel_sigma[2]));
+        s.om.x = clipn(n3, rc.ang_vel_sigma[0]);
+        x = philox4x32(3, count, 0, 0, seed, env);
+        box_muller(x.x, x.y, n0, n1); box_muller(x.z, x.w, n2, n3);
+        s.om.y = clipn(n0, rc.ang_vel_sigma[1]); s.om.z = clipn(n1, rc.ang_vel_sigma[2]);
+        if (PEND) {
+            s.hx = clipn(n2, rc.pend_rp_sigma[0]); s.hy = clipn(n3, rc.pend_rp_sigma[1]);
+            x = philox4x32(4, count, 0, 0, seed, env);
+            box_muller(x.x, x.y, n0, n1);
+            s.hvx = clipn(n0, rc.pend_vel_sigma[0]); s.hvy = clipn(n1, rc.pend_vel_sigma[1]);
+        }
+    }
+    // mujoco_rpy2quat: qz(yaw) * qy(pitch) * qx(roll)
+    T sr, cr, sp, cp, sy, cy;
+    sincos_(T(0.5) * roll, &sr, &cr); sincos_(T(0.5) * pitch, &sp, &cp); sincos_(T(0.5) * yaw, &sy, &cy);
+    s.qw = cy * cp * cr + sy * sp * sr;
+    s.qx = cy * cp * sr - sy * sp * cr;
+    s.qy = cy * sp * cr + sy * cp * sr;
+    s.qz = sy * cp * cr - cy * sp * sr;
+}
+
+}  // namespace dsim

@@ -1,0 +1,813 @@
+// dsim_kernels.cu — kernels and the C ABI of libdronesim_b200.so (see include/dronesim_b200.h).
+// Target: sm_100a (B200).  One thread per env; SoA state rows are read and written fully coalesced; the
+// physics, state extraction, termination, reward, observation, episode statistics and (optionally) the
+// Philox reset of truncated envs all happen in ONE kernel launch per env-step.  There is no CPU fallback: every
+// entry point either launches on the GPU or returns an error code.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#include "../../include/dronesim_b200.h"
+#include "dsim_device.cuh"
+#include "dsim_obs_reward.cuh"
+#include "dsim_params.cuh"
+
+using namespace dsim;
+
+namespace {
+
+constexpr int kBlock = 128;
+
+// ------------------------------------------------------------------ kernel parameter block (constant bank)
+template <typename T> struct KParams {
+    int n, ld;
+    T *state;
+    int *num_steps;
+    unsigned *reset_count;
+    const T *consts;          // [13][ld]
+    const T *params;          // [6][ld]
+    T *ref_env;               // [4][ld] (per-env setpoints) or nullptr
+    T *obs, *reward, *ep_return;
+    unsigned char *trunc;
+    double *stats;
+    const T *actions;         // [n][4]
+    T uconst[C_ROWS];         // uniform-parameter fast path (random_params == False)
+    T uparams[6];
+    int per_env_consts, auto_reset, obs_id, reward_id, obs_layout, obs_dim, frame_skip, max_steps;
+    int eval_only;            // 1: termination / reward / obs of the CURRENT state, nothing advanced or stored
+    T h, max_distance_t;
+    T ref_off[3], ref_yaw, start_t[3];
+    double start[3], ref64[3], max_distance;
+    ResetCfg<T> rc;
+    unsigned seed, env_base;
+};
+
+template <typename T> DSIM_DEV EnvState<T> load_state(const KParams<T> &p, int i) {
+    const T *b = p.state + i;
+    const size_t ld = p.ld;
+    EnvState<T> s;
+    s.pos = mk(b[0 * ld], b[1 * ld], b[2 * ld]);
+    s.qw = b[3 * ld]; s.qx = b[4 * ld]; s.qy = b[5 * ld]; s.qz = b[6 * ld];
+    s.hx = b[7 * ld]; s.hy = b[8 * ld];
+    s.vel = mk(b[9 * ld], b[10 * ld], b[11 * ld]);
+    s.om = mk(b[12 * ld], b[13 * ld], b[14 * ld]);
+    s.hvx = b[15 * ld]; s.hvy = b[16 * ld];
+    #pragma unroll
+    for (int k = 0; k < 4; k++) s.act[k] = b[(S_ACT + k) * ld];
+    s.acc = mk(b[21 * ld], b[22 * ld], b[23 * ld]);
+    return s;
+}
+template <typename T> DSIM_DEV void store_state(const KParams<T> &p, int i, const EnvState<T> &s) {
+    T *b = p.state + i;
+    const size_t ld = p.ld;
+    b[0 * ld] = s.pos.x; b[1 * ld] = s.pos.y; b[2 * ld] = s.pos.z;
+    b[3 * ld] = s.qw; b[4 * ld] = s.qx; b[5 * ld] = s.qy; b[6 * ld] = s.qz;
+    b[7 * ld] = s.hx; b[8 * ld] = s.hy;
+    b[9 * ld] = s.vel.x; b[10 * ld] = s.vel.y; b[11 * ld] = s.vel.z;
+    b[12 * ld] = s.om.x; b[13 * ld] = s.om.y; b[14 * ld] = s.om.z;
+    b[15 * ld] = s.hvx; b[16 * ld] = s.hvy;
+    #pragma unroll
+    for (int k = 0; k < 4; k++) b[(S_ACT + k) * ld] = s.act[k];
+    b[21 * ld] = s.acc.x; b[22 * ld] = s.acc.y; b[23 * ld] = s.acc.z;
+}
+template <typename T> DSIM_DEV EnvConsts<T> load_consts(const KParams<T> &p, int i) {
+    EnvConsts<T> c;
+    T v[C_ROWS];
+    if (p.per_env_consts) {
+        #pragma unroll
+        for (int k = 0; k < C_ROWS; k++) v[k] = __ldg(p.consts + (size_t)k * p.ld + i);
+    } else {
+        #pragma unroll
+        for (int k = 0; k < C_ROWS; k++) v[k] = p.uconst[k];
+    }
+    c.mB = v[C_MB]; c.cz = v[C_CZ]; c.IBx = v[C_IBX]; c.IBy = v[C_IBY]; c.IBz = v[C_IBZ];
+    c.mD = v[C_MD]; c.zD = v[C_ZD]; c.IDx = v[C_IDX]; c.IDz = v[C_IDZ];
+    c.Fs = v[C_FS]; c.F = v[C_F]; c.kq = v[C_KQ]; c.inv_tau = v[C_INVTAU];
+    return c;
+}
+template <typename T> DSIM_DEV void load_params(const KParams<T> &p, int i, T prm[6]) {
+    if (p.per_env_consts) {
+        #pragma unroll
+        for (int k = 0; k < 6; k++) prm[k] = __ldg(p.params + (size_t)k * p.ld + i);
+    } else {
+        #pragma unroll
+        for (int k = 0; k < 6; k++) prm[k] = p.uparams[k];
+    }
+}
+template <typename T> DSIM_DEV void load_ref(const KParams<T> &p, int i, V3<T> &ref_off, T &ref_yaw, double ref64[3]) {
+    if (p.ref_env) {
+        const T *r = p.ref_env + i;
+        ref_off = mk(r[0], r[(size_t)p.ld], r[2 * (size_t)p.ld]);
+        ref_yaw = r[3 * (size_t)p.ld];
+        ref64[0] = p.start[0] + (double)ref_off.x; ref64[1] = p.start[1] + (double)ref_off.y; ref64[2] = p.start[2] + (double)ref_off.z;
+    } else {
+        ref_off = mk(p.ref_off[0], p.ref_off[1], p.ref_off[2]);
+        ref_yaw = p.ref_yaw;
+        ref64[0] = p.ref64[0]; ref64[1] = p.ref64[1]; ref64[2] = p.ref64[2];
+    }
+}
+template <typename T> DSIM_DEV bool state_finite(const EnvState<T> &s) {
+    const T a = s.pos.x + s.pos.y + s.pos.z + s.qw + s.qx + s.qy + s.qz + s.hx + s.hy;
+    const T b = s.vel.x + s.vel.y + s.vel.z + s.om.x + s.om.y + s.om.z + s.hvx + s.hvy + s.act[0] + s.act[1] + s.act[2] + s.act[3];
+    // MuJoCo's mj_check* also rejects |x| > mjMAXVAL (1e10)
+    return finite_(a) && finite_(b) && abs_(a) < T(1e10) && abs_(b) < T(1e10);
+}
+template <typename T> struct ObsWriter {
+    T *base; size_t stride;
+    DSIM_DEV void operator()(int j, T v) const { base[(size_t)j * stride] = v; }
+};
+template <typename T> DSIM_DEV ObsWriter<T> obs_writer(const KParams<T> &p, int i) {
+    ObsWriter<T> w;
+    if (p.obs_layout == DSIM_LAYOUT_SOA) { w.base = p.obs + i; w.stride = p.ld; }
+    else { w.base = p.obs + (size_t)i * p.obs_dim; w.stride = 1; }
+    return w;
+}
+
+// ------------------------------------------------------------------ THE fused env-step kernel
+// BaseDroneEnv.vector_step (:259-294): ctrl remap (:269) -> mj_step x frame_skip (mujoco_vecenv.py:404-407) ->
+// num_steps += 1 (:271) -> get_drone_states (:357-380) -> terminated_fcn / reward_fcn (:275-284) -> _get_obs.
+template <typename T, bool PEND>
+__global__ void __launch_bounds__(kBlock) step_kernel(const KParams<T> p) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= p.n) return;
+    EnvState<T> s = load_state(p, i);
+    const EnvConsts<T> c = load_consts(p, i);
+    T a[4], ctrl[4];
+    if constexpr (std::is_same<T, float>::value) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p.actions) + i);
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    } else {
+        const double2 v0 = __ldg(reinterpret_cast<const double2 *>(p.actions) + 2 * (size_t)i);
+        const double2 v1 = __ldg(reinterpret_cast<const double2 *>(p.actions) + 2 * (size_t)i + 1);
+        a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y;
+    }
+    #pragma unroll
+    for (int k = 0; k < 4; k++) ctrl[k] = clamp_(T(0.1) + T(0.9) * a[k], T(0), T(1));   // :269, ctrlrange (0,1) clamp of mj_fwdActuation
+    for (int f = 0; f < p.frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
+    int ns = p.num_steps[i] + (p.eval_only ? 0 : 1);
+
+    const unsigned env = p.env_base + (unsigned)i;
+    const bool bad = !state_finite(s);
+    if (bad) {   // MuJoCo: mj_checkPos/Vel/Acc warn and reset the data; here: per-env re-sample, counted, never silent
+        sample_state<T, PEND>(s, p.rc, p.seed, env, p.reset_count[i] + 1u);
+        #pragma unroll
+        for (int k = 0; k < 4; k++) s.act[k] = T(0);
+        s.acc = mk(T(0), T(0), T(0));
+        p.reset_count[i] += 1u;
+        atomicAdd(p.stats + 3, 1.0);
+    }
+
+    V3<T> ref_off; T ref_yaw; double ref64[3];
+    load_ref(p, i, ref_off, ref_yaw, ref64);
+    T prm[6];
+    load_params(p, i, prm);
+    const PostState<T> ps = post_state(s, ref_off, ref_yaw);
+    bool trunc = terminated(s.pos, p.start, ref64, p.max_distance, ns, p.max_steps);
+    const T rew = bad ? T(0) : reward_fn<T, PEND>(p.reward_id, s, ps, a, ns, prm, p.max_distance_t);
+    trunc = trunc || bad;
+    emit_obs<T, PEND>(p.obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, obs_writer(p, i));
+    p.reward[i] = rew;
+    p.trunc[i] = trunc ? 1 : 0;
+    if (p.eval_only) return;
+
+    // would-be ground contact (the floor plane is out of reach in the BASELINE configs; detected, never ignored)
+    if (p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(p.stats + 4, 1.0);
+
+    T ret = p.ep_return[i] + rew;
+    if (trunc) {
+        atomicAdd(p.stats + 0, (double)ret); atomicAdd(p.stats + 1, (double)ns); atomicAdd(p.stats + 2, 1.0);
+        ret = T(0);
+        if (p.auto_reset && !bad) {   // native loop: the RLlib reset_at() round trip (:334-351) folded into the step
+            const unsigned rcnt = p.reset_count[i] + 1u;
+            sample_state<T, PEND>(s, p.rc, p.seed, env, rcnt);
+            p.reset_count[i] = rcnt;
+        }
+        if (p.auto_reset || bad) ns = 0;
+    }
+    p.ep_return[i] = ret;
+    p.num_steps[i] = ns;
+    store_state(p, i, s);
+}
+
+// mj_forward after set_state (mujoco_vecenv.py:396-402): refresh sensordata (+ obs) from the current state
+template <typename T, bool PEND>
+__global__ void __launch_bounds__(kBlock) forward_kernel(const KParams<T> p, int refresh_obs) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= p.n) return;
+    EnvState<T> s = load_state(p, i);
+    const EnvConsts<T> c = load_consts(p, i);
+    const T ctrl[4] = {T(0), T(0), T(0), T(0)};
+    substep<T, PEND, false>(s, c, ctrl, p.h);
+    T *b = p.state + i;
+    b[21 * (size_t)p.ld] = s.acc.x; b[22 * (size_t)p.ld] = s.acc.y; b[23 * (size_t)p.ld] = s.acc.z;
+    if (refresh_obs) {
+        V3<T> ref_off; T ref_yaw; double ref64[3];
+        load_ref(p, i, ref_off, ref_yaw, ref64);
+        T prm[6];
+        load_params(p, i, prm);
+        const PostState<T> ps = post_state(s, ref_off, ref_yaw);
+        emit_obs<T, PEND>(p.obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, obs_writer(p, i));
+    }
+}
+
+// reset_model / reset_at: sample_state into qpos/qvel, num_steps = 0; act, ctrl persist (Q3)
+template <typename T, bool PEND>
+__global__ void __launch_bounds__(kBlock) reset_kernel(const KParams<T> p, const unsigned char *mask, int single, int first) {
+    int i = blockIdx.x * kBlock + threadIdx.x;
+    if (single >= 0) { if (i != 0) return; i = single; }
+    if (i >= p.n) return;
+    if (mask && !mask[i]) return;
+    EnvState<T> s = load_state(p, i);
+    const unsigned rcnt = first ? 0u : p.reset_count[i] + 1u;
+    sample_state<T, PEND>(s, p.rc, p.seed, p.env_base + (unsigned)i, rcnt);
+    p.reset_count[i] = rcnt;
+    p.num_steps[i] = 0;
+    p.ep_return[i] = T(0);
+    store_state(p, i, s);
+}
+
+// get_drone_states (:357-380) for every env -> [n][33|29]
+template <typename T, bool PEND>
+__global__ void __launch_bounds__(kBlock) states_kernel(const KParams<T> p, T *out, int width) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= p.n) return;
+    const EnvState<T> s = load_state(p, i);
+    V3<T> ref_off; T ref_yaw; double ref64[3];
+    load_ref(p, i, ref_off, ref_yaw, ref64);
+    T prm[6];
+    load_params(p, i, prm);
+    const PostState<T> ps = post_state(s, ref_off, ref_yaw);
+    ObsWriter<T> w; w.base = out + (size_t)i * width; w.stride = 1;
+    emit_state_row<T, PEND>(s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
+}
+
+// generate_drone_params (:180-216) on device: Philox stream 1 keyed by (seed, global env, epoch)
+__global__ void draw_params_kernel(int n, int ld, double *params64, unsigned seed, unsigned env_base, unsigned epoch,
+                                   int random_params, int pendulum, double difficulty, const double *center_hw /*12*/) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v[6];
+    for (int k = 0; k < 6; k++) v[k] = center_hw[k];
+    if (random_params) {
+        const U4 x0 = philox4x32(0, epoch, 1, 0, seed, env_base + i), x1 = philox4x32(1, epoch, 1, 0, seed, env_base + i);
+        const uint32_t u[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+        for (int k = 0; k < 6; k++) { const double w = center_hw[6 + k]; v[k] = center_hw[k] + (-w + 2 * w * u01<double>(u[k])) * difficulty; }
+    }
+    if (!pendulum) { v[4] = 0; v[5] = 0; }                      // self.pendulum * pendulum_lens[i] (:212-213)
+    for (int k = 0; k < 6; k++) params64[(size_t)k * ld + i] = v[k];
+}
+// env_gen + MuJoCo compile on device
+template <typename T>
+__global__ void compile_kernel(int n, int ld, const double *params64, T *params, T *consts, int pendulum, int rounding) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[6], c[C_ROWS];
+    for (int k = 0; k < 6; k++) p[k] = params64[(size_t)k * ld + i];
+    compile_consts(p, pendulum != 0, rounding != 0, c);
+    for (int k = 0; k < 6; k++) params[(size_t)k * ld + i] = (T)p[k];
+    for (int k = 0; k < C_ROWS; k++) consts[(size_t)k * ld + i] = (T)c[k];
+}
+// control_reference (:151-172) per env: axes are the already sign-flipped joystick values (x, -y, -z, -yaw)
+template <typename T>
+__global__ void control_reference_kernel(int n, int ld, const T *axes, T *ref) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T pert[4], r[4];
+    for (int k = 0; k < 4; k++) { pert[k] = axes[(size_t)k * ld + i]; r[k] = ref[(size_t)k * ld + i]; }
+    const bool xy = sqrt_(pert[0] * pert[0] + pert[1] * pert[1]) > T(0.2), zy = sqrt_(pert[2] * pert[2] + pert[3] * pert[3]) > T(0.2);
+    const T lim[3] = {T(5), T(5), T(6)};
+    for (int k = 0; k < 4; k++) {
+        const T mag = max_(abs_(pert[k]) - T(0.1), T(0));
+        const T sg = pert[k] > T(0) ? T(1) : (pert[k] < T(0) ? T(-1) : T(0));
+        const bool active = k < 2 ? xy : zy;
+        r[k] += active ? T(0.1) * mag * sg : T(0);
+    }
+    r[3] = wrap_pi(r[3]);
+    for (int k = 0; k < 3; k++) r[k] = clamp_(r[k], -lim[k], lim[k]);      // clip to start_pos +- (5,5,6); ref rows are offsets
+    for (int k = 0; k < 4; k++) ref[(size_t)k * ld + i] = r[k];
+}
+template <typename T> __global__ void fill_rows_kernel(int n, int ld, T *dst, int row0, int nrows, T value) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < nrows; k++) dst[(size_t)(row0 + k) * ld + i] = value;
+}
+
+}  // namespace
+
+// ====================================================================== host side
+struct DsimHandle {
+    DsimConfig cfg;
+    int device, n, ld, obs_dim, state_width;
+    size_t rs;                        // sizeof(real)
+    void *state, *obs, *reward, *ep_return, *params, *consts, *ref_env, *states33, *actions_stage;
+    double *params64, *stats, *center_hw;
+    int *num_steps;
+    unsigned *reset_count;
+    unsigned char *trunc;
+    int per_env_consts;
+    double uconst[C_ROWS], uparams[6];
+    double h;
+    int first_reset_done;
+    int64_t launches;
+    char err[512];
+};
+
+static char g_create_err[512] = "";
+
+static int fail(DsimHandle *h, int code, const char *fmt, const char *detail) {
+    char *dst = h ? h->err : g_create_err;
+    snprintf(dst, 512, fmt, detail ? detail : "");
+    return code;
+}
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) return fail(h, DSIM_ECUDA, "CUDA error: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+static const int kObsDimPend[DSIM_NUM_OBS] = {33, 16, 16, 23, 24, 19, 22, 25, 22, 22, 16, 15, 21, 28, 17};
+
+extern "C" int dsim_abi_version(void) { return DSIM_ABI_VERSION; }
+
+extern "C" int dsim_obs_dim(int obs_id, int pendulum) {
+    if (obs_id < 0 || obs_id >= DSIM_NUM_OBS) return DSIM_EINVAL;
+    if (obs_id == 0) return pendulum ? 33 : 29;
+    return kObsDimPend[obs_id];
+}
+
+extern "C" const char *dsim_last_error(const DsimHandle *h) { return h ? h->err : g_create_err; }
+
+template <typename T> static KParams<T> make_params(const DsimHandle *h, const void *actions) {
+    KParams<T> p;
+    memset(&p, 0, sizeof p);
+    const DsimConfig &c = h->cfg;
+    p.n = h->n; p.ld = h->ld;
+    p.state = (T *)h->state; p.num_steps = h->num_steps; p.reset_count = h->reset_count;
+    p.consts = (const T *)h->consts; p.params = (const T *)h->params;
+    p.ref_env = c.per_env_reference ? (T *)h->ref_env : nullptr;
+    p.obs = (T *)h->obs; p.reward = (T *)h->reward; p.ep_return = (T *)h->ep_return;
+    p.trunc = h->trunc; p.stats = h->stats; p.actions = (const T *)actions;
+    for (int k = 0; k < C_ROWS; k++) p.uconst[k] = (T)h->uconst[k];
+    for (int k = 0; k < 6; k++) p.uparams[k] = (T)h->uparams[k];
+    p.per_env_consts = h->per_env_consts; p.auto_reset = c.auto_reset; p.obs_id = c.obs_id; p.reward_id = c.reward_id;
+    p.obs_layout = c.obs_layout; p.obs_dim = h->obs_dim; p.frame_skip = c.frame_skip;
+    p.max_steps = (int)(c.max_steps > 2147483647LL ? 2147483647LL : c.max_steps);
+    p.h = (T)h->h; p.max_distance_t = (T)c.max_distance; p.max_distance = c.max_distance;
+    for (int k = 0; k < 3; k++) {
+        p.ref_off[k] = (T)(c.reference[k] - c.start_pos[k]);
+        p.start_t[k] = (T)c.start_pos[k]; p.start[k] = c.start_pos[k]; p.ref64[k] = c.reference[k];
+    }
+    p.ref_yaw = (T)c.reference[3];
+    p.rc.start_yaw = (T)c.start_pos[3]; p.rc.max_pos_offset = (T)c.max_pos_offset;
+    for (int k = 0; k < 2; k++) { p.rc.angle_sigma[k] = (T)c.angle_sigma[k]; p.rc.pend_rp_sigma[k] = (T)c.pend_rp_sigma[k]; p.rc.pend_vel_sigma[k] = (T)c.pend_vel_sigma[k]; }
+    for (int k = 0; k < 3; k++) { p.rc.vel_sigma[k] = (T)c.vel_sigma[k]; p.rc.ang_vel_sigma[k] = (T)c.ang_vel_sigma[k]; }
+    p.rc.random_start_pos = c.random_start_pos;
+    p.seed = c.seed; p.env_base = (unsigned)c.env_id_offset;
+    return p;
+}
+
+#define DISPATCH(h, KERNEL, stream, ...)                                                                  \
+    do {                                                                                                  \
+        const int grid_ = ((h)->n + kBlock - 1) / kBlock;                                                 \
+        cudaStream_t st_ = (cudaStream_t)(stream);                                                        \
+        if ((h)->cfg.precision == DSIM_FP32) {                                                            \
+            auto kp = make_params<float>((h), actions_);                                                  \
+            if ((h)->cfg.pendulum) KERNEL<float, true><<<grid_, kBlock, 0, st_>>>(kp, ##__VA_ARGS__);     \
+            else KERNEL<float, false><<<grid_, kBlock, 0, st_>>>(kp, ##__VA_ARGS__);                      \
+        } else {                                                                                          \
+            auto kp = make_params<double>((h), actions_);                                                 \
+            if ((h)->cfg.pendulum) KERNEL<double, true><<<grid_, kBlock, 0, st_>>>(kp, ##__VA_ARGS__);    \
+            else KERNEL<double, false><<<grid_, kBlock, 0, st_>>>(kp, ##__VA_ARGS__);                     \
+        }                                                                                                 \
+        (h)->launches++;                                                                                  \
+        CK(cudaGetLastError());                                                                           \
+    } while (0)
+
+static int validate(const DsimConfig *c) {
+    if (!c || c->struct_size != (int)sizeof(DsimConfig)) return fail(nullptr, DSIM_EINVAL, "DsimConfig.struct_size mismatch%s", "");
+    if (c->abi_version != DSIM_ABI_VERSION) return fail(nullptr, DSIM_EINVAL, "ABI version mismatch%s", "");
+    if (c->num_envs <= 0) return fail(nullptr, DSIM_EINVAL, "num_envs must be positive%s", "");
+    if (c->precision != DSIM_FP32 && c->precision != DSIM_FP64) return fail(nullptr, DSIM_EINVAL, "precision must be DSIM_FP32 or DSIM_FP64%s", "");
+    if (c->obs_id < 0 || c->obs_id >= DSIM_NUM_OBS) return fail(nullptr, DSIM_EINVAL, "unknown obs_id%s", "");
+    if (c->obs_id == DSIM_OBS_LOCAL_PRY_ACC_PARAMS_NOPEND)
+        return fail(nullptr, DSIM_EUNSUPPORTED, "LocalFramePRYaccParamsNoPendEnv raises NameError in the reference (observation_wrappers.py:448)%s", "");
+    if (c->reward_id < 0 || c->reward_id >= DSIM_NUM_REWARDS) return fail(nullptr, DSIM_EINVAL, "unknown reward_id%s", "");
+    if (!c->pendulum) {
+        if (!(c->obs_id == 0 || c->obs_id == DSIM_OBS_LOCAL_PRY_ACC_NOPEND))
+            return fail(nullptr, DSIM_EUNSUPPORTED, "pendulum=False supports only BaseDroneEnv and LocalFramePRYaccNoPendEnv observations%s", "");
+        if (!(c->reward_id <= 2 || c->reward_id == 10))
+            return fail(nullptr, DSIM_EUNSUPPORTED, "pendulum=False supports only rewards that do not index pendulum state%s", "");
+    }
+    if (c->frame_skip < 1 || c->frequency <= 0) return fail(nullptr, DSIM_EINVAL, "frame_skip >= 1 and frequency > 0 required%s", "");
+    if (c->obs_layout != DSIM_LAYOUT_ENV_MAJOR && c->obs_layout != DSIM_LAYOUT_SOA) return fail(nullptr, DSIM_EINVAL, "bad obs_layout%s", "");
+    return DSIM_OK;
+}
+
+extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) {
+    if (!out) return fail(nullptr, DSIM_EINVAL, "out is NULL%s", "");
+    *out = nullptr;
+    int rc = validate(cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, DSIM_ECUDA, "no CUDA device available (%s): libdronesim_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, DSIM_EINVAL, "bad device ordinal%s", "");
+    DsimHandle *h = new (std::nothrow) DsimHandle();
+    if (!h) return fail(nullptr, DSIM_ENOMEM, "out of host memory%s", "");
+    memset(h, 0, sizeof *h);
+    h->cfg = *cfg; h->device = device; h->n = cfg->num_envs; h->ld = (cfg->num_envs + 31) / 32 * 32;
+    h->rs = cfg->precision == DSIM_FP32 ? 4 : 8;
+    h->obs_dim = dsim_obs_dim(cfg->obs_id, cfg->pendulum);
+    h->state_width = cfg->pendulum ? 33 : 29;
+    h->h = cfg->round_precision ? round_prec5(1.0 / cfg->frequency) : 1.0 / cfg->frequency;
+#define ALLOC(ptr, bytes)                                                                                  \
+    do {                                                                                                   \
+        cudaError_t e2 = cudaMalloc((void **)&(ptr), (bytes));                                             \
+        if (e2 == cudaSuccess) e2 = cudaMemset((ptr), 0, (bytes));                                         \
+        if (e2 != cudaSuccess) { fail(nullptr, e2 == cudaErrorMemoryAllocation ? DSIM_ENOMEM : DSIM_ECUDA, "allocation failed: %s", cudaGetErrorString(e2)); dsim_destroy(h); return e2 == cudaErrorMemoryAllocation ? DSIM_ENOMEM : DSIM_ECUDA; } \
+    } while (0)
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { delete h; return fail(nullptr, DSIM_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); }
+    const size_t ld = h->ld, n = h->n, rs = h->rs;
+    ALLOC(h->state, DSIM_NSTATE_ROWS * ld * rs);
+    ALLOC(h->obs, (size_t)DSIM_MAX_OBS * ld * rs);
+    ALLOC(h->reward, ld * rs);
+    ALLOC(h->ep_return, ld * rs);
+    ALLOC(h->params, 6 * ld * rs);
+    ALLOC(h->consts, C_ROWS * ld * rs);
+    ALLOC(h->ref_env, 4 * ld * rs);
+    ALLOC(h->states33, (size_t)h->state_width * n * rs);
+    ALLOC(h->actions_stage, 4 * ld * rs);
+    ALLOC(h->params64, 6 * ld * sizeof(double));
+    ALLOC(h->stats, 8 * sizeof(double));
+    ALLOC(h->center_hw, 12 * sizeof(double));
+    ALLOC(h->num_steps, ld * sizeof(int));
+    ALLOC(h->reset_count, ld * sizeof(unsigned));
+    ALLOC(h->trunc, ld);
+#undef ALLOC
+    double chw[12];
+    for (int k = 0; k < 6; k++) { chw[k] = cfg->param_center[k]; chw[6 + k] = cfg->param_halfwidth[k]; }
+    CK(cudaMemcpy(h->center_hw, chw, sizeof chw, cudaMemcpyHostToDevice));
+    // quaternion rows start as identity (MjData qpos0 of a free joint), per-env reference = shared reference
+    {
+        const int grid = (h->n + 255) / 256;
+        if (h->rs == 4) {
+            fill_rows_kernel<float><<<grid, 256>>>(h->n, h->ld, (float *)h->state, S_QUAT, 1, 1.0f);
+            for (int k = 0; k < 4; k++)
+                fill_rows_kernel<float><<<grid, 256>>>(h->n, h->ld, (float *)h->ref_env, k, 1, (float)(k < 3 ? cfg->reference[k] - cfg->start_pos[k] : cfg->reference[3]));
+        } else {
+            fill_rows_kernel<double><<<grid, 256>>>(h->n, h->ld, (double *)h->state, S_QUAT, 1, 1.0);
+            for (int k = 0; k < 4; k++)
+                fill_rows_kernel<double><<<grid, 256>>>(h->n, h->ld, (double *)h->ref_env, k, 1, k < 3 ? cfg->reference[k] - cfg->start_pos[k] : cfg->reference[3]);
+        }
+        h->launches += 5;
+        CK(cudaGetLastError());
+    }
+    rc = dsim_regen_params(h, 0, nullptr);
+    if (rc) { snprintf(g_create_err, 512, "%s", h->err); dsim_destroy(h); return rc; }
+    CK(cudaDeviceSynchronize());
+    *out = h;
+    return DSIM_OK;
+}
+
+extern "C" void dsim_destroy(DsimHandle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->state, h->obs, h->reward, h->ep_return, h->params, h->consts, h->ref_env, h->states33, h->actions_stage,
+                    h->params64, h->stats, h->center_hw, h->num_steps, h->reset_count, h->trunc};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete h;
+}
+
+static int compile_on_device(DsimHandle *h, cudaStream_t st) {
+    const int grid = (h->n + 127) / 128;
+    if (h->rs == 4) compile_kernel<float><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (float *)h->params, (float *)h->consts, h->cfg.pendulum, h->cfg.round_precision);
+    else compile_kernel<double><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (double *)h->params, (double *)h->consts, h->cfg.pendulum, h->cfg.round_precision);
+    h->launches++;
+    CK(cudaGetLastError());
+    return DSIM_OK;
+}
+
+extern "C" int dsim_regen_params(DsimHandle *h, uint32_t epoch, void *stream) {
+    if (!h) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DsimConfig &c = h->cfg;
+    draw_params_kernel<<<(h->n + 127) / 128, 128, 0, st>>>(h->n, h->ld, h->params64, c.seed, (unsigned)c.env_id_offset, epoch,
+                                                          c.random_params, c.pendulum, c.param_difficulty, h->center_hw);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->per_env_consts = c.random_params ? 1 : 0;
+    if (!c.random_params) {
+        for (int k = 0; k < 6; k++) h->uparams[k] = c.param_center[k];
+        if (!c.pendulum) { h->uparams[4] = 0; h->uparams[5] = 0; }
+        compile_consts(h->uparams, c.pendulum != 0, c.round_precision != 0, h->uconst);
+    }
+    return compile_on_device(h, st);
+}
+
+extern "C" int dsim_set_params(DsimHandle *h, const double *params_host, void *stream) {
+    if (!h || !params_host) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    std::vector<double> t((size_t)6 * h->ld, 0.0);
+    bool uniform = true;
+    for (int i = 0; i < h->n; i++)
+        for (int k = 0; k < 6; k++) {
+            t[(size_t)k * h->ld + i] = params_host[(size_t)i * 6 + k];
+            if (params_host[(size_t)i * 6 + k] != params_host[k]) uniform = false;
+        }
+    CK(cudaMemcpyAsync(h->params64, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    h->per_env_consts = uniform ? 0 : 1;
+    if (uniform) {
+        for (int k = 0; k < 6; k++) h->uparams[k] = params_host[k];
+        compile_consts(h->uparams, h->cfg.pendulum != 0, h->cfg.round_precision != 0, h->uconst);
+    }
+    return compile_on_device(h, (cudaStream_t)stream);
+}
+
+extern "C" int dsim_get_params(DsimHandle *h, double *out) {
+    if (!h || !out) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    std::vector<double> t((size_t)6 * h->ld);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(t.data(), h->params64, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < h->n; i++) for (int k = 0; k < 6; k++) out[(size_t)i * 6 + k] = t[(size_t)k * h->ld + i];
+    return DSIM_OK;
+}
+
+extern "C" int dsim_get_consts(DsimHandle *h, double *out) {
+    if (!h || !out) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    const size_t cnt = (size_t)C_ROWS * h->ld;
+    if (h->rs == 4) {
+        std::vector<float> t(cnt);
+        CK(cudaMemcpy(t.data(), h->consts, cnt * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < h->n; i++) for (int k = 0; k < C_ROWS; k++) out[(size_t)i * C_ROWS + k] = t[(size_t)k * h->ld + i];
+    } else {
+        std::vector<double> t(cnt);
+        CK(cudaMemcpy(t.data(), h->consts, cnt * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < h->n; i++) for (int k = 0; k < C_ROWS; k++) out[(size_t)i * C_ROWS + k] = t[(size_t)k * h->ld + i];
+    }
+    return DSIM_OK;
+}
+
+extern "C" int dsim_forward(DsimHandle *h, int refresh_obs, void *stream) {
+    if (!h) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const void *actions_ = nullptr;
+    DISPATCH(h, forward_kernel, stream, refresh_obs);
+    return DSIM_OK;
+}
+
+static int reset_impl(DsimHandle *h, const uint8_t *mask, int single, void *stream) {
+    CK(cudaSetDevice(h->device));
+    const void *actions_ = nullptr;
+    const int first = (!h->first_reset_done && !mask && single < 0) ? 1 : 0;
+    DISPATCH(h, reset_kernel, stream, mask, single, first);
+    return DSIM_OK;
+}
+extern "C" int dsim_reset_all(DsimHandle *h, void *stream) {
+    if (!h) return DSIM_EINVAL;
+    int rc = reset_impl(h, nullptr, -1, stream);
+    if (rc) return rc;
+    h->first_reset_done = 1;
+    return dsim_forward(h, 1, stream);                 // reset_model: set_state -> mj_forward, then states/_get_obs (:324-326)
+}
+extern "C" int dsim_reset_masked(DsimHandle *h, const uint8_t *mask_dev, void *stream) {
+    if (!h || !mask_dev) return DSIM_EINVAL;
+    return reset_impl(h, mask_dev, -1, stream);
+}
+extern "C" int dsim_reset_at(DsimHandle *h, int index, void *stream) {
+    if (!h) return DSIM_EINVAL;
+    if (index < 0 || index >= h->n) return fail(h, DSIM_EINVAL, "reset_at: index out of range%s", "");   // assert index < num_drones (:338)
+    return reset_impl(h, nullptr, index, stream);
+}
+extern "C" int dsim_zero_act(DsimHandle *h, void *stream) {
+    if (!h) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync((char *)h->state + (size_t)S_ACT * h->ld * h->rs, 0, (size_t)7 * h->ld * h->rs, (cudaStream_t)stream));   // act + sensordata
+    return DSIM_OK;
+}
+
+extern "C" int dsim_step(DsimHandle *h, const void *actions_dev, void *stream) {
+    if (!h || !actions_dev) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const void *actions_ = actions_dev;
+    DISPATCH(h, step_kernel, stream);
+    return DSIM_OK;
+}
+
+extern "C" int dsim_evaluate(DsimHandle *h, const void *actions_dev, void *stream) {
+    if (!h || !actions_dev) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const void *actions_ = actions_dev;
+    const int fs = h->cfg.frame_skip;
+    int rc = DSIM_OK;
+    {
+        const int grid = (h->n + kBlock - 1) / kBlock;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (h->cfg.precision == DSIM_FP32) {
+            auto kp = make_params<float>(h, actions_); kp.frame_skip = 0; kp.eval_only = 1;
+            if (h->cfg.pendulum) step_kernel<float, true><<<grid, kBlock, 0, st>>>(kp); else step_kernel<float, false><<<grid, kBlock, 0, st>>>(kp);
+        } else {
+            auto kp = make_params<double>(h, actions_); kp.frame_skip = 0; kp.eval_only = 1;
+            if (h->cfg.pendulum) step_kernel<double, true><<<grid, kBlock, 0, st>>>(kp); else step_kernel<double, false><<<grid, kBlock, 0, st>>>(kp);
+        }
+        h->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(h, DSIM_ECUDA, "CUDA error in dsim_evaluate%s", "");
+    }
+    h->cfg.frame_skip = fs;
+    return rc;
+}
+
+extern "C" int dsim_step_host(DsimHandle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *trunc_host, void *stream) {
+    if (!h || !actions_host) return DSIM_EINVAL;
+    if (h->cfg.precision != DSIM_FP32) return fail(h, DSIM_EUNSUPPORTED, "dsim_step_host moves float32 buffers; use dsim_step with precision=FP64%s", "");
+    if (h->cfg.obs_layout != DSIM_LAYOUT_ENV_MAJOR && obs_host) return fail(h, DSIM_EUNSUPPORTED, "dsim_step_host needs DSIM_LAYOUT_ENV_MAJOR%s", "");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h->actions_stage, actions_host, (size_t)h->n * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = dsim_step(h, h->actions_stage, stream);
+    if (rc) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, h->obs, (size_t)h->n * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (reward_host) CK(cudaMemcpyAsync(reward_host, h->reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (trunc_host) CK(cudaMemcpyAsync(trunc_host, h->trunc, (size_t)h->n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DSIM_OK;
+}
+
+extern "C" int dsim_set_reference(DsimHandle *h, const double ref[4]) {
+    if (!h || !ref) return DSIM_EINVAL;
+    for (int k = 0; k < 4; k++) h->cfg.reference[k] = ref[k];
+    return DSIM_OK;
+}
+
+extern "C" int dsim_control_reference(DsimHandle *h, const void *axes_dev, void *stream) {
+    if (!h || !axes_dev) return DSIM_EINVAL;
+    if (!h->cfg.per_env_reference) return fail(h, DSIM_EUNSUPPORTED, "dsim_control_reference needs per_env_reference=1%s", "");
+    CK(cudaSetDevice(h->device));
+    const int grid = (h->n + 127) / 128;
+    if (h->rs == 4) control_reference_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(h->n, h->ld, (const float *)axes_dev, (float *)h->ref_env);
+    else control_reference_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(h->n, h->ld, (const double *)axes_dev, (double *)h->ref_env);
+    h->launches++;
+    CK(cudaGetLastError());
+    return DSIM_OK;
+}
+
+template <typename T>
+static void pack_state(const DsimHandle *h, std::vector<T> &t, const double *qpos, const double *qvel, const double *act) {
+    const int nq = h->cfg.pendulum ? 9 : 7, nv = h->cfg.pendulum ? 8 : 6;
+    const size_t ld = h->ld;
+    for (int i = 0; i < h->n; i++) {
+        if (qpos) {
+            const double *q = qpos + (size_t)i * nq;
+            for (int k = 0; k < 3; k++) t[(size_t)k * ld + i] = (T)(q[k] - h->cfg.start_pos[k]);
+            for (int k = 0; k < 4; k++) t[(size_t)(S_QUAT + k) * ld + i] = (T)q[3 + k];
+            if (nq == 9) { t[(size_t)S_HINGE * ld + i] = (T)q[7]; t[(size_t)(S_HINGE + 1) * ld + i] = (T)q[8]; }
+        }
+        if (qvel) {
+            const double *v = qvel + (size_t)i * nv;
+            for (int k = 0; k < 6; k++) t[(size_t)(S_VEL + k) * ld + i] = (T)v[k];
+            if (nv == 8) { t[(size_t)S_HVEL * ld + i] = (T)v[6]; t[(size_t)(S_HVEL + 1) * ld + i] = (T)v[7]; }
+        }
+        if (act) for (int k = 0; k < 4; k++) t[(size_t)(S_ACT + k) * ld + i] = (T)act[(size_t)i * 4 + k];
+    }
+}
+template <typename T>
+static void unpack_state(const DsimHandle *h, const std::vector<T> &t, double *qpos, double *qvel, double *act, double *sens) {
+    const int nq = h->cfg.pendulum ? 9 : 7, nv = h->cfg.pendulum ? 8 : 6;
+    const size_t ld = h->ld;
+    for (int i = 0; i < h->n; i++) {
+        if (qpos) {
+            double *q = qpos + (size_t)i * nq;
+            for (int k = 0; k < 3; k++) q[k] = h->cfg.start_pos[k] + (double)t[(size_t)k * ld + i];
+            for (int k = 0; k < 4; k++) q[3 + k] = (double)t[(size_t)(S_QUAT + k) * ld + i];
+            if (nq == 9) { q[7] = (double)t[(size_t)S_HINGE * ld + i]; q[8] = (double)t[(size_t)(S_HINGE + 1) * ld + i]; }
+        }
+        if (qvel) {
+            double *v = qvel + (size_t)i * nv;
+            for (int k = 0; k < 6; k++) v[k] = (double)t[(size_t)(S_VEL + k) * ld + i];
+            if (nv == 8) { v[6] = (double)t[(size_t)S_HVEL * ld + i]; v[7] = (double)t[(size_t)(S_HVEL + 1) * ld + i]; }
+        }
+        if (act) for (int k = 0; k < 4; k++) act[(size_t)i * 4 + k] = (double)t[(size_t)(S_ACT + k) * ld + i];
+        if (sens) for (int k = 0; k < 3; k++) sens[(size_t)i * 3 + k] = (double)t[(size_t)(S_ACC + k) * ld + i];
+    }
+}
+
+extern "C" int dsim_set_state(DsimHandle *h, const double *qpos, const double *qvel, const double *act, const int32_t *num_steps, void *stream) {
+    if (!h) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaStreamSynchronize(st));
+    const size_t cnt = (size_t)DSIM_NSTATE_ROWS * h->ld;
+    if (h->rs == 4) {
+        std::vector<float> t(cnt);
+        CK(cudaMemcpy(t.data(), h->state, cnt * 4, cudaMemcpyDeviceToHost));
+        pack_state(h, t, qpos, qvel, act);
+        CK(cudaMemcpy(h->state, t.data(), cnt * 4, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<double> t(cnt);
+        CK(cudaMemcpy(t.data(), h->state, cnt * 8, cudaMemcpyDeviceToHost));
+        pack_state(h, t, qpos, qvel, act);
+        CK(cudaMemcpy(h->state, t.data(), cnt * 8, cudaMemcpyHostToDevice));
+    }
+    if (num_steps) CK(cudaMemcpy(h->num_steps, num_steps, (size_t)h->n * sizeof(int), cudaMemcpyHostToDevice));
+    return DSIM_OK;
+}
+
+extern "C" int dsim_get_state(DsimHandle *h, double *qpos, double *qvel, double *act, double *sens, int32_t *num_steps) {
+    if (!h) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    const size_t cnt = (size_t)DSIM_NSTATE_ROWS * h->ld;
+    if (h->rs == 4) {
+        std::vector<float> t(cnt);
+        CK(cudaMemcpy(t.data(), h->state, cnt * 4, cudaMemcpyDeviceToHost));
+        unpack_state(h, t, qpos, qvel, act, sens);
+    } else {
+        std::vector<double> t(cnt);
+        CK(cudaMemcpy(t.data(), h->state, cnt * 8, cudaMemcpyDeviceToHost));
+        unpack_state(h, t, qpos, qvel, act, sens);
+    }
+    if (num_steps) CK(cudaMemcpy(num_steps, h->num_steps, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToHost));
+    return DSIM_OK;
+}
+
+extern "C" int dsim_compute_states(DsimHandle *h, void *stream) {
+    if (!h) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const int grid = (h->n + kBlock - 1) / kBlock;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->rs == 4) {
+        auto kp = make_params<float>(h, nullptr);
+        if (h->cfg.pendulum) states_kernel<float, true><<<grid, kBlock, 0, st>>>(kp, (float *)h->states33, h->state_width);
+        else states_kernel<float, false><<<grid, kBlock, 0, st>>>(kp, (float *)h->states33, h->state_width);
+    } else {
+        auto kp = make_params<double>(h, nullptr);
+        if (h->cfg.pendulum) states_kernel<double, true><<<grid, kBlock, 0, st>>>(kp, (double *)h->states33, h->state_width);
+        else states_kernel<double, false><<<grid, kBlock, 0, st>>>(kp, (double *)h->states33, h->state_width);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return DSIM_OK;
+}
+
+extern "C" int dsim_buffer(DsimHandle *h, int id, void **ptr, int64_t *rows, int64_t *cols, int64_t *ld, int32_t *dtype) {
+    if (!h || !ptr || !rows || !cols || !ld || !dtype) return DSIM_EINVAL;
+    const int32_t rdt = h->rs == 4 ? DSIM_DT_F32 : DSIM_DT_F64;
+    const int64_t n = h->n, L = h->ld;
+    switch (id) {
+    case DSIM_BUF_STATE: *ptr = h->state; *rows = DSIM_NSTATE_ROWS; *cols = n; *ld = L; *dtype = rdt; break;
+    case DSIM_BUF_NUM_STEPS: *ptr = h->num_steps; *rows = 1; *cols = n; *ld = L; *dtype = DSIM_DT_I32; break;
+    case DSIM_BUF_OBS:
+        *ptr = h->obs; *dtype = rdt;
+        if (h->cfg.obs_layout == DSIM_LAYOUT_SOA) { *rows = h->obs_dim; *cols = n; *ld = L; }
+        else { *rows = n; *cols = h->obs_dim; *ld = h->obs_dim; }
+        break;
+    case DSIM_BUF_REWARD: *ptr = h->reward; *rows = 1; *cols = n; *ld = L; *dtype = rdt; break;
+    case DSIM_BUF_TRUNCATED: *ptr = h->trunc; *rows = 1; *cols = n; *ld = L; *dtype = DSIM_DT_U8; break;
+    case DSIM_BUF_PARAMS: *ptr = h->params; *rows = 6; *cols = n; *ld = L; *dtype = rdt; break;
+    case DSIM_BUF_CONSTS: *ptr = h->consts; *rows = C_ROWS; *cols = n; *ld = L; *dtype = rdt; break;
+    case DSIM_BUF_REFERENCE: *ptr = h->ref_env; *rows = 4; *cols = n; *ld = L; *dtype = rdt; break;
+    case DSIM_BUF_RESET_COUNT: *ptr = h->reset_count; *rows = 1; *cols = n; *ld = L; *dtype = DSIM_DT_U32; break;
+    case DSIM_BUF_STATES33: *ptr = h->states33; *rows = n; *cols = h->state_width; *ld = h->state_width; *dtype = rdt; break;
+    case DSIM_BUF_EP_RETURN: *ptr = h->ep_return; *rows = 1; *cols = n; *ld = L; *dtype = rdt; break;
+    case DSIM_BUF_STATS: *ptr = h->stats; *rows = 1; *cols = 8; *ld = 8; *dtype = DSIM_DT_F64; break;
+    default: return fail(h, DSIM_EINVAL, "unknown buffer id%s", "");
+    }
+    return DSIM_OK;
+}
+
+extern "C" int dsim_stats(DsimHandle *h, double out[8], int reset) {
+    if (!h || !out) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, h->stats, 8 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(h->stats, 0, 8 * sizeof(double)));
+    return DSIM_OK;
+}
+
+extern "C" int dsim_sync(DsimHandle *h, void *stream) {
+    if (!h) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return DSIM_OK;
+}
+
+extern "C" int64_t dsim_launch_count(const DsimHandle *h) { return h ? h->launches : 0; }
+
+extern "C" int dsim_kernel_info(int which, int32_t *regs, int32_t *local_bytes, int32_t *max_threads) {
+    cudaFuncAttributes a;
+    cudaError_t e = which == 0 ? cudaFuncGetAttributes(&a, step_kernel<float, true>) : cudaFuncGetAttributes(&a, step_kernel<double, true>);
+    if (e != cudaSuccess) return DSIM_ECUDA;
+    if (regs) *regs = a.numRegs;
+    if (local_bytes) *local_bytes = (int32_t)a.localSizeBytes;
+    if (max_threads) *max_threads = a.maxThreadsPerBlock;
+    return DSIM_OK;
+}

@@ -1,0 +1,327 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via mujoco_drone_b200.BaseDroneEnv) against the CPU
+oracle on identical seeded inputs and against the committed golden fixtures.  Nothing here reads /root/reference.
+
+Stated tolerances (FP32 product path; FP64 build of the same kernel source in brackets):
+  per substep  |d pos| <= 2e-6 m [1e-12], |d quat| <= 2e-6 [1e-12], |d vel| <= 2e-5 (1+|v|) [1e-11],
+               accelerometer <= 2e-4 (1+|a|) [1e-10]
+  obs / reward on identical states: <= 5e-5 (1+|x|) [1e-10]
+  100-step open-loop trajectory: |d pos| <= 1e-3 m
+  truncation bits, step counters, reset index sets: exact
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, has_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+NOMINAL = np.array([1, 0.17, 7, 0.01, 1.2, 0.3])
+
+
+def _mk(cls_name="BaseDroneEnv", **over):
+    import mujoco_drone_b200 as M
+    cls = M.BaseDroneEnv if cls_name == "BaseDroneEnv" else getattr(M.observation_wrappers, cls_name)
+    cfg = dict(M.base_config)
+    cfg.update(over)
+    return cls(cfg)
+
+
+def _rand_inputs(rng, n, pend=True, scale=1.0):
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    pos = np.array([0, 0, 15.0]) + rng.normal(size=(n, 3))
+    qpos = np.concatenate([pos, q] + ([rng.normal(size=(n, 2)) * 0.6] if pend else []), axis=1)
+    qvel = rng.normal(size=(n, 8 if pend else 6)) * scale
+    act = rng.uniform(0, 1, size=(n, 4))
+    actions = rng.uniform(0, 1, size=(n, 4))
+    params = NOMINAL * rng.uniform(0.85, 1.15, size=(n, 6))
+    return qpos, qvel, act, actions, params
+
+
+def _set(env, qpos, qvel, act, params, num_steps=None):
+    env.drone_params = [dict(zip(("mass", "arm_len", "motor_force", "motor_tau", "pendulum_len", "weight_mass"), p)) for p in params]
+    env.set_state(qpos, qvel, act, num_steps)
+
+
+@pytest.mark.parametrize("precision,frame_skip,pend", [("fp64", 1, True), ("fp64", 3, True), ("fp64", 2, False),
+                                                       ("fp32", 1, True), ("fp32", 2, True), ("fp32", 1, False)])
+def test_substep_matches_oracle(oracle, precision, frame_skip, pend):
+    """One vector_step (= frame_skip mj_steps) on identical states/actions/params vs the FP64 oracle."""
+    import torch
+    rng = np.random.default_rng(7)
+    n = 192
+    qpos, qvel, act, actions, params = _rand_inputs(rng, n, pend)
+    if not pend:
+        params[:, 4:] = 0
+    env = _mk(num_drones=n, precision=precision, skip_steps=frame_skip, pendulum=pend, random_params=False, max_distance=100)
+    _set(env, qpos, qvel, act, params)
+    # the device holds float32 in fp32 mode: the oracle must start from exactly what the device holds
+    qpos_d, qvel_d, act_d, _, _ = env.get_state()
+    env.step_tensor(torch.as_tensor(actions, device="cuda"))
+    qp, qv, ac, sens, ns = env.get_state()
+    a_in = actions.astype(np.float32).astype(np.float64) if precision == "fp32" else actions
+    prm = env.drone_params
+    tol = dict(pos=1e-12, quat=1e-12, vel=1e-11, acc=1e-10) if precision == "fp64" else dict(pos=2e-6, quat=2e-6, vel=2e-5, acc=2e-4)
+    for i in range(n):
+        p = np.array(list(prm[i].values()))
+        m = oracle.compile_model(p, pend, 100, True)
+        oqp, oqv, oact, osens = oracle.step(m, qpos_d[i], qvel_d[i], act_d[i], 0.1 + 0.9 * a_in[i], frame_skip)
+        assert np.abs(qp[i, :3] - oqp[:3]).max() <= tol["pos"] * frame_skip
+        assert np.abs(qp[i, 3:] - oqp[3:]).max() <= tol["quat"] * frame_skip
+        assert (np.abs(qv[i] - oqv) <= tol["vel"] * frame_skip * (1 + np.abs(oqv))).all()
+        assert (np.abs(sens[i] - osens) <= tol["acc"] * frame_skip * (1 + np.abs(osens))).all()
+        assert np.abs(ac[i] - oact).max() <= (1e-12 if precision == "fp64" else 5e-6)
+    assert (ns == 1).all()
+    env.close()
+
+
+def test_compiled_constants_match_oracle_model(oracle):
+    """device model compiler (csrc/dsim_params.cuh, incl. the %.5g stage) vs the oracle's MuJoCo-style compile"""
+    rng = np.random.default_rng(3)
+    n = 257
+    params = NOMINAL * rng.uniform(0.6, 1.4, size=(n, 6))
+    for rounding in (True, False):
+        env = _mk(num_drones=n, precision="fp64", round_precision=rounding)
+        env.drone_params = [dict(zip(("mass", "arm_len", "motor_force", "motor_tau", "pendulum_len", "weight_mass"), p)) for p in params]
+        c = env.compiled_constants()
+        for i in range(n):
+            m = oracle.compile_model(params[i], True, 100, rounding)
+            RB = oracle.quat2dcm(list(m.iquat[2]))
+            IB = RB @ np.diag(list(m.inertia[2])) @ RB.T
+            assert np.abs(IB - np.diag(np.diag(IB))).max() < 1e-12           # principal frame == body frame
+            exp = [m.mass[2], m.ipos[2][2], IB[0, 0], IB[1, 1], IB[2, 2], m.mass[4], m.ipos[4][2]]
+            RD = oracle.quat2dcm(list(m.iquat[4]))
+            ID = RD @ np.diag(list(m.inertia[4])) @ RD.T
+            exp += [ID[0, 0], ID[2, 2], m.gear[1][2] * m.site_pos[1][0], m.gear[0][2], abs(m.gear[0][5]), 1.0 / m.tau[0]]
+            np.testing.assert_allclose(c[i], exp, rtol=1e-12, atol=1e-15)
+            assert abs(m.ipos[2][0]) < 1e-12 and abs(m.ipos[2][1]) < 1e-12    # COM on the body z axis
+        env.close()
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_rewards_golden(precision):
+    """all 17 rewards.py functions on the reference's own outputs (tests/golden/rewards.npz)"""
+    import torch
+    import mujoco_drone_b200 as M
+    from oracle import oracle as O
+    g = golden("rewards.npz")
+    S, n = g["states"], len(g["states"])
+    qpos = np.concatenate([S[:, :3], np.array([O.rpy2quat(r) for r in S[:, 3:6]]), S[:, 12:14]], axis=1)
+    qvel = np.concatenate([S[:, 6:12], S[:, 14:16]], axis=1)
+    for name, rid in M.rewards.REWARD_IDS.items():
+        env = _mk(num_drones=n, precision=precision, reward_fcn=getattr(M.rewards, name), reference=list(g["reference"]),
+                  start_pos=[0, 0, 15, 0], max_distance=float(g["max_distance"]), max_steps=10 ** 6)
+        _set(env, qpos, qvel, S[:, 19:23], S[:, 27:33], g["num_steps"].astype(np.int32))
+        _, rew, _ = env.evaluate_tensor(torch.as_tensor(g["actions"], device="cuda"))
+        out = rew.cpu().numpy().astype(np.float64)
+        ref = g["out_" + name]
+        tol = 1e-9 if precision == "fp64" else 2e-4
+        assert (np.abs(out - ref) <= tol * (1 + np.abs(ref))).all(), (name, np.abs(out - ref).max())
+        env.close()
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_obs_golden(precision):
+    """the 14 observation variants + raw states on the reference's own outputs (tests/golden/obs.npz)"""
+    import torch
+    import mujoco_drone_b200 as M
+    from oracle import oracle as O
+    g = golden("obs.npz")
+    S, n = g["states"], len(g["states"])
+    qpos = np.concatenate([S[:, :3], np.array([O.rpy2quat(r) for r in S[:, 3:6]]), S[:, 12:14]], axis=1)
+    qvel = np.concatenate([S[:, 6:12], S[:, 14:16]], axis=1)
+    for name, cls in M.observation_wrappers.WRAPPERS.items():
+        if name == "LocalFramePRYaccParamsNoPendEnv":
+            continue
+        env = _mk(name, num_drones=n, precision=precision, reference=list(g["reference"]), start_pos=[0, 0, 15, 0])
+        _set(env, qpos, qvel, S[:, 19:23], S[:, 27:33])
+        env.state_tensor[21:24, :n] = torch.as_tensor(S[:, 16:19].T, device="cuda", dtype=env.state_tensor.dtype)   # inject sensordata
+        obs, _, _ = env.evaluate_tensor(torch.zeros((n, 4), device="cuda"))
+        out = obs.cpu().numpy().astype(np.float64)
+        ref = g["out_" + name]
+        assert out.shape == ref.shape, name
+        tol = 1e-9 if precision == "fp64" else 5e-5
+        assert (np.abs(out - ref) <= tol * (1 + np.abs(ref))).all(), (name, np.abs(out - ref).max())
+        # get_drone_states rows (BaseDroneEnv.py:357-380)
+        st = np.array(env.get_drone_states())
+        assert (np.abs(st - S) <= tol * (1 + np.abs(S))).all()
+        env.close()
+
+
+def test_nameerror_wrapper_behaves_like_reference():
+    env = _mk("LocalFramePRYaccParamsNoPendEnv", num_drones=4)
+    with pytest.raises(NameError):
+        env.vector_reset()
+    env.close()
+
+
+def test_termination_bits_exact(oracle):
+    """truncated flags vs the oracle's FP64 termination on the SAME stored state; includes near-boundary cases"""
+    import torch
+    rng = np.random.default_rng(11)
+    n = 4096
+    qpos, qvel, act, actions, params = _rand_inputs(rng, n)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = np.where(rng.uniform(size=n) < 0.5, 4.0 + rng.normal(size=n) * 1e-6, rng.uniform(0, 8, size=n))
+    qpos[:, :3] = np.array([0.25, -0.5, 14.0]) + d * r[:, None]
+    ns = rng.integers(505, 515, size=n).astype(np.int32)
+    env = _mk(num_drones=n, reference=[0.25, -0.5, 14.0, 0.3], start_pos=[0, 0, 15, 0], max_distance=4, max_steps=512)
+    _set(env, qpos, qvel, act, np.tile(NOMINAL, (n, 1)), ns)
+    _, _, trunc = env.evaluate_tensor(torch.as_tensor(actions, device="cuda"))
+    qp, _, _, _, ns_d = env.get_state()
+    exp = np.array([oracle.termination(qp[i], [0.25, -0.5, 14.0, 0.3], 4.0, int(ns_d[i]), 512) for i in range(n)])
+    got = trunc.cpu().numpy().astype(bool)
+    assert (got == exp).all()
+    assert exp.any() and (~exp).any()
+    env.close()
+
+
+def test_protocol_replay_golden():
+    """BaseDroneEnv.vector_step through the compat API on the pre-step MjData the REFERENCE saw (tests/golden/protocol.npz):
+    obs / rewards / truncated / counters, incl. frame_skip=2 and per-drone params."""
+    g = golden("protocol.npz")
+    import mujoco_drone_b200 as M
+    T, N = g["actions"].shape[:2]
+    env = _mk("LocalFrameRPYParamsEnv", num_drones=N, precision="fp64", skip_steps=int(g["frame_skip"]), max_steps=int(g["max_steps"]),
+              max_distance=float(g["max_distance"]), reward_fcn=M.rewards.distance_energy_reward, frequency=float(g["frequency"]),
+              reference=list(g["reference"]))
+    for t in range(T):
+        if int(g["total_steps"][t]) == 0:
+            continue                                         # regen step: parameters re-drawn by the reference's PCG64
+        prm = g["params"][t - 1] if t > 0 else g["params0"]
+        prev = g["num_steps"][t - 1].copy() if t > 0 else np.zeros(N, dtype=np.int64)
+        if t > 0:
+            prev[g["reset_idx"][t - 1]] = 0
+        _set(env, g["qpos_pre"][t].reshape(N, 9), g["qvel_pre"][t].reshape(N, 8), g["act_pre"][t].reshape(N, 4), prm, prev.astype(np.int32))
+        obs, rew, dones, trunc, infos = env.vector_step(list(g["actions"][t]))
+        np.testing.assert_allclose(np.array(obs), g["obs"][t], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(np.array(rew), g["rewards"][t], rtol=1e-9, atol=1e-9)
+        assert list(trunc) == list(g["truncated"][t]) and not any(dones) and len(infos) == N
+        assert (env.num_steps == g["num_steps"][t]).all()
+        np.testing.assert_allclose(env.data.qpos, g["qpos_after"][t], atol=1e-10)
+    with pytest.raises(ValueError, match="Action dimension mismatch"):
+        env.vector_step(list(np.zeros((N - 1, 4))))
+    env.close()
+
+
+def test_reset_sampler_matches_oracle(oracle):
+    """Philox reset / parameter streams: kernel vs oracle on the same (seed, global env id, count)"""
+    n = 300
+    env = _mk(num_drones=n, precision="fp64", angle_variance=[0.3, 0.2], env_id_offset=1000, param_difficulty=1.0)
+    cfg = oracle.make_reset_cfg([0, 0, 15, 0], 0.4 * 2, [0.12, 0.08], [0.4] * 3, [0.4] * 3, [0.2] * 2, [0.2] * 2, True, True,
+                                NOMINAL, [0.1, 0.02, 1, 0.0025, 0.2, 0.05], 1.0, True)
+    seed = env.seed_value
+    P = np.array([list(d.values()) for d in env.drone_params])
+    for i in range(n):
+        np.testing.assert_allclose(P[i], oracle.sample_params(cfg, seed, 1000 + i, 0), rtol=1e-14)
+    env.vector_reset()
+    qp, qv, _, _, ns = env.get_state()
+    for i in range(n):
+        oq, ov = oracle.sample_state(cfg, seed, 1000 + i, 0)
+        np.testing.assert_allclose(qp[i], oq, atol=1e-12)
+        np.testing.assert_allclose(qv[i], ov, atol=1e-12)
+    env.reset_at(5)
+    env.reset_at(5)
+    qp2, qv2, _, _, _ = env.get_state()
+    oq, ov = oracle.sample_state(cfg, seed, 1005, 2)
+    np.testing.assert_allclose(qp2[5], oq, atol=1e-12)
+    assert np.array_equal(np.delete(qp2, 5, 0), np.delete(qp, 5, 0))
+    env.reset_model(regen=True)
+    P2 = np.array([list(d.values()) for d in env.drone_params])
+    np.testing.assert_allclose(P2[7], oracle.sample_params(cfg, seed, 1007, 1), rtol=1e-14)
+    env.close()
+
+
+def test_vector_env_protocol_and_auto_reset(oracle):
+    """compat protocol (stale reset_at obs Q1, act persistence Q3, dones False Q7, regen Q8) and the native auto-reset
+    loop: reset index set == truncated set, counters exact."""
+    import torch
+    import mujoco_drone_b200 as M
+    n = 512
+    env = _mk("LocalFrameRPYParamsEnv", num_drones=n, max_steps=7, max_distance=1.0, regen_env_at_steps=20,
+              reward_fcn=M.rewards.distance_energy_reward, param_difficulty=1.0)
+    obs, infos = env.vector_reset()
+    assert len(obs) == n and obs[0].shape == (22,) and obs[0].dtype == np.float64 and len(infos) == n
+    rng = np.random.default_rng(0)
+    counters = np.zeros(n, dtype=np.int64)
+    for t in range(1, 24):
+        obs, rew, dones, trunc, infos = env.vector_step(list(rng.uniform(0, 1, size=(n, 4))))
+        counters += 1
+        if t == 20:
+            assert isinstance(trunc, np.ndarray) and trunc.all()            # np.ones on regen (:292)
+            counters[:] = 0
+            assert env.total_steps == 0
+        else:
+            assert isinstance(trunc, list) and not any(dones)
+        assert (env.num_steps == counters).all()
+        _, _, act_before, _, _ = env.get_state()
+        for i in np.nonzero(np.asarray(trunc))[0]:
+            ob, info = env.reset_at(int(i))
+            assert np.array_equal(ob, obs[i]) and info == {}                    # stale observation (Q1)
+            counters[i] = 0
+        _, _, act_after, _, _ = env.get_state()
+        assert np.array_equal(act_before, act_after)                             # act persists across reset_at (Q3)
+        assert (env.num_steps == counters).all()
+    assert env.episode_stats()["n_episodes"] > 0
+    env.close()
+    # native loop
+    env = _mk("LocalFrameRPYParamsEnv", num_drones=n, max_steps=9, max_distance=1.5, auto_reset=True)
+    env.reset_tensor()
+    rc = env.tensor(M._lib.BUF_RESET_COUNT)
+    counters = np.zeros(n, dtype=np.int64)
+    resets = np.zeros(n, dtype=np.int64)
+    for t in range(40):
+        _, _, trunc = env.step_tensor(torch.rand((n, 4), device="cuda"))
+        tr = trunc.cpu().numpy().astype(bool)
+        counters = np.where(tr, 0, counters + 1)
+        resets += tr
+        assert (env.num_steps == counters).all()
+        assert (rc.cpu().numpy()[:n] == resets).all()
+    assert resets.sum() > n
+    st = env.episode_stats()
+    assert st["n_episodes"] == resets.sum() and st["n_nonfinite"] == 0
+    env.close()
+
+
+def test_open_loop_trajectory_fp32_vs_oracle(oracle):
+    """100 steps open loop near hover: FP32 kernel trajectory vs FP64 oracle, |d pos| <= 1e-3 m"""
+    import torch
+    n = 64
+    rng = np.random.default_rng(5)
+    env = _mk(num_drones=n, random_params=False, max_distance=100, max_steps=10 ** 6)
+    env.vector_reset()
+    qp, qv, act, _, _ = env.get_state()
+    m = oracle.compile_model(NOMINAL, True, 100, True)
+    hov = 0.49228
+    oqp, oqv, oact = qp.copy(), qv.copy(), act.copy()
+    for t in range(100):
+        a = (hov + rng.normal(size=(n, 4)) * 0.05).clip(0, 1).astype(np.float32)
+        env.step_tensor(torch.as_tensor(a, device="cuda"))
+        for i in range(n):
+            oqp[i], oqv[i], oact[i], _ = oracle.step(m, oqp[i], oqv[i], oact[i], 0.1 + 0.9 * a[i].astype(np.float64), 1)
+    qp, qv, _, _, _ = env.get_state()
+    assert np.abs(qp[:, :3] - oqp[:, :3]).max() <= 1e-3
+    assert np.abs(qv - oqv).max() <= 2e-2
+    env.close()
+
+
+def test_large_batch_properties():
+    """BASELINE-size batch (131072 envs): size-independent properties — finite outputs, unit quaternions, counters,
+    truncated == (|pos-ref| > max_distance or steps >= max_steps) recomputed on the device state, hover invariance."""
+    import torch
+    import mujoco_drone_b200 as M
+    n = 131072
+    env = _mk("LocalFrameRPYParamsEnv", num_drones=n, param_difficulty=1.0, state_difficulty=0.3, max_steps=1024,
+              reward_fcn=M.rewards.distance_energy_reward, auto_reset=True)
+    env.reset_tensor()
+    for t in range(20):
+        obs, rew, trunc = env.step_tensor(torch.rand((n, 4), device="cuda"))
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    st = env.state_tensor[:, :n]
+    qn = (st[3:7] ** 2).sum(0).sqrt()
+    assert (qn - 1).abs().max() < 1e-5
+    assert (env.num_steps_tensor[:n] <= 20).all()
+    assert env.episode_stats()["n_nonfinite"] == 0
+    assert env.launch_count() > 0
+    env.close()
