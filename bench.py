@@ -59,7 +59,19 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml = [], None, None
+        try:   # NVML in-process: ~2 ms period, fine enough for a timed region of a few tens of ms
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.samples, self._stop = [], False
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -72,7 +84,34 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def _poll(self):
+        nv = self.nvml
+        while not self._stop:
+            try:
+                clk = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.time(), clk, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _stop_nvml(self, t0, t1):
+        self._stop = True
+        self.t.join(timeout=1.0)
+        nv = self.nvml
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        inside = [(c, r) for ts, c, r in self.samples if t0 <= ts <= t1]
+        reasons = sorted({nm for _, r in inside for nm, b in bits.items() if r & b})
+        return {"sm_mhz": float(np.median([c for c, _ in inside])) if inside else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                "samples": len(inside), "source": "nvml polled every ~2 ms during the timed region"}
+
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            return self._stop_nvml(t0, t1)
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdronesim_b200.so")
+LIB_PATH = os.environ.get("DSIM_LIB") or os.path.join(_HERE, "libdronesim_b200.so")   # DSIM_LIB: kernel-variant experiments
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ESHAPE = 0, -1, -2, -3, -4, -5
 FP32, FP64 = 0, 1

@@ -40,6 +40,9 @@ enum { C_MB = 0, C_CZ, C_IBX, C_IBY, C_IBZ, C_MD, C_ZD, C_IDX, C_IDZ, C_FS, C_F,
 
 // ------------------------------------------------------------------ scalar helpers
 template <typename T> DSIM_DEV T sqrt_(T x) { if constexpr (std::is_same<T, float>::value) return sqrtf(x); else return sqrt(x); }
+// reciprocal without the IEEE-division slow path (MUFU.RCP + Newton step, correctly rounded for normal inputs)
+template <typename T> DSIM_DEV T rcp_(T x) { if constexpr (std::is_same<T, float>::value) return __frcp_rn(x); else return 1.0 / x; }
+template <typename T> DSIM_DEV T floor_(T x) { if constexpr (std::is_same<T, float>::value) return floorf(x); else return floor(x); }
 template <typename T> DSIM_DEV T rsqrt_(T x) { if constexpr (std::is_same<T, float>::value) return rsqrtf(x); else return 1.0 / sqrt(x); }
 template <typename T> DSIM_DEV T abs_(T x) { if constexpr (std::is_same<T, float>::value) return fabsf(x); else return fabs(x); }
 template <typename T> DSIM_DEV T max_(T a, T b) { if constexpr (std::is_same<T, float>::value) return fmaxf(a, b); else return fmax(a, b); }
@@ -51,9 +54,12 @@ template <typename T> DSIM_DEV T cbrt_(T x) { if constexpr (std::is_same<T, floa
 template <typename T> DSIM_DEV void sincos_(T a, T *s, T *c) { if constexpr (std::is_same<T, float>::value) sincosf(a, s, c); else sincos(a, s, c); }
 template <typename T> DSIM_DEV bool finite_(T x) { return isfinite(x); }
 template <typename T> DSIM_DEV T clamp_(T x, T lo, T hi) { return min_(max_(x, lo), hi); }
-// Python's float % for a positive modulus (rewards.py / observation_wrappers.py heading wrap)
-template <typename T> DSIM_DEV T pymod_(T a, T b) { T r = fmod_(a, b); return (r < T(0)) ? r + b : r; }
-template <typename T> DSIM_DEV T wrap_pi(T a) { return pymod_(a + T(kPi), T(2 * kPi)) - T(kPi); }
+// (a + pi) % (2 pi) - pi with Python's sign convention (rewards.py / observation_wrappers.py / scipy as_euler):
+// a - 2 pi floor((a + pi) / 2 pi); returns `a` itself when it already lies in [-pi, pi)
+template <typename T> DSIM_DEV T wrap_pi(T a) {
+    const T k = floor_((a + T(kPi)) * T(1.0 / (2 * kPi)));
+    return a - k * T(2 * kPi);
+}
 
 template <typename T> struct V3 { T x, y, z; };
 template <typename T> DSIM_DEV V3<T> mk(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
@@ -106,7 +112,7 @@ template <typename T> struct EnvConsts { T mB, cz, IBx, IBy, IBz, mD, zD, IDx, I
 // local force / torque.  Box from (mass, principal inertia).
 template <typename T> struct FluidBox { T fq[3], tq[3], kv, kw; };
 template <typename T> DSIM_DEV FluidBox<T> fluid_box(T mass, T Ix, T Iy, T Iz) {
-    T s = T(6) / mass;
+    T s = T(6) * rcp_(mass);
     T bx = sqrt_(max_(T(kMinVal), Iy + Iz - Ix) * s), by = sqrt_(max_(T(kMinVal), Ix + Iz - Iy) * s), bz = sqrt_(max_(T(kMinVal), Ix + Iy - Iz) * s);
     T d = (bx + by + bz) * T(1.0 / 3.0);
     FluidBox<T> f;
@@ -127,13 +133,13 @@ template <typename T> DSIM_DEV void fluid_apply(const FluidBox<T> &b, V3<T> w, V
 template <typename T> struct Ldl3 { T l10, l20, l21, id0, id1, id2; };
 template <typename T> DSIM_DEV Ldl3<T> ldl3(T a00, T a10, T a11, T a20, T a21, T a22) {
     Ldl3<T> f;
-    f.id0 = T(1) / a00;
+    f.id0 = rcp_(a00);
     f.l10 = a10 * f.id0; f.l20 = a20 * f.id0;
     T d1 = a11 - f.l10 * a10;
-    f.id1 = T(1) / d1;
+    f.id1 = rcp_(d1);
     f.l21 = (a21 - f.l20 * a10) * f.id1;
     T d2 = a22 - f.l20 * a20 - f.l21 * f.l21 * d1;
-    f.id2 = T(1) / d2;
+    f.id2 = rcp_(d2);
     return f;
 }
 template <typename T> DSIM_DEV V3<T> ldl3_solve(const Ldl3<T> &f, V3<T> b) {
@@ -159,7 +165,7 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
     const V3<T> om = s.om;
     const T mC = PEND ? T(kMassC) : T(0), IC = PEND ? T(kInertiaC) : T(0), dl = T(kLinkDrop);
     const T mD = PEND ? c.mD : T(0);
-    const T mh = mC + mD, mtot = c.mB + mh, inv_m = T(1) / mtot;
+    const T mh = mC + mD, mtot = c.mB + mh, inv_m = rcp_(mtot);
 
     T sx = 0, cx = 1, sy = 0, cy = 1;
     if (PEND) { sincos_(s.hx, &sx, &cx); sincos_(s.hy, &sy, &cy); }
@@ -275,7 +281,7 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
         const T Syy = P - (dot(py, acy) + dot(Ly, aly));
         const T r1 = rx - (dot(px, ac0) + dot(Lx, al0)), r2 = ry - (dot(py, ac0) + dot(Ly, al0));
         {   // explicit (qacc of mj_fwdAcceleration): feeds the accelerometer
-            const T idet = T(1) / (Sxx * Syy - Sxy * Sxy);
+            const T idet = rcp_(Sxx * Syy - Sxy * Sxy);
             const T hax = (Syy * r1 - Sxy * r2) * idet, hay = (Sxx * r2 - Sxy * r1) * idet;
             a_e = ac0 - hax * acx - hay * acy;
             al_e = al0 - hax * alx - hay * aly;
@@ -283,7 +289,7 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
         if (ADVANCE) {  // implicit in joint damping (mj_EulerSkip): (M + h diag(B)) qacc = qfrc_smooth
             const T hb = h * T(kHingeDamping);
             const T Sxx2 = Sxx + hb, Syy2 = Syy + hb;
-            const T idet = T(1) / (Sxx2 * Syy2 - Sxy * Sxy);
+            const T idet = rcp_(Sxx2 * Syy2 - Sxy * Sxy);
             hax_i = (Syy2 * r1 - Sxy * r2) * idet; hay_i = (Sxx2 * r2 - Sxy * r1) * idet;
             a_i = ac0 - hax_i * acx - hay_i * acy;
             al_i = al0 - hax_i * alx - hay_i * aly;

@@ -2,7 +2,9 @@
 oracle on identical seeded inputs and against the committed golden fixtures.  Nothing here reads /root/reference.
 
 Stated tolerances (FP32 product path; FP64 build of the same kernel source in brackets):
-  per substep  |d pos| <= 2e-6 m [1e-12], |d quat| <= 2e-6 [1e-12], |d vel| <= 2e-5 (1+|v|) [1e-11],
+  per substep  |d pos| <= 2e-6 m [1e-12], |d quat| <= 2e-6 [1e-12], |d v_lin| <= 2e-5 (1+|v|) [1e-11],
+               |d omega|, |d hinge rate| <= 1e-4 (1+|w|) [1e-11]  (cond(M) ~ 5e2: the body-vs-pendulum relative
+               rotation is the ill-conditioned direction; the SUM omega + hinge rate is held to 2e-5),
                accelerometer <= 2e-4 (1+|a|) [1e-10]
   obs / reward on identical states: <= 5e-5 (1+|x|) [1e-10]
   100-step open-loop trajectory: |d pos| <= 1e-3 m
@@ -61,14 +63,17 @@ def test_substep_matches_oracle(oracle, precision, frame_skip, pend):
     qp, qv, ac, sens, ns = env.get_state()
     a_in = actions.astype(np.float32).astype(np.float64) if precision == "fp32" else actions
     prm = env.drone_params
-    tol = dict(pos=1e-12, quat=1e-12, vel=1e-11, acc=1e-10) if precision == "fp64" else dict(pos=2e-6, quat=2e-6, vel=2e-5, acc=2e-4)
+    tol = dict(pos=1e-12, quat=1e-12, vel=1e-11, rot=1e-11, acc=1e-10) if precision == "fp64" else dict(pos=2e-6, quat=2e-6, vel=2e-5, rot=1e-4, acc=2e-4)
     for i in range(n):
         p = np.array(list(prm[i].values()))
         m = oracle.compile_model(p, pend, 100, True)
         oqp, oqv, oact, osens = oracle.step(m, qpos_d[i], qvel_d[i], act_d[i], 0.1 + 0.9 * a_in[i], frame_skip)
         assert np.abs(qp[i, :3] - oqp[:3]).max() <= tol["pos"] * frame_skip
         assert np.abs(qp[i, 3:] - oqp[3:]).max() <= tol["quat"] * frame_skip
-        assert (np.abs(qv[i] - oqv) <= tol["vel"] * frame_skip * (1 + np.abs(oqv))).all()
+        assert (np.abs(qv[i, :3] - oqv[:3]) <= tol["vel"] * frame_skip * (1 + np.abs(oqv[:3]))).all()
+        assert (np.abs(qv[i, 3:] - oqv[3:]) <= tol["rot"] * frame_skip * (1 + np.abs(oqv[3:]))).all()
+        if pend:   # well-conditioned combination: absolute pendulum rate about the hinge axes
+            assert abs((qv[i, 3] + qv[i, 6]) - (oqv[3] + oqv[6])) <= tol["vel"] * frame_skip * (1 + abs(oqv[3]) + abs(oqv[6]))
         assert (np.abs(sens[i] - osens) <= tol["acc"] * frame_skip * (1 + np.abs(osens))).all()
         assert np.abs(ac[i] - oact).max() <= (1e-12 if precision == "fp64" else 5e-6)
     assert (ns == 1).all()
