@@ -23,257 +23,7 @@ namespace {
 
 constexpr int kBlock = 128;
 
-// ------------------------------------------------------------------ kernel parameter block (constant bank)
-template <typename T> struct KParams {
-    int n, ld;
-    T *state;
-    int *num_steps;
-    unsigned *reset_count;
-    const T *consts;          // [13][ld]
-    const T *params;          // [6][ld]
-    T *ref_env;               // [4][ld] (per-env setpoints) or nullptr
-    T *obs, *reward, *ep_return;
-    unsigned char *trunc;
-    double *stats;
-    const T *actions;         // [n][4]
-    T uconst[C_ROWS];         // uniform-parameter fast path (random_params == False)
-    T uparams[6];
-    int per_env_consts, auto_reset, obs_id, reward_id, obs_layout, obs_dim, frame_skip, max_steps;
-    int eval_only;            // 1: termination / reward / obs of the CURRENT state, nothing advanced or stored
-    T h, max_distance_t;
-    T ref_off[3], ref_yaw, start_t[3];
-    double start[3], ref64[3], max_distance;
-    ResetCfg<T> rc;
-    unsigned seed, env_base;
-};
-
-template <typename T> DSIM_DEV EnvState<T> load_state(const KParams<T> &p, int i) {
-    const T *b = p.state + i;
-    const size_t ld = p.ld;
-    EnvState<T> s;
-    s.pos = mk(b[0 * ld], b[1 * ld], b[2 * ld]);
-    s.qw = b[3 * ld]; s.qx = b[4 * ld]; s.qy = b[5 * ld]; s.qz = b[6 * ld];
-    s.hx = b[7 * ld]; s.hy = b[8 * ld];
-    s.vel = mk(b[9 * ld], b[10 * ld], b[11 * ld]);
-    s.om = mk(b[12 * ld], b[13 * ld], b[14 * ld]);
-    s.hvx = b[15 * ld]; s.hvy = b[16 * ld];
-    #pragma unroll
-    for (int k = 0; k < 4; k++) s.act[k] = b[(S_ACT + k) * ld];
-    s.acc = mk(b[21 * ld], b[22 * ld], b[23 * ld]);
-    return s;
-}
-template <typename T> DSIM_DEV void store_state(const KParams<T> &p, int i, const EnvState<T> &s) {
-    T *b = p.state + i;
-    const size_t ld = p.ld;
-    b[0 * ld] = s.pos.x; b[1 * ld] = s.pos.y; b[2 * ld] = s.pos.z;
-    b[3 * ld] = s.qw; b[4 * ld] = s.qx; b[5 * ld] = s.qy; b[6 * ld] = s.qz;
-    b[7 * ld] = s.hx; b[8 * ld] = s.hy;
-    b[9 * ld] = s.vel.x; b[10 * ld] = s.vel.y; b[11 * ld] = s.vel.z;
-    b[12 * ld] = s.om.x; b[13 * ld] = s.om.y; b[14 * ld] = s.om.z;
-    b[15 * ld] = s.hvx; b[16 * ld] = s.hvy;
-    #pragma unroll
-    for (int k = 0; k < 4; k++) b[(S_ACT + k) * ld] = s.act[k];
-    b[21 * ld] = s.acc.x; b[22 * ld] = s.acc.y; b[23 * ld] = s.acc.z;
-}
-template <typename T> DSIM_DEV EnvConsts<T> load_consts(const KParams<T> &p, int i) {
-    EnvConsts<T> c;
-    T v[C_ROWS];
-    if (p.per_env_consts) {
-        #pragma unroll
-        for (int k = 0; k < C_ROWS; k++) v[k] = __ldg(p.consts + (size_t)k * p.ld + i);
-    } else {
-        #pragma unroll
-        for (int k = 0; k < C_ROWS; k++) v[k] = p.uconst[k];
-    }
-    c.mB = v[C_MB]; c.cz = v[C_CZ]; c.IBx = v[C_IBX]; c.IBy = v[C_IBY]; c.IBz = v[C_IBZ];
-    c.mD = v[C_MD]; c.zD = v[C_ZD]; c.IDx = v[C_IDX]; c.IDz = v[C_IDZ];
-    c.Fs = v[C_FS]; c.F = v[C_F]; c.kq = v[C_KQ]; c.inv_tau = v[C_INVTAU];
-    return c;
-}
-template <typename T> DSIM_DEV void load_params(const KParams<T> &p, int i, T prm[6]) {
-    if (p.per_env_consts) {
-        #pragma unroll
-        for (int k = 0; k < 6; k++) prm[k] = __ldg(p.params + (size_t)k * p.ld + i);
-    } else {
-        #pragma unroll
-        for (int k = 0; k < 6; k++) prm[k] = p.uparams[k];
-    }
-}
-template <typename T> DSIM_DEV void load_ref(const KParams<T> &p, int i, V3<T> &ref_off, T &ref_yaw, double ref64[3]) {
-    if (p.ref_env) {
-        const T *r = p.ref_env + i;
-        ref_off = mk(r[0], r[(size_t)p.ld], r[2 * (size_t)p.ld]);
-        ref_yaw = r[3 * (size_t)p.ld];
-        ref64[0] = p.start[0] + (double)ref_off.x; ref64[1] = p.start[1] + (double)ref_off.y; ref64[2] = p.start[2] + (double)ref_off.z;
-    } else {
-        ref_off = mk(p.ref_off[0], p.ref_off[1], p.ref_off[2]);
-        ref_yaw = p.ref_yaw;
-        ref64[0] = p.ref64[0]; ref64[1] = p.ref64[1]; ref64[2] = p.ref64[2];
-    }
-}
-template <typename T> DSIM_DEV bool state_finite(const EnvState<T> &s) {
-    const T a = s.pos.x + s.pos.y + s.pos.z + s.qw + s.qx + s.qy + s.qz + s.hx + s.hy;
-    const T b = s.vel.x + s.vel.y + s.vel.z + s.om.x + s.om.y + s.om.z + s.hvx + s.hvy + s.act[0] + s.act[1] + s.act[2] + s.act[3];
-    // MuJoCo's mj_check* also rejects |x| > mjMAXVAL (1e10)
-    return finite_(a) && finite_(b) && abs_(a) < T(1e10) && abs_(b) < T(1e10);
-}
-template <typename T> struct ObsWriter {
-    T *base; size_t stride;
-    DSIM_DEV void operator()(int j, T v) const { base[(size_t)j * stride] = v; }
-};
-template <typename T> DSIM_DEV ObsWriter<T> obs_writer(const KParams<T> &p, int i) {
-    ObsWriter<T> w;
-    if (p.obs_layout == DSIM_LAYOUT_SOA) { w.base = p.obs + i; w.stride = p.ld; }
-    else { w.base = p.obs + (size_t)i * p.obs_dim; w.stride = 1; }
-    return w;
-}
-
-// ------------------------------------------------------------------ THE fused env-step kernel
-// BaseDroneEnv.vector_step (:259-294): ctrl remap (:269) -> mj_step x frame_skip (mujoco_vecenv.py:404-407) ->
-// num_steps += 1 (:271) -> get_drone_states (:357-380) -> terminated_fcn / reward_fcn (:275-284) -> _get_obs.
-// OBS / REW >= 0 are compile-time specialisations of the wrapper class / reward function (smaller code, no dispatch
-// branches); -1 reads the id from the parameter block.  The FP32 build is register-capped for kMinBlocksF32 resident
-// CTAs per SM (latency hiding: the kernel is issue/latency bound, not HBM bound).
-#ifndef DSIM_MINB
-#define DSIM_MINB 4
-#endif
-template <typename T> constexpr int min_blocks() { return std::is_same<T, float>::value ? DSIM_MINB : 1; }
-
-constexpr int kObsPad = DSIM_MAX_OBS | 1;      // odd row pitch of the smem observation tile: conflict-free row writes
-constexpr int kLate = 11;                      // ep_return, params[6], ref[4]: needed only after the physics
-
-// cooperative, fully coalesced copy of the block's observation tile (smem, row pitch Dp) to obs[row0*D ...] (row pitch D)
-template <typename T>
-DSIM_DEV void copy_out_obs(const T *tile, int Dp, T *gout, int D, int nvalid, int t) {
-    const int E = nvalid * D;
-    if constexpr (std::is_same<T, float>::value) {
-        if ((E & 3) == 0) {                    // 128 rows: always; the ragged last block falls through to the scalar loop
-            const int q = 512 / D, rem = 512 - q * D;
-            int r = (4 * t) / D, j = 4 * t - r * D;
-            float4 *g4 = reinterpret_cast<float4 *>(gout);
-            for (int e4 = t; e4 < (E >> 2); e4 += kBlock) {
-                float v[4];
-                int rr = r, jj = j;
-                #pragma unroll
-                for (int k = 0; k < 4; k++) { v[k] = tile[rr * Dp + jj]; if (++jj == D) { jj = 0; ++rr; } }
-                g4[e4] = make_float4(v[0], v[1], v[2], v[3]);
-                r += q; j += rem;
-                if (j >= D) { j -= D; ++r; }
-            }
-            return;
-        }
-    }
-    const int q = kBlock / D, rem = kBlock - q * D;
-    int r = t / D, j = t - r * D;
-    for (int e = t; e < E; e += kBlock) {
-        gout[e] = tile[r * Dp + j];
-        r += q; j += rem;
-        if (j >= D) { j -= D; ++r; }
-    }
-}
-
-template <typename T, bool PEND, int OBS, int REW>
-__global__ void __launch_bounds__(kBlock, min_blocks<T>()) step_kernel(const KParams<T> p) {
-    __shared__ T s_obs[kBlock * kObsPad];
-    __shared__ T s_late[kLate][kBlock];
-    __shared__ int s_ns[kBlock];
-    const int t = threadIdx.x, i = blockIdx.x * kBlock + t;
-    const bool active = i < p.n;
-    const int obs_id = OBS >= 0 ? OBS : p.obs_id, reward_id = REW >= 0 ? REW : p.reward_id;
-    const int D = p.obs_dim, Dp = D | 1;
-    const bool staged = p.obs_layout == DSIM_LAYOUT_ENV_MAJOR;
-    if (active) {
-        // values used only after the physics go global -> shared with cp.async at the very top: their DRAM latency
-        // overlaps the physics and they occupy no registers meanwhile
-        __pipeline_memcpy_async(&s_ns[t], p.num_steps + i, sizeof(int));
-        __pipeline_memcpy_async(&s_late[0][t], p.ep_return + i, sizeof(T));
-        if (p.per_env_consts) {
-            #pragma unroll
-            for (int k = 0; k < 6; k++) __pipeline_memcpy_async(&s_late[1 + k][t], p.params + (size_t)k * p.ld + i, sizeof(T));
-        }
-        if (p.ref_env) {
-            #pragma unroll
-            for (int k = 0; k < 4; k++) __pipeline_memcpy_async(&s_late[7 + k][t], p.ref_env + (size_t)k * p.ld + i, sizeof(T));
-        }
-        __pipeline_commit();
-
-        EnvState<T> s = load_state(p, i);
-        const EnvConsts<T> c = load_consts(p, i);
-        T a[4], ctrl[4];
-        if constexpr (std::is_same<T, float>::value) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(p.actions) + i);
-            a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-        } else {
-            const double2 v0 = __ldg(reinterpret_cast<const double2 *>(p.actions) + 2 * (size_t)i);
-            const double2 v1 = __ldg(reinterpret_cast<const double2 *>(p.actions) + 2 * (size_t)i + 1);
-            a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y;
-        }
-        #pragma unroll
-        for (int k = 0; k < 4; k++) ctrl[k] = clamp_(T(0.1) + T(0.9) * a[k], T(0), T(1));   // :269, ctrlrange (0,1) clamp of mj_fwdActuation
-        for (int f = 0; f < p.frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
-
-        __pipeline_wait_prior(0);
-        int ns = s_ns[t] + (p.eval_only ? 0 : 1);
-        const unsigned env = p.env_base + (unsigned)i;
-        const bool bad = !state_finite(s);
-        if (bad) {   // MuJoCo: mj_checkPos/Vel/Acc warn and reset the data; here: per-env re-sample, counted, never silent
-            sample_state<T, PEND>(s, p.rc, p.seed, env, p.reset_count[i] + 1u);
-            #pragma unroll
-            for (int k = 0; k < 4; k++) s.act[k] = T(0);
-            s.acc = mk(T(0), T(0), T(0));
-            p.reset_count[i] += 1u;
-            atomicAdd(p.stats + 3, 1.0);
-        }
-
-        V3<T> ref_off; T ref_yaw; double ref64[3];
-        if (p.ref_env) {
-            ref_off = mk(s_late[7][t], s_late[8][t], s_late[9][t]);
-            ref_yaw = s_late[10][t];
-            ref64[0] = p.start[0] + (double)ref_off.x; ref64[1] = p.start[1] + (double)ref_off.y; ref64[2] = p.start[2] + (double)ref_off.z;
-        } else {
-            ref_off = mk(p.ref_off[0], p.ref_off[1], p.ref_off[2]);
-            ref_yaw = p.ref_yaw;
-            ref64[0] = p.ref64[0]; ref64[1] = p.ref64[1]; ref64[2] = p.ref64[2];
-        }
-        T prm[6];
-        #pragma unroll
-        for (int k = 0; k < 6; k++) prm[k] = p.per_env_consts ? s_late[1 + k][t] : p.uparams[k];
-        const PostState<T> ps = post_state(s, ref_off, ref_yaw);
-        bool trunc = terminated(s.pos, p.start, ref64, p.max_distance, ns, p.max_steps);
-        const T rew = bad ? T(0) : reward_fn<T, PEND>(reward_id, s, ps, a, ns, prm, p.max_distance_t);
-        trunc = trunc || bad;
-        ObsWriter<T> w;
-        if (staged) { w.base = s_obs + t * Dp; w.stride = 1; }
-        else { w.base = p.obs + i; w.stride = p.ld; }
-        emit_obs<T, PEND>(obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
-        p.reward[i] = rew;
-        p.trunc[i] = trunc ? 1 : 0;
-
-        if (!p.eval_only) {
-            // would-be ground contact (the floor plane is out of reach in the BASELINE configs; detected, never ignored)
-            if (p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(p.stats + 4, 1.0);
-            T ret = s_late[0][t] + rew;
-            if (trunc) {
-                atomicAdd(p.stats + 0, (double)ret); atomicAdd(p.stats + 1, (double)ns); atomicAdd(p.stats + 2, 1.0);
-                ret = T(0);
-                if (p.auto_reset && !bad) {   // native loop: the RLlib reset_at() round trip (:334-351) folded into the step
-                    const unsigned rcnt = p.reset_count[i] + 1u;
-                    sample_state<T, PEND>(s, p.rc, p.seed, env, rcnt);
-                    p.reset_count[i] = rcnt;
-                }
-                if (p.auto_reset || bad) ns = 0;
-            }
-            p.ep_return[i] = ret;
-            p.num_steps[i] = ns;
-            store_state(p, i, s);
-        }
-    }
-    if (staged) {   // smem-staged transpose: the [N][D] policy-ready rows leave the SM as full 128-byte lines
-        __syncthreads();
-        const int row0 = blockIdx.x * kBlock;
-        copy_out_obs<T>(s_obs, Dp, p.obs + (size_t)row0 * D, D, min(kBlock, p.n - row0), t);
-    }
-}
+#include "dsim_step.cuh"
 
 // mj_forward after set_state (mujoco_vecenv.py:396-402): refresh sensordata (+ obs) from the current state
 template <typename T, bool PEND>
@@ -679,15 +429,15 @@ extern "C" int dsim_zero_act(DsimHandle *h, void *stream) {
 
 // step-kernel dispatch: compile-time specialisations for the BASELINE configs, generic kernel otherwise
 template <typename T> static void launch_step(const DsimHandle *h, const KParams<T> &kp, cudaStream_t st) {
-    const int grid = (h->n + kBlock - 1) / kBlock;
-    if (!h->cfg.pendulum) { step_kernel<T, false, -1, -1><<<grid, kBlock, 0, st>>>(kp); return; }
+    const int grid = (h->n + kStepBlock - 1) / kStepBlock;
+    if (!h->cfg.pendulum) { step_kernel<T, false, -1, -1><<<grid, kStepBlock, 0, st>>>(kp); return; }
     if constexpr (std::is_same<T, float>::value) {
         const int o = kp.obs_id, r = kp.reward_id;
-        if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2) { step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2><<<grid, kBlock, 0, st>>>(kp); return; }   // C4 / C5
-        if (o == DSIM_OBS_LOCAL_RPY && r == 1) { step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1><<<grid, kBlock, 0, st>>>(kp); return; }                 // C3
-        if (o == DSIM_OBS_BASE && r == 0) { step_kernel<float, true, DSIM_OBS_BASE, 0><<<grid, kBlock, 0, st>>>(kp); return; }                           // C2
+        if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2) { step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2><<<grid, kStepBlock, 0, st>>>(kp); return; }   // C4 / C5
+        if (o == DSIM_OBS_LOCAL_RPY && r == 1) { step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1><<<grid, kStepBlock, 0, st>>>(kp); return; }                 // C3
+        if (o == DSIM_OBS_BASE && r == 0) { step_kernel<float, true, DSIM_OBS_BASE, 0><<<grid, kStepBlock, 0, st>>>(kp); return; }                           // C2
     }
-    step_kernel<T, true, -1, -1><<<grid, kBlock, 0, st>>>(kp);
+    step_kernel<T, true, -1, -1><<<grid, kStepBlock, 0, st>>>(kp);
 }
 static int step_impl(DsimHandle *h, const void *actions_dev, void *stream, int eval_only) {
     CK(cudaSetDevice(h->device));
