@@ -10,13 +10,17 @@
  * thread, one stream at a time (reference threading model: one env object per Ray worker process,
  * BaseDroneEnv.py:53).
  *
- * Device memory layout (all buffers owned by the handle, valid until dsim_destroy):
- *   state   [DSIM_NSTATE_ROWS][ld]  SoA rows of `real` (float, or double when precision==DSIM_FP64):
- *           0-2 position OFFSET from start_pos[0:3] | 3-6 quat (w,x,y,z) | 7-8 hinge angles (x,y)
- *           9-11 world linear velocity | 12-14 body angular velocity | 15-16 hinge rates
- *           17-20 motor activations `act` | 21-23 accelerometer `sensordata`
- *           i.e. MuJoCo's qpos[9], qvel[8], act[4], sensordata[3] per drone (BaseDroneEnv.py:367-375).
- *   ld = num_envs rounded up to a multiple of 32 (every row is 128-byte aligned).
+ * Device memory layout (all buffers owned by the handle, valid until dsim_destroy).  `real` = float, or double when
+ * precision == DSIM_FP64.  Per-env data lives in PAGES of 32 envs (one warp of the step kernel); a page of a buffer
+ * with R rows is the contiguous block real[R][32], so ONE 1D bulk copy (TMA) moves a warp's whole working set:
+ *     element (row r, env i)  =  base[(i / 32) * R * 32 + r * 32 + (i % 32)]          ("PAGED", R = page_rows)
+ *   read-write page (R = 26):  rows 0-23 state = MuJoCo's qpos[9], qvel[8], act[4], sensordata[3] per drone
+ *           (BaseDroneEnv.py:367-375): 0-2 position OFFSET from start_pos[0:3] | 3-6 quat (w,x,y,z) | 7-8 hinge angles
+ *           | 9-11 world linear velocity | 12-14 body angular velocity | 15-16 hinge rates | 17-20 `act` | 21-23 accelerometer;
+ *           row 24 BaseDroneEnv.num_steps (integer of the width of `real`), row 25 running episode return
+ *   read-only page  (R = 19):  rows 0-12 compiled rigid-body constants, rows 13-18 raw drone_params
+ *   setpoint page   (R = 4):   x, y, z offsets from start_pos and yaw (only read when per_env_reference)
+ *   ld = num_envs rounded up to a multiple of 32.
  */
 #ifndef DRONESIM_B200_H
 #define DRONESIM_B200_H
@@ -26,29 +30,28 @@
 extern "C" {
 #endif
 
-#define DSIM_ABI_VERSION 1
+#define DSIM_ABI_VERSION 2
 
 enum { DSIM_OK = 0, DSIM_EINVAL = -1, DSIM_ECUDA = -2, DSIM_ENOMEM = -3, DSIM_EUNSUPPORTED = -4, DSIM_ESHAPE = -5 };
 enum { DSIM_FP32 = 0, DSIM_FP64 = 1 };
-enum { DSIM_LAYOUT_ENV_MAJOR = 0 /* [N][D], policy-ready rows */, DSIM_LAYOUT_SOA = 1 /* [D][ld] */ };
 enum { DSIM_NSTATE_ROWS = 24, DSIM_NCONST = 13, DSIM_NPARAM = 6, DSIM_MAX_OBS = 33 };
 
 /* buffer ids for dsim_buffer() */
 enum {
-    DSIM_BUF_STATE = 0,      /* real  [24][ld]                                   data.qpos/qvel/act/sensordata */
-    DSIM_BUF_NUM_STEPS = 1,  /* int32 [N]                                        BaseDroneEnv.num_steps (:110) */
-    DSIM_BUF_OBS = 2,        /* real  [N][obs_dim] or [obs_dim][ld]              vector_step()[0] */
+    DSIM_BUF_STATE = 0,      /* real  PAGED 24 rows of the read-write page       data.qpos/qvel/act/sensordata */
+    DSIM_BUF_NUM_STEPS = 1,  /* int   PAGED 1 row (int32 | int64 as `real`)      BaseDroneEnv.num_steps (:110) */
+    DSIM_BUF_OBS = 2,        /* real  [N][obs_dim] policy-ready rows             vector_step()[0] */
     DSIM_BUF_REWARD = 3,     /* real  [N]                                        vector_step()[1] */
     DSIM_BUF_TRUNCATED = 4,  /* uint8 [N]                                        vector_step()[3] */
-    DSIM_BUF_PARAMS = 5,     /* real  [6][ld] raw drone_params                   BaseDroneEnv.drone_params (:117) */
-    DSIM_BUF_CONSTS = 6,     /* real  [13][ld] compiled rigid-body constants     (MjModel of env_gen.py) */
-    DSIM_BUF_REFERENCE = 7,  /* real  [4][ld] per-env setpoint (xyz offset from start_pos, yaw); only if per_env_reference */
+    DSIM_BUF_PARAMS = 5,     /* real  PAGED 6 rows of the read-only page         BaseDroneEnv.drone_params (:117) */
+    DSIM_BUF_CONSTS = 6,     /* real  PAGED 13 rows of the read-only page        (MjModel of env_gen.py) */
+    DSIM_BUF_REFERENCE = 7,  /* real  PAGED 4 rows: per-env setpoint (xyz offset from start_pos, yaw); only if per_env_reference */
     DSIM_BUF_RESET_COUNT = 8,/* uint32[N] Philox epoch of each env's reset stream */
     DSIM_BUF_STATES33 = 9,   /* real  [N][33|29] get_drone_states() rows, filled by dsim_compute_states */
-    DSIM_BUF_EP_RETURN = 10, /* real  [N] running return of the current episode */
+    DSIM_BUF_EP_RETURN = 10, /* real  PAGED 1 row: running return of the current episode */
     DSIM_BUF_STATS = 11      /* double[8]: sum_return, sum_length, n_episodes, n_nonfinite, n_near_ground, 0,0,0 */
 };
-enum { DSIM_DT_F32 = 0, DSIM_DT_F64 = 1, DSIM_DT_I32 = 2, DSIM_DT_U8 = 3, DSIM_DT_U32 = 4 };
+enum { DSIM_DT_F32 = 0, DSIM_DT_F64 = 1, DSIM_DT_I32 = 2, DSIM_DT_U8 = 3, DSIM_DT_U32 = 4, DSIM_DT_I64 = 5 };
 
 /* observation variants: class names of environments/observation_wrappers.py (ids == oracle OBS_IDS) */
 enum {
@@ -74,7 +77,7 @@ typedef struct DsimConfig {
     int32_t round_precision;       /* 1: apply mjcf precision=5 ("%.5g") to every model attribute (env_gen.py:129) */
     double frequency;              /* config['frequency'] -> timestep = 1/frequency (env_gen.py:82) */
     int32_t obs_id, reward_id;     /* wrapper class / config['reward_fcn'] resolved by name */
-    int32_t obs_layout;            /* DSIM_LAYOUT_* */
+    int32_t reserved0;             /* must be 0 */
     int32_t per_env_reference;     /* 0: one reference shared by all drones (BaseDroneEnv.py:80) */
     int32_t auto_reset;            /* 1: truncated envs are re-sampled inside the step kernel (native loop) */
     int32_t random_start_pos, random_params;
@@ -119,7 +122,7 @@ int dsim_step_host(DsimHandle *h, const float *actions_host /*[N][4]*/, float *o
 
 /* -- reference / setpoints: self.reference (:80), control_reference (:151-172) */
 int dsim_set_reference(DsimHandle *h, const double ref[4]);
-int dsim_control_reference(DsimHandle *h, const void *axes_dev /* real [4][ld] joystick axes x,y,z,yaw after sign flips */, void *stream);
+int dsim_control_reference(DsimHandle *h, const void *axes_dev /* real [4][ld] DENSE rows: joystick axes x,y,z,yaw after sign flips */, void *stream);
 
 /* -- state access for callers that poke MjData (BaseDroneEnv.py:342-346) and for parity tests.
  *    Host arrays use the reference's drone-major layout: qpos [N][9|7] (ABSOLUTE positions), qvel [N][8|6], act [N][4], sensordata [N][3] */
@@ -127,8 +130,9 @@ int dsim_set_state(DsimHandle *h, const double *qpos, const double *qvel, const 
 int dsim_get_state(DsimHandle *h, double *qpos, double *qvel, double *act, double *sensordata, int32_t *num_steps);
 int dsim_compute_states(DsimHandle *h, void *stream);                           /* get_drone_states (:357-380) -> DSIM_BUF_STATES33 */
 
-/* -- zero-copy views for the policy */
-int dsim_buffer(DsimHandle *h, int buf_id, void **dev_ptr, int64_t *rows, int64_t *cols, int64_t *ld, int32_t *dtype);
+/* -- zero-copy views for the policy.  *page_rows == 0: dense row-major, element (r, c) = ptr[r * ld + c].
+ *    *page_rows == R > 0: PAGED (see the layout note above), element (row r, env i) = ptr[(i / 32) * R * 32 + r * 32 + i % 32]. */
+int dsim_buffer(DsimHandle *h, int buf_id, void **dev_ptr, int64_t *rows, int64_t *cols, int64_t *ld, int32_t *dtype, int64_t *page_rows);
 int dsim_stats(DsimHandle *h, double out[8], int reset);                        /* episode statistics (device sync) */
 int dsim_sync(DsimHandle *h, void *stream);
 

@@ -11,11 +11,11 @@ LIB_PATH = os.environ.get("DSIM_LIB") or os.path.join(_HERE, "libdronesim_b200.s
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ESHAPE = 0, -1, -2, -3, -4, -5
 FP32, FP64 = 0, 1
-LAYOUT_ENV_MAJOR, LAYOUT_SOA = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
+TILE = 32                     # envs per page (include/dronesim_b200.h: PAGED buffers)
 (BUF_STATE, BUF_NUM_STEPS, BUF_OBS, BUF_REWARD, BUF_TRUNCATED, BUF_PARAMS, BUF_CONSTS, BUF_REFERENCE,
  BUF_RESET_COUNT, BUF_STATES33, BUF_EP_RETURN, BUF_STATS) = range(12)
-DT_F32, DT_F64, DT_I32, DT_U8, DT_U32 = range(5)
+DT_F32, DT_F64, DT_I32, DT_U8, DT_U32, DT_I64 = range(6)
 
 EXPORTS = [
     "dsim_abi_version", "dsim_create", "dsim_destroy", "dsim_last_error", "dsim_obs_dim", "dsim_regen_params",
@@ -31,7 +31,7 @@ class DsimConfig(C.Structure):
         ("struct_size", C.c_int32), ("abi_version", C.c_int32), ("num_envs", C.c_int32), ("precision", C.c_int32),
         ("env_id_offset", C.c_int64), ("seed", C.c_uint32), ("pendulum", C.c_int32), ("frame_skip", C.c_int32),
         ("round_precision", C.c_int32), ("frequency", C.c_double), ("obs_id", C.c_int32), ("reward_id", C.c_int32),
-        ("obs_layout", C.c_int32), ("per_env_reference", C.c_int32), ("auto_reset", C.c_int32),
+        ("reserved0", C.c_int32), ("per_env_reference", C.c_int32), ("auto_reset", C.c_int32),
         ("random_start_pos", C.c_int32), ("random_params", C.c_int32),
         ("reference", C.c_double * 4), ("start_pos", C.c_double * 4), ("max_distance", C.c_double),
         ("max_steps", C.c_int64), ("max_pos_offset", C.c_double),
@@ -86,7 +86,7 @@ def load():
     L.dsim_get_state.argtypes = [vp, dp, dp, dp, dp, C.POINTER(i32)]
     L.dsim_compute_states.argtypes = [vp, vp]
     L.dsim_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
-                              C.POINTER(C.c_int64), C.POINTER(i32)]
+                              C.POINTER(C.c_int64), C.POINTER(i32), C.POINTER(C.c_int64)]
     L.dsim_stats.argtypes = [vp, dp, C.c_int]
     L.dsim_sync.argtypes = [vp, vp]
     L.dsim_launch_count.argtypes = [vp]

@@ -33,10 +33,23 @@ constexpr double kInertiaC = 0.4 * 0.01 * 0.02 * 0.02;   // solid sphere r = 0.0
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kMinVal = 1e-15;        // mjMINVAL
 
-// rows of the SoA state buffer (include/dronesim_b200.h)
+// rows of the per-env state (include/dronesim_b200.h)
 enum { S_POS = 0, S_QUAT = 3, S_HINGE = 7, S_VEL = 9, S_OMEGA = 12, S_HVEL = 15, S_ACT = 17, S_ACC = 21, S_ROWS = 24 };
-// rows of the compiled-constants buffer
+// rows of the compiled constants
 enum { C_MB = 0, C_CZ, C_IBX, C_IBY, C_IBZ, C_MD, C_ZD, C_IDX, C_IDZ, C_FS, C_F, C_KQ, C_INVTAU, C_ROWS };
+
+// ------------------------------------------------------------------ paged env memory (include/dronesim_b200.h)
+// Env data lives in PAGES of kTile = 32 envs (one warp): page p of a buffer with R rows is the contiguous block
+// [R][32] at base + p * R * 32, element (row r, env i) at (i / 32) * R * 32 + r * 32 + (i % 32).  One page is one
+// contiguous 1D bulk-copy (TMA, cp.async.bulk) between HBM and a warp's shared-memory slot; inside the slot every
+// row is a conflict-free 128-byte (FP32) line and each row is reached with an immediate offset from one base.
+constexpr int kTile = 32;
+// read-write page: MuJoCo state (qpos, qvel, act, sensordata) + BaseDroneEnv.num_steps + running episode return
+enum { RW_NUM_STEPS = S_ROWS, RW_EP_RETURN = S_ROWS + 1, RW_ROWS = S_ROWS + 2 };
+// read-only page: compiled rigid-body constants + raw drone_params (rewritten only by regen / set_params)
+enum { RO_CONSTS = 0, RO_PARAMS = C_ROWS, RO_ROWS = C_ROWS + 6 };
+enum { REF_ROWS = 4 };                        // per-env setpoint page (x, y, z offsets from start_pos, yaw)
+DSIM_HD size_t page_elem(int rows, int r, int i) { return (size_t)(i >> 5) * (size_t)(rows * kTile) + (size_t)(r * kTile + (i & 31)); }
 
 // ------------------------------------------------------------------ scalar helpers
 template <typename T> DSIM_DEV T sqrt_(T x) { if constexpr (std::is_same<T, float>::value) return sqrtf(x); else return sqrt(x); }

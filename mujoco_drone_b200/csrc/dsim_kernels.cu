@@ -3,7 +3,6 @@
 // physics, state extraction, termination, reward, observation, episode statistics and (optionally) the
 // Philox reset of truncated envs all happen in ONE kernel launch per env-step.  There is no CPU fallback: every
 // entry point either launches on the GPU or returns an error code.
-#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -30,19 +29,21 @@ template <typename T, bool PEND>
 __global__ void __launch_bounds__(kBlock) forward_kernel(const KParams<T> p, int refresh_obs) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= p.n) return;
-    EnvState<T> s = load_state(p, i);
-    const EnvConsts<T> c = load_consts(p, i);
+    T *col = p.rw + page_elem(RW_ROWS, 0, i);
+    const T *ro_col = p.ro + page_elem(RO_ROWS, 0, i);
+    EnvState<T> s = load_state(col);
+    const EnvConsts<T> c = load_consts(p, ro_col);
     const T ctrl[4] = {T(0), T(0), T(0), T(0)};
     substep<T, PEND, false>(s, c, ctrl, p.h);
-    T *b = p.state + i;
-    b[21 * (size_t)p.ld] = s.acc.x; b[22 * (size_t)p.ld] = s.acc.y; b[23 * (size_t)p.ld] = s.acc.z;
+    col[21 * kTile] = s.acc.x; col[22 * kTile] = s.acc.y; col[23 * kTile] = s.acc.z;
     if (refresh_obs) {
         V3<T> ref_off; T ref_yaw; double ref64[3];
-        load_ref(p, i, ref_off, ref_yaw, ref64);
+        load_ref(p, p.refp ? p.refp + page_elem(REF_ROWS, 0, i) : nullptr, ref_off, ref_yaw, ref64);
         T prm[6];
-        load_params(p, i, prm);
+        load_params(p, ro_col, prm);
         const PostState<T> ps = post_state(s, ref_off, ref_yaw);
-        emit_obs<T, PEND>(p.obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, obs_writer(p, i));
+        ObsWriter<T, 1> w; w.base = p.obs + (size_t)i * p.obs_dim; w.stride = 1;
+        emit_obs<T, PEND>(p.obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
     }
 }
 
@@ -53,13 +54,14 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const KParams<T> p, const
     if (single >= 0) { if (i != 0) return; i = single; }
     if (i >= p.n) return;
     if (mask && !mask[i]) return;
-    EnvState<T> s = load_state(p, i);
+    T *col = p.rw + page_elem(RW_ROWS, 0, i);
+    EnvState<T> s = load_state(col);
     const unsigned rcnt = first ? 0u : p.reset_count[i] + 1u;
     sample_state<T, PEND>(s, p.rc, p.seed, p.env_base + (unsigned)i, rcnt);
     p.reset_count[i] = rcnt;
-    p.num_steps[i] = 0;
-    p.ep_return[i] = T(0);
-    store_state(p, i, s);
+    col[RW_NUM_STEPS * kTile] = int_to_slot<T>(0);
+    col[RW_EP_RETURN * kTile] = T(0);
+    store_state(col, s);
 }
 
 // get_drone_states (:357-380) for every env -> [n][33|29]
@@ -67,11 +69,11 @@ template <typename T, bool PEND>
 __global__ void __launch_bounds__(kBlock) states_kernel(const KParams<T> p, T *out, int width) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= p.n) return;
-    const EnvState<T> s = load_state(p, i);
+    const EnvState<T> s = load_state(p.rw + page_elem(RW_ROWS, 0, i));
     V3<T> ref_off; T ref_yaw; double ref64[3];
-    load_ref(p, i, ref_off, ref_yaw, ref64);
+    load_ref(p, p.refp ? p.refp + page_elem(REF_ROWS, 0, i) : nullptr, ref_off, ref_yaw, ref64);
     T prm[6];
-    load_params(p, i, prm);
+    load_params(p, p.ro + page_elem(RO_ROWS, 0, i), prm);
     const PostState<T> ps = post_state(s, ref_off, ref_yaw);
     ObsWriter<T> w; w.base = out + (size_t)i * width; w.stride = 1;
     emit_state_row<T, PEND>(s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
@@ -92,24 +94,26 @@ __global__ void draw_params_kernel(int n, int ld, double *params64, unsigned see
     if (!pendulum) { v[4] = 0; v[5] = 0; }                      // self.pendulum * pendulum_lens[i] (:212-213)
     for (int k = 0; k < 6; k++) params64[(size_t)k * ld + i] = v[k];
 }
-// env_gen + MuJoCo compile on device
+// env_gen + MuJoCo compile on device: FP64 drone_params [6][ld] -> read-only page (constants + raw params)
 template <typename T>
-__global__ void compile_kernel(int n, int ld, const double *params64, T *params, T *consts, int pendulum, int rounding) {
+__global__ void compile_kernel(int n, int ld, const double *params64, T *ro, int pendulum, int rounding) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double p[6], c[C_ROWS];
     for (int k = 0; k < 6; k++) p[k] = params64[(size_t)k * ld + i];
     compile_consts(p, pendulum != 0, rounding != 0, c);
-    for (int k = 0; k < 6; k++) params[(size_t)k * ld + i] = (T)p[k];
-    for (int k = 0; k < C_ROWS; k++) consts[(size_t)k * ld + i] = (T)c[k];
+    T *col = ro + page_elem(RO_ROWS, 0, i);
+    for (int k = 0; k < C_ROWS; k++) col[(RO_CONSTS + k) * kTile] = (T)c[k];
+    for (int k = 0; k < 6; k++) col[(RO_PARAMS + k) * kTile] = (T)p[k];
 }
-// control_reference (:151-172) per env: axes are the already sign-flipped joystick values (x, -y, -z, -yaw)
+// control_reference (:151-172) per env: axes [4][ld] are the already sign-flipped joystick values (x, -y, -z, -yaw)
 template <typename T>
-__global__ void control_reference_kernel(int n, int ld, const T *axes, T *ref) {
+__global__ void control_reference_kernel(int n, int ld, const T *axes, T *refp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    T *col = refp + page_elem(REF_ROWS, 0, i);
     T pert[4], r[4];
-    for (int k = 0; k < 4; k++) { pert[k] = axes[(size_t)k * ld + i]; r[k] = ref[(size_t)k * ld + i]; }
+    for (int k = 0; k < 4; k++) { pert[k] = axes[(size_t)k * ld + i]; r[k] = col[k * kTile]; }
     const bool xy = sqrt_(pert[0] * pert[0] + pert[1] * pert[1]) > T(0.2), zy = sqrt_(pert[2] * pert[2] + pert[3] * pert[3]) > T(0.2);
     const T lim[3] = {T(5), T(5), T(6)};
     for (int k = 0; k < 4; k++) {
@@ -120,12 +124,13 @@ __global__ void control_reference_kernel(int n, int ld, const T *axes, T *ref) {
     }
     r[3] = wrap_pi(r[3]);
     for (int k = 0; k < 3; k++) r[k] = clamp_(r[k], -lim[k], lim[k]);      // clip to start_pos +- (5,5,6); ref rows are offsets
-    for (int k = 0; k < 4; k++) ref[(size_t)k * ld + i] = r[k];
+    for (int k = 0; k < 4; k++) col[k * kTile] = r[k];
 }
-template <typename T> __global__ void fill_rows_kernel(int n, int ld, T *dst, int row0, int nrows, T value) {
+// one row of a paged buffer := value, for the first n envs
+template <typename T> __global__ void fill_row_kernel(int n, T *base, int page_rows, int row, T value) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    for (int k = 0; k < nrows; k++) dst[(size_t)(row0 + k) * ld + i] = value;
+    base[page_elem(page_rows, row, i)] = value;
 }
 
 }  // namespace
@@ -133,17 +138,16 @@ template <typename T> __global__ void fill_rows_kernel(int n, int ld, T *dst, in
 // ====================================================================== host side
 struct DsimHandle {
     DsimConfig cfg;
-    int device, n, ld, obs_dim, state_width;
+    int device, n, ld, npages, obs_dim, state_width;
     size_t rs;                        // sizeof(real)
-    void *state, *obs, *reward, *ep_return, *params, *consts, *ref_env, *states33, *actions_stage;
+    void *rw, *ro, *refp, *obs, *reward, *states33, *actions_stage;
     double *params64, *stats, *center_hw;
-    int *num_steps;
     unsigned *reset_count;
     unsigned char *trunc;
     int per_env_consts;
     double uconst[C_ROWS], uparams[6];
     double h;
-    int first_reset_done;
+    int first_reset_done, smem_configured;
     int64_t launches;
     char err[512];
 };
@@ -177,17 +181,17 @@ template <typename T> static KParams<T> make_params(const DsimHandle *h, const v
     KParams<T> p;
     memset(&p, 0, sizeof p);
     const DsimConfig &c = h->cfg;
-    p.n = h->n; p.ld = h->ld;
-    p.state = (T *)h->state; p.num_steps = h->num_steps; p.reset_count = h->reset_count;
-    p.consts = (const T *)h->consts; p.params = (const T *)h->params;
-    p.ref_env = c.per_env_reference ? (T *)h->ref_env : nullptr;
-    p.obs = (T *)h->obs; p.reward = (T *)h->reward; p.ep_return = (T *)h->ep_return;
+    p.n = h->n; p.npages = h->npages;
+    p.rw = (T *)h->rw; p.ro = (const T *)h->ro; p.reset_count = h->reset_count;
+    p.refp = c.per_env_reference ? (T *)h->refp : nullptr;
+    p.obs = (T *)h->obs; p.reward = (T *)h->reward;
     p.trunc = h->trunc; p.stats = h->stats; p.actions = (const T *)actions;
     for (int k = 0; k < C_ROWS; k++) p.uconst[k] = (T)h->uconst[k];
     for (int k = 0; k < 6; k++) p.uparams[k] = (T)h->uparams[k];
     p.per_env_consts = h->per_env_consts; p.auto_reset = c.auto_reset; p.obs_id = c.obs_id; p.reward_id = c.reward_id;
-    p.obs_layout = c.obs_layout; p.obs_dim = h->obs_dim; p.frame_skip = c.frame_skip;
+    p.obs_dim = h->obs_dim; p.frame_skip = c.frame_skip;
     p.max_steps = (int)(c.max_steps > 2147483647LL ? 2147483647LL : c.max_steps);
+    p.smem_per_warp = slot_bytes(h->obs_dim, (int)sizeof(T));
     p.h = (T)h->h; p.max_distance_t = (T)c.max_distance; p.max_distance = c.max_distance;
     for (int k = 0; k < 3; k++) {
         p.ref_off[k] = (T)(c.reference[k] - c.start_pos[k]);
@@ -235,8 +239,12 @@ static int validate(const DsimConfig *c) {
             return fail(nullptr, DSIM_EUNSUPPORTED, "pendulum=False supports only rewards that do not index pendulum state%s", "");
     }
     if (c->frame_skip < 1 || c->frequency <= 0) return fail(nullptr, DSIM_EINVAL, "frame_skip >= 1 and frequency > 0 required%s", "");
-    if (c->obs_layout != DSIM_LAYOUT_ENV_MAJOR && c->obs_layout != DSIM_LAYOUT_SOA) return fail(nullptr, DSIM_EINVAL, "bad obs_layout%s", "");
     return DSIM_OK;
+}
+
+template <typename T> static void fill_row(DsimHandle *h, void *base, int page_rows, int row, double value) {
+    fill_row_kernel<T><<<(h->n + 255) / 256, 256>>>(h->n, (T *)base, page_rows, row, (T)value);
+    h->launches++;
 }
 
 extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) {
@@ -252,7 +260,8 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
     DsimHandle *h = new (std::nothrow) DsimHandle();
     if (!h) return fail(nullptr, DSIM_ENOMEM, "out of host memory%s", "");
     memset(h, 0, sizeof *h);
-    h->cfg = *cfg; h->device = device; h->n = cfg->num_envs; h->ld = (cfg->num_envs + 31) / 32 * 32;
+    h->cfg = *cfg; h->device = device; h->n = cfg->num_envs;
+    h->npages = (cfg->num_envs + kTile - 1) / kTile; h->ld = h->npages * kTile;
     h->rs = cfg->precision == DSIM_FP32 ? 4 : 8;
     h->obs_dim = dsim_obs_dim(cfg->obs_id, cfg->pendulum);
     h->state_width = cfg->pendulum ? 33 : 29;
@@ -265,19 +274,16 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
     } while (0)
     if ((e = cudaSetDevice(device)) != cudaSuccess) { delete h; return fail(nullptr, DSIM_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); }
     const size_t ld = h->ld, n = h->n, rs = h->rs;
-    ALLOC(h->state, DSIM_NSTATE_ROWS * ld * rs);
+    ALLOC(h->rw, (size_t)RW_ROWS * ld * rs);
+    ALLOC(h->ro, (size_t)RO_ROWS * ld * rs);
+    ALLOC(h->refp, (size_t)REF_ROWS * ld * rs);
     ALLOC(h->obs, (size_t)DSIM_MAX_OBS * ld * rs);
     ALLOC(h->reward, ld * rs);
-    ALLOC(h->ep_return, ld * rs);
-    ALLOC(h->params, 6 * ld * rs);
-    ALLOC(h->consts, C_ROWS * ld * rs);
-    ALLOC(h->ref_env, 4 * ld * rs);
     ALLOC(h->states33, (size_t)h->state_width * n * rs);
     ALLOC(h->actions_stage, 4 * ld * rs);
     ALLOC(h->params64, 6 * ld * sizeof(double));
     ALLOC(h->stats, 8 * sizeof(double));
     ALLOC(h->center_hw, 12 * sizeof(double));
-    ALLOC(h->num_steps, ld * sizeof(int));
     ALLOC(h->reset_count, ld * sizeof(unsigned));
     ALLOC(h->trunc, ld);
 #undef ALLOC
@@ -285,20 +291,14 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
     for (int k = 0; k < 6; k++) { chw[k] = cfg->param_center[k]; chw[6 + k] = cfg->param_halfwidth[k]; }
     CK(cudaMemcpy(h->center_hw, chw, sizeof chw, cudaMemcpyHostToDevice));
     // quaternion rows start as identity (MjData qpos0 of a free joint), per-env reference = shared reference
-    {
-        const int grid = (h->n + 255) / 256;
-        if (h->rs == 4) {
-            fill_rows_kernel<float><<<grid, 256>>>(h->n, h->ld, (float *)h->state, S_QUAT, 1, 1.0f);
-            for (int k = 0; k < 4; k++)
-                fill_rows_kernel<float><<<grid, 256>>>(h->n, h->ld, (float *)h->ref_env, k, 1, (float)(k < 3 ? cfg->reference[k] - cfg->start_pos[k] : cfg->reference[3]));
-        } else {
-            fill_rows_kernel<double><<<grid, 256>>>(h->n, h->ld, (double *)h->state, S_QUAT, 1, 1.0);
-            for (int k = 0; k < 4; k++)
-                fill_rows_kernel<double><<<grid, 256>>>(h->n, h->ld, (double *)h->ref_env, k, 1, k < 3 ? cfg->reference[k] - cfg->start_pos[k] : cfg->reference[3]);
-        }
-        h->launches += 5;
-        CK(cudaGetLastError());
+    for (int k = 0; k < 5; k++) {
+        const int is_ref = k < 4;
+        const double v = !is_ref ? 1.0 : (k < 3 ? cfg->reference[k] - cfg->start_pos[k] : cfg->reference[3]);
+        void *base = is_ref ? h->refp : h->rw;
+        const int rows = is_ref ? (int)REF_ROWS : (int)RW_ROWS, row = is_ref ? k : (int)S_QUAT;
+        if (h->rs == 4) fill_row<float>(h, base, rows, row, v); else fill_row<double>(h, base, rows, row, v);
     }
+    CK(cudaGetLastError());
     rc = dsim_regen_params(h, 0, nullptr);
     if (rc) { snprintf(g_create_err, 512, "%s", h->err); dsim_destroy(h); return rc; }
     CK(cudaDeviceSynchronize());
@@ -309,16 +309,16 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
 extern "C" void dsim_destroy(DsimHandle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    void *ptrs[] = {h->state, h->obs, h->reward, h->ep_return, h->params, h->consts, h->ref_env, h->states33, h->actions_stage,
-                    h->params64, h->stats, h->center_hw, h->num_steps, h->reset_count, h->trunc};
+    void *ptrs[] = {h->rw, h->ro, h->refp, h->obs, h->reward, h->states33, h->actions_stage,
+                    h->params64, h->stats, h->center_hw, h->reset_count, h->trunc};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete h;
 }
 
 static int compile_on_device(DsimHandle *h, cudaStream_t st) {
     const int grid = (h->n + 127) / 128;
-    if (h->rs == 4) compile_kernel<float><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (float *)h->params, (float *)h->consts, h->cfg.pendulum, h->cfg.round_precision);
-    else compile_kernel<double><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (double *)h->params, (double *)h->consts, h->cfg.pendulum, h->cfg.round_precision);
+    if (h->rs == 4) compile_kernel<float><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (float *)h->ro, h->cfg.pendulum, h->cfg.round_precision);
+    else compile_kernel<double><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (double *)h->ro, h->cfg.pendulum, h->cfg.round_precision);
     h->launches++;
     CK(cudaGetLastError());
     return DSIM_OK;
@@ -372,19 +372,24 @@ extern "C" int dsim_get_params(DsimHandle *h, double *out) {
     return DSIM_OK;
 }
 
+// whole paged buffer -> host vector
+template <typename T> static cudaError_t fetch_pages(const DsimHandle *h, const void *dev, int rows, std::vector<T> &t) {
+    t.resize((size_t)rows * h->ld);
+    return cudaMemcpy(t.data(), dev, t.size() * sizeof(T), cudaMemcpyDeviceToHost);
+}
+
 extern "C" int dsim_get_consts(DsimHandle *h, double *out) {
     if (!h || !out) return DSIM_EINVAL;
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
-    const size_t cnt = (size_t)C_ROWS * h->ld;
     if (h->rs == 4) {
-        std::vector<float> t(cnt);
-        CK(cudaMemcpy(t.data(), h->consts, cnt * 4, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < h->n; i++) for (int k = 0; k < C_ROWS; k++) out[(size_t)i * C_ROWS + k] = t[(size_t)k * h->ld + i];
+        std::vector<float> t;
+        CK(fetch_pages(h, h->ro, RO_ROWS, t));
+        for (int i = 0; i < h->n; i++) for (int k = 0; k < C_ROWS; k++) out[(size_t)i * C_ROWS + k] = t[page_elem(RO_ROWS, RO_CONSTS + k, i)];
     } else {
-        std::vector<double> t(cnt);
-        CK(cudaMemcpy(t.data(), h->consts, cnt * 8, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < h->n; i++) for (int k = 0; k < C_ROWS; k++) out[(size_t)i * C_ROWS + k] = t[(size_t)k * h->ld + i];
+        std::vector<double> t;
+        CK(fetch_pages(h, h->ro, RO_ROWS, t));
+        for (int i = 0; i < h->n; i++) for (int k = 0; k < C_ROWS; k++) out[(size_t)i * C_ROWS + k] = t[page_elem(RO_ROWS, RO_CONSTS + k, i)];
     }
     return DSIM_OK;
 }
@@ -423,33 +428,50 @@ extern "C" int dsim_reset_at(DsimHandle *h, int index, void *stream) {
 extern "C" int dsim_zero_act(DsimHandle *h, void *stream) {
     if (!h) return DSIM_EINVAL;
     CK(cudaSetDevice(h->device));
-    CK(cudaMemsetAsync((char *)h->state + (size_t)S_ACT * h->ld * h->rs, 0, (size_t)7 * h->ld * h->rs, (cudaStream_t)stream));   // act + sensordata
+    for (int r = S_ACT; r < S_ROWS; r++) {                                   // act + sensordata of a fresh MjData
+        if (h->rs == 4) fill_row_kernel<float><<<(h->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->n, (float *)h->rw, RW_ROWS, r, 0.0f);
+        else fill_row_kernel<double><<<(h->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->n, (double *)h->rw, RW_ROWS, r, 0.0);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
     return DSIM_OK;
 }
 
 // step-kernel dispatch: compile-time specialisations for the BASELINE configs, generic kernel otherwise
-template <typename T> static void launch_step(const DsimHandle *h, const KParams<T> &kp, cudaStream_t st) {
-    const int grid = (h->n + kStepBlock - 1) / kStepBlock;
-    if (!h->cfg.pendulum) { step_kernel<T, false, -1, -1><<<grid, kStepBlock, 0, st>>>(kp); return; }
+template <typename K> static cudaError_t launch_one(K kernel, int grid, unsigned smem, cudaStream_t st, const void *kp_ptr, bool configure) {
+    if (configure) {
+        // opt in once to the largest slot any handle can ask for (the attribute is per function, not per handle)
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(slot_bytes(DSIM_MAX_OBS, 8) * kStepWarps));
+        if (e != cudaSuccess) return e;
+    }
+    void *args[] = {const_cast<void *>(kp_ptr)};
+    return cudaLaunchKernel((const void *)kernel, dim3(grid), dim3(kStepBlock), args, smem, st);
+}
+template <typename T> static cudaError_t launch_step(const DsimHandle *h, const KParams<T> &kp, cudaStream_t st, bool configure) {
+    const int grid = (h->npages + kStepWarps - 1) / kStepWarps;
+    const unsigned smem = kp.smem_per_warp * kStepWarps;
+    if (!h->cfg.pendulum) return launch_one(step_kernel<T, false, -1, -1>, grid, smem, st, &kp, configure);
     if constexpr (std::is_same<T, float>::value) {
         const int o = kp.obs_id, r = kp.reward_id;
-        if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2) { step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2><<<grid, kStepBlock, 0, st>>>(kp); return; }   // C4 / C5
-        if (o == DSIM_OBS_LOCAL_RPY && r == 1) { step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1><<<grid, kStepBlock, 0, st>>>(kp); return; }                 // C3
-        if (o == DSIM_OBS_BASE && r == 0) { step_kernel<float, true, DSIM_OBS_BASE, 0><<<grid, kStepBlock, 0, st>>>(kp); return; }                           // C2
+        if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2) return launch_one(step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2>, grid, smem, st, &kp, configure);   // C4 / C5
+        if (o == DSIM_OBS_LOCAL_RPY && r == 1) return launch_one(step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1>, grid, smem, st, &kp, configure);                 // C3
+        if (o == DSIM_OBS_BASE && r == 0) return launch_one(step_kernel<float, true, DSIM_OBS_BASE, 0>, grid, smem, st, &kp, configure);                           // C2
     }
-    step_kernel<T, true, -1, -1><<<grid, kStepBlock, 0, st>>>(kp);
+    return launch_one(step_kernel<T, true, -1, -1>, grid, smem, st, &kp, configure);
 }
 static int step_impl(DsimHandle *h, const void *actions_dev, void *stream, int eval_only) {
     CK(cudaSetDevice(h->device));
+    const bool configure = !h->smem_configured;
     if (h->cfg.precision == DSIM_FP32) {
         auto kp = make_params<float>(h, actions_dev);
         if (eval_only) { kp.frame_skip = 0; kp.eval_only = 1; }
-        launch_step<float>(h, kp, (cudaStream_t)stream);
+        CK(launch_step<float>(h, kp, (cudaStream_t)stream, configure));
     } else {
         auto kp = make_params<double>(h, actions_dev);
         if (eval_only) { kp.frame_skip = 0; kp.eval_only = 1; }
-        launch_step<double>(h, kp, (cudaStream_t)stream);
+        CK(launch_step<double>(h, kp, (cudaStream_t)stream, configure));
     }
+    h->smem_configured = 1;
     h->launches++;
     CK(cudaGetLastError());
     return DSIM_OK;
@@ -468,7 +490,6 @@ extern "C" int dsim_evaluate(DsimHandle *h, const void *actions_dev, void *strea
 extern "C" int dsim_step_host(DsimHandle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *trunc_host, void *stream) {
     if (!h || !actions_host) return DSIM_EINVAL;
     if (h->cfg.precision != DSIM_FP32) return fail(h, DSIM_EUNSUPPORTED, "dsim_step_host moves float32 buffers; use dsim_step with precision=FP64%s", "");
-    if (h->cfg.obs_layout != DSIM_LAYOUT_ENV_MAJOR && obs_host) return fail(h, DSIM_EUNSUPPORTED, "dsim_step_host needs DSIM_LAYOUT_ENV_MAJOR%s", "");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemcpyAsync(h->actions_stage, actions_host, (size_t)h->n * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -492,71 +513,79 @@ extern "C" int dsim_control_reference(DsimHandle *h, const void *axes_dev, void 
     if (!h->cfg.per_env_reference) return fail(h, DSIM_EUNSUPPORTED, "dsim_control_reference needs per_env_reference=1%s", "");
     CK(cudaSetDevice(h->device));
     const int grid = (h->n + 127) / 128;
-    if (h->rs == 4) control_reference_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(h->n, h->ld, (const float *)axes_dev, (float *)h->ref_env);
-    else control_reference_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(h->n, h->ld, (const double *)axes_dev, (double *)h->ref_env);
+    if (h->rs == 4) control_reference_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(h->n, h->ld, (const float *)axes_dev, (float *)h->refp);
+    else control_reference_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(h->n, h->ld, (const double *)axes_dev, (double *)h->refp);
     h->launches++;
     CK(cudaGetLastError());
     return DSIM_OK;
 }
 
+template <typename T> static T int_slot(int v) {
+    T out;
+    if (sizeof(T) == 4) { int32_t x = v; memcpy(&out, &x, 4); } else { int64_t x = v; memcpy(&out, &x, 8); }
+    return out;
+}
+template <typename T> static int slot_int(T v) {
+    if (sizeof(T) == 4) { int32_t x; memcpy(&x, &v, 4); return x; }
+    int64_t x; memcpy(&x, &v, 8); return (int)x;
+}
 template <typename T>
-static void pack_state(const DsimHandle *h, std::vector<T> &t, const double *qpos, const double *qvel, const double *act) {
+static void pack_state(const DsimHandle *h, std::vector<T> &t, const double *qpos, const double *qvel, const double *act, const int32_t *num_steps) {
     const int nq = h->cfg.pendulum ? 9 : 7, nv = h->cfg.pendulum ? 8 : 6;
-    const size_t ld = h->ld;
     for (int i = 0; i < h->n; i++) {
+        T *c = t.data() + page_elem(RW_ROWS, 0, i);
         if (qpos) {
             const double *q = qpos + (size_t)i * nq;
-            for (int k = 0; k < 3; k++) t[(size_t)k * ld + i] = (T)(q[k] - h->cfg.start_pos[k]);
-            for (int k = 0; k < 4; k++) t[(size_t)(S_QUAT + k) * ld + i] = (T)q[3 + k];
-            if (nq == 9) { t[(size_t)S_HINGE * ld + i] = (T)q[7]; t[(size_t)(S_HINGE + 1) * ld + i] = (T)q[8]; }
+            for (int k = 0; k < 3; k++) c[k * kTile] = (T)(q[k] - h->cfg.start_pos[k]);
+            for (int k = 0; k < 4; k++) c[(S_QUAT + k) * kTile] = (T)q[3 + k];
+            if (nq == 9) { c[S_HINGE * kTile] = (T)q[7]; c[(S_HINGE + 1) * kTile] = (T)q[8]; }
         }
         if (qvel) {
             const double *v = qvel + (size_t)i * nv;
-            for (int k = 0; k < 6; k++) t[(size_t)(S_VEL + k) * ld + i] = (T)v[k];
-            if (nv == 8) { t[(size_t)S_HVEL * ld + i] = (T)v[6]; t[(size_t)(S_HVEL + 1) * ld + i] = (T)v[7]; }
+            for (int k = 0; k < 6; k++) c[(S_VEL + k) * kTile] = (T)v[k];
+            if (nv == 8) { c[S_HVEL * kTile] = (T)v[6]; c[(S_HVEL + 1) * kTile] = (T)v[7]; }
         }
-        if (act) for (int k = 0; k < 4; k++) t[(size_t)(S_ACT + k) * ld + i] = (T)act[(size_t)i * 4 + k];
+        if (act) for (int k = 0; k < 4; k++) c[(S_ACT + k) * kTile] = (T)act[(size_t)i * 4 + k];
+        if (num_steps) c[RW_NUM_STEPS * kTile] = int_slot<T>(num_steps[i]);
     }
 }
 template <typename T>
-static void unpack_state(const DsimHandle *h, const std::vector<T> &t, double *qpos, double *qvel, double *act, double *sens) {
+static void unpack_state(const DsimHandle *h, const std::vector<T> &t, double *qpos, double *qvel, double *act, double *sens, int32_t *num_steps) {
     const int nq = h->cfg.pendulum ? 9 : 7, nv = h->cfg.pendulum ? 8 : 6;
-    const size_t ld = h->ld;
     for (int i = 0; i < h->n; i++) {
+        const T *c = t.data() + page_elem(RW_ROWS, 0, i);
         if (qpos) {
             double *q = qpos + (size_t)i * nq;
-            for (int k = 0; k < 3; k++) q[k] = h->cfg.start_pos[k] + (double)t[(size_t)k * ld + i];
-            for (int k = 0; k < 4; k++) q[3 + k] = (double)t[(size_t)(S_QUAT + k) * ld + i];
-            if (nq == 9) { q[7] = (double)t[(size_t)S_HINGE * ld + i]; q[8] = (double)t[(size_t)(S_HINGE + 1) * ld + i]; }
+            for (int k = 0; k < 3; k++) q[k] = h->cfg.start_pos[k] + (double)c[k * kTile];
+            for (int k = 0; k < 4; k++) q[3 + k] = (double)c[(S_QUAT + k) * kTile];
+            if (nq == 9) { q[7] = (double)c[S_HINGE * kTile]; q[8] = (double)c[(S_HINGE + 1) * kTile]; }
         }
         if (qvel) {
             double *v = qvel + (size_t)i * nv;
-            for (int k = 0; k < 6; k++) v[k] = (double)t[(size_t)(S_VEL + k) * ld + i];
-            if (nv == 8) { v[6] = (double)t[(size_t)S_HVEL * ld + i]; v[7] = (double)t[(size_t)(S_HVEL + 1) * ld + i]; }
+            for (int k = 0; k < 6; k++) v[k] = (double)c[(S_VEL + k) * kTile];
+            if (nv == 8) { v[6] = (double)c[S_HVEL * kTile]; v[7] = (double)c[(S_HVEL + 1) * kTile]; }
         }
-        if (act) for (int k = 0; k < 4; k++) act[(size_t)i * 4 + k] = (double)t[(size_t)(S_ACT + k) * ld + i];
-        if (sens) for (int k = 0; k < 3; k++) sens[(size_t)i * 3 + k] = (double)t[(size_t)(S_ACC + k) * ld + i];
+        if (act) for (int k = 0; k < 4; k++) act[(size_t)i * 4 + k] = (double)c[(S_ACT + k) * kTile];
+        if (sens) for (int k = 0; k < 3; k++) sens[(size_t)i * 3 + k] = (double)c[(S_ACC + k) * kTile];
+        if (num_steps) num_steps[i] = slot_int<T>(c[RW_NUM_STEPS * kTile]);
     }
 }
 
 extern "C" int dsim_set_state(DsimHandle *h, const double *qpos, const double *qvel, const double *act, const int32_t *num_steps, void *stream) {
     if (!h) return DSIM_EINVAL;
     CK(cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaStreamSynchronize(st));
-    const size_t cnt = (size_t)DSIM_NSTATE_ROWS * h->ld;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
     if (h->rs == 4) {
-        std::vector<float> t(cnt);
-        CK(cudaMemcpy(t.data(), h->state, cnt * 4, cudaMemcpyDeviceToHost));
-        pack_state(h, t, qpos, qvel, act);
-        CK(cudaMemcpy(h->state, t.data(), cnt * 4, cudaMemcpyHostToDevice));
+        std::vector<float> t;
+        CK(fetch_pages(h, h->rw, RW_ROWS, t));
+        pack_state(h, t, qpos, qvel, act, num_steps);
+        CK(cudaMemcpy(h->rw, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
     } else {
-        std::vector<double> t(cnt);
-        CK(cudaMemcpy(t.data(), h->state, cnt * 8, cudaMemcpyDeviceToHost));
-        pack_state(h, t, qpos, qvel, act);
-        CK(cudaMemcpy(h->state, t.data(), cnt * 8, cudaMemcpyHostToDevice));
+        std::vector<double> t;
+        CK(fetch_pages(h, h->rw, RW_ROWS, t));
+        pack_state(h, t, qpos, qvel, act, num_steps);
+        CK(cudaMemcpy(h->rw, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
     }
-    if (num_steps) CK(cudaMemcpy(h->num_steps, num_steps, (size_t)h->n * sizeof(int), cudaMemcpyHostToDevice));
     return DSIM_OK;
 }
 
@@ -564,17 +593,15 @@ extern "C" int dsim_get_state(DsimHandle *h, double *qpos, double *qvel, double 
     if (!h) return DSIM_EINVAL;
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
-    const size_t cnt = (size_t)DSIM_NSTATE_ROWS * h->ld;
     if (h->rs == 4) {
-        std::vector<float> t(cnt);
-        CK(cudaMemcpy(t.data(), h->state, cnt * 4, cudaMemcpyDeviceToHost));
-        unpack_state(h, t, qpos, qvel, act, sens);
+        std::vector<float> t;
+        CK(fetch_pages(h, h->rw, RW_ROWS, t));
+        unpack_state(h, t, qpos, qvel, act, sens, num_steps);
     } else {
-        std::vector<double> t(cnt);
-        CK(cudaMemcpy(t.data(), h->state, cnt * 8, cudaMemcpyDeviceToHost));
-        unpack_state(h, t, qpos, qvel, act, sens);
+        std::vector<double> t;
+        CK(fetch_pages(h, h->rw, RW_ROWS, t));
+        unpack_state(h, t, qpos, qvel, act, sens, num_steps);
     }
-    if (num_steps) CK(cudaMemcpy(num_steps, h->num_steps, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToHost));
     return DSIM_OK;
 }
 
@@ -597,26 +624,25 @@ extern "C" int dsim_compute_states(DsimHandle *h, void *stream) {
     return DSIM_OK;
 }
 
-extern "C" int dsim_buffer(DsimHandle *h, int id, void **ptr, int64_t *rows, int64_t *cols, int64_t *ld, int32_t *dtype) {
-    if (!h || !ptr || !rows || !cols || !ld || !dtype) return DSIM_EINVAL;
-    const int32_t rdt = h->rs == 4 ? DSIM_DT_F32 : DSIM_DT_F64;
+extern "C" int dsim_buffer(DsimHandle *h, int id, void **ptr, int64_t *rows, int64_t *cols, int64_t *ld, int32_t *dtype, int64_t *page_rows) {
+    if (!h || !ptr || !rows || !cols || !ld || !dtype || !page_rows) return DSIM_EINVAL;
+    const int32_t rdt = h->rs == 4 ? DSIM_DT_F32 : DSIM_DT_F64, idt = h->rs == 4 ? DSIM_DT_I32 : DSIM_DT_I64;
     const int64_t n = h->n, L = h->ld;
+    *page_rows = 0;
+    char *rw = (char *)h->rw, *ro = (char *)h->ro;
+    const size_t row_bytes = (size_t)kTile * h->rs;
     switch (id) {
-    case DSIM_BUF_STATE: *ptr = h->state; *rows = DSIM_NSTATE_ROWS; *cols = n; *ld = L; *dtype = rdt; break;
-    case DSIM_BUF_NUM_STEPS: *ptr = h->num_steps; *rows = 1; *cols = n; *ld = L; *dtype = DSIM_DT_I32; break;
-    case DSIM_BUF_OBS:
-        *ptr = h->obs; *dtype = rdt;
-        if (h->cfg.obs_layout == DSIM_LAYOUT_SOA) { *rows = h->obs_dim; *cols = n; *ld = L; }
-        else { *rows = n; *cols = h->obs_dim; *ld = h->obs_dim; }
-        break;
+    case DSIM_BUF_STATE: *ptr = rw; *rows = S_ROWS; *cols = n; *ld = L; *dtype = rdt; *page_rows = RW_ROWS; break;
+    case DSIM_BUF_NUM_STEPS: *ptr = rw + RW_NUM_STEPS * row_bytes; *rows = 1; *cols = n; *ld = L; *dtype = idt; *page_rows = RW_ROWS; break;
+    case DSIM_BUF_EP_RETURN: *ptr = rw + RW_EP_RETURN * row_bytes; *rows = 1; *cols = n; *ld = L; *dtype = rdt; *page_rows = RW_ROWS; break;
+    case DSIM_BUF_CONSTS: *ptr = ro + RO_CONSTS * row_bytes; *rows = C_ROWS; *cols = n; *ld = L; *dtype = rdt; *page_rows = RO_ROWS; break;
+    case DSIM_BUF_PARAMS: *ptr = ro + RO_PARAMS * row_bytes; *rows = 6; *cols = n; *ld = L; *dtype = rdt; *page_rows = RO_ROWS; break;
+    case DSIM_BUF_REFERENCE: *ptr = h->refp; *rows = REF_ROWS; *cols = n; *ld = L; *dtype = rdt; *page_rows = REF_ROWS; break;
+    case DSIM_BUF_OBS: *ptr = h->obs; *rows = n; *cols = h->obs_dim; *ld = h->obs_dim; *dtype = rdt; break;
     case DSIM_BUF_REWARD: *ptr = h->reward; *rows = 1; *cols = n; *ld = L; *dtype = rdt; break;
     case DSIM_BUF_TRUNCATED: *ptr = h->trunc; *rows = 1; *cols = n; *ld = L; *dtype = DSIM_DT_U8; break;
-    case DSIM_BUF_PARAMS: *ptr = h->params; *rows = 6; *cols = n; *ld = L; *dtype = rdt; break;
-    case DSIM_BUF_CONSTS: *ptr = h->consts; *rows = C_ROWS; *cols = n; *ld = L; *dtype = rdt; break;
-    case DSIM_BUF_REFERENCE: *ptr = h->ref_env; *rows = 4; *cols = n; *ld = L; *dtype = rdt; break;
     case DSIM_BUF_RESET_COUNT: *ptr = h->reset_count; *rows = 1; *cols = n; *ld = L; *dtype = DSIM_DT_U32; break;
     case DSIM_BUF_STATES33: *ptr = h->states33; *rows = n; *cols = h->state_width; *ld = h->state_width; *dtype = rdt; break;
-    case DSIM_BUF_EP_RETURN: *ptr = h->ep_return; *rows = 1; *cols = n; *ld = L; *dtype = rdt; break;
     case DSIM_BUF_STATS: *ptr = h->stats; *rows = 1; *cols = 8; *ld = 8; *dtype = DSIM_DT_F64; break;
     default: return fail(h, DSIM_EINVAL, "unknown buffer id%s", "");
     }

@@ -5,12 +5,17 @@
 // (:275-284) -> _get_obs (observation_wrappers.py), plus the RLlib reset_at() round trip (:334-351) folded in
 // when auto_reset is on.
 //
-// Memory plan per CTA of kStepBlock envs (one env per thread):
-//   * SoA state / constant rows: coalesced 4-byte loads, all issued up front;
-//   * operands used only AFTER the physics (step counter, episode return, raw params, per-env setpoint) go
-//     global -> shared with cp.async at kernel entry: no registers held, DRAM latency hidden behind the physics;
-//   * the [N][D] policy-ready observation rows are written to a padded smem tile (odd pitch, conflict-free) and leave
-//     the SM as coalesced 16-byte vectors; a per-thread strided store would cost 32 L1 wavefronts per value;
+// Execution plan (sm_100a): one WARP owns one page of 32 envs, one env per lane; warps never synchronise with
+// each other.
+//   * lane 0 arms the warp's mbarrier and issues 1D bulk copies (cp.async.bulk, the TMA engine: SASS UBLKCP) that
+//     bring the warp's read-write page (state + step counter + episode return), read-only page (compiled constants +
+//     raw parameters) and setpoint page from HBM into the warp's shared-memory slot: three instructions move ~6 KB,
+//     no per-row address arithmetic, no registers held while the data is in flight;
+//   * every lane reads its own column with immediate-offset LDS (row pitch = 32 lanes: conflict-free), runs the
+//     physics / termination / reward / observation in registers, and writes the new column and its policy-ready
+//     observation row back into the slot;
+//   * after fence.proxy.async + __syncwarp lane 0 sends the read-write page and the warp's contiguous [32][obs_dim]
+//     observation block back with two bulk stores and waits only for their shared-memory reads.
 //   * rare paths (Philox re-sampling) are one out-of-line call so they do not inflate the hot path's registers/I-cache.
 #pragma once
 
@@ -21,24 +26,58 @@
 #define DSIM_MINB 4
 #endif
 constexpr int kStepBlock = DSIM_BLOCK;
+constexpr int kStepWarps = kStepBlock / 32;
+
+// ------------------------------------------------------------------ async-proxy primitives (PTX ISA 8.x, sm_90+)
+DSIM_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DSIM_DEV void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");      // make the init visible to the async proxy
+}
+DSIM_DEV void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DSIM_DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// HBM -> shared, completion counted in bytes on the mbarrier.  size % 16 == 0, both addresses 16-byte aligned.
+DSIM_DEV void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> HBM, tracked by the issuing thread's bulk async-group
+DSIM_DEV void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+DSIM_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+DSIM_DEV void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (the bulk store that follows)
+DSIM_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------ kernel parameter block (constant bank)
 template <typename T> struct KParams {
-    int n, ld;
-    T *state;
-    int *num_steps;
-    unsigned *reset_count;
-    const T *consts;          // [13][ld]
-    const T *params;          // [6][ld]
-    T *ref_env;               // [4][ld] (per-env setpoints) or nullptr
-    T *obs, *reward, *ep_return;
+    int n, npages;
+    T *rw;                    // [npages][RW_ROWS][32]
+    const T *ro;              // [npages][RO_ROWS][32]
+    T *refp;                  // [npages][REF_ROWS][32] (per-env setpoints) or nullptr
+    unsigned *reset_count;    // [npages * 32]
+    T *obs, *reward;          // [n][obs_dim], [n]
     unsigned char *trunc;
     double *stats;
     const T *actions;         // [n][4]
     T uconst[C_ROWS];         // uniform-parameter fast path (random_params == False)
     T uparams[6];
-    int per_env_consts, auto_reset, obs_id, reward_id, obs_layout, obs_dim, frame_skip, max_steps;
+    int per_env_consts, auto_reset, obs_id, reward_id, obs_dim, frame_skip, max_steps;
     int eval_only;            // 1: termination / reward / obs of the CURRENT state, nothing advanced or stored
+    unsigned smem_per_warp;   // bytes
     T h, max_distance_t;
     T ref_off[3], ref_yaw, start_t[3];
     double start[3], ref64[3], max_distance;
@@ -46,63 +85,64 @@ template <typename T> struct KParams {
     unsigned seed, env_base;
 };
 
-template <typename T> DSIM_DEV EnvState<T> load_state(const KParams<T> &p, int i) {
-    const T *b = p.state + i;
-    const size_t ld = p.ld;
+// integer rows of the read-write page are stored in a lane-sized slot (int32 for float pages, int64 for double)
+template <typename T> struct IntOf { typedef int type; };
+template <> struct IntOf<double> { typedef long long type; };
+template <typename T> DSIM_DEV int slot_to_int(T v) {
+    if constexpr (std::is_same<T, float>::value) return __float_as_int(v); else return (int)__double_as_longlong(v);
+}
+template <typename T> DSIM_DEV T int_to_slot(int v) {
+    if constexpr (std::is_same<T, float>::value) return __int_as_float(v); else return __longlong_as_double((long long)v);
+}
+
+// column accessors: `col` points at (row 0, this env) of a page, in shared or global memory; row pitch = kTile
+template <typename T> DSIM_DEV EnvState<T> load_state(const T *col) {
     EnvState<T> s;
-    s.pos = mk(b[0 * ld], b[1 * ld], b[2 * ld]);
-    s.qw = b[3 * ld]; s.qx = b[4 * ld]; s.qy = b[5 * ld]; s.qz = b[6 * ld];
-    s.hx = b[7 * ld]; s.hy = b[8 * ld];
-    s.vel = mk(b[9 * ld], b[10 * ld], b[11 * ld]);
-    s.om = mk(b[12 * ld], b[13 * ld], b[14 * ld]);
-    s.hvx = b[15 * ld]; s.hvy = b[16 * ld];
+    s.pos = mk(col[0 * kTile], col[1 * kTile], col[2 * kTile]);
+    s.qw = col[3 * kTile]; s.qx = col[4 * kTile]; s.qy = col[5 * kTile]; s.qz = col[6 * kTile];
+    s.hx = col[7 * kTile]; s.hy = col[8 * kTile];
+    s.vel = mk(col[9 * kTile], col[10 * kTile], col[11 * kTile]);
+    s.om = mk(col[12 * kTile], col[13 * kTile], col[14 * kTile]);
+    s.hvx = col[15 * kTile]; s.hvy = col[16 * kTile];
     #pragma unroll
-    for (int k = 0; k < 4; k++) s.act[k] = b[(S_ACT + k) * ld];
-    s.acc = mk(b[21 * ld], b[22 * ld], b[23 * ld]);
+    for (int k = 0; k < 4; k++) s.act[k] = col[(S_ACT + k) * kTile];
+    s.acc = mk(col[21 * kTile], col[22 * kTile], col[23 * kTile]);
     return s;
 }
-template <typename T> DSIM_DEV void store_state(const KParams<T> &p, int i, const EnvState<T> &s) {
-    T *b = p.state + i;
-    const size_t ld = p.ld;
-    b[0 * ld] = s.pos.x; b[1 * ld] = s.pos.y; b[2 * ld] = s.pos.z;
-    b[3 * ld] = s.qw; b[4 * ld] = s.qx; b[5 * ld] = s.qy; b[6 * ld] = s.qz;
-    b[7 * ld] = s.hx; b[8 * ld] = s.hy;
-    b[9 * ld] = s.vel.x; b[10 * ld] = s.vel.y; b[11 * ld] = s.vel.z;
-    b[12 * ld] = s.om.x; b[13 * ld] = s.om.y; b[14 * ld] = s.om.z;
-    b[15 * ld] = s.hvx; b[16 * ld] = s.hvy;
+template <typename T> DSIM_DEV void store_state(T *col, const EnvState<T> &s) {
+    col[0 * kTile] = s.pos.x; col[1 * kTile] = s.pos.y; col[2 * kTile] = s.pos.z;
+    col[3 * kTile] = s.qw; col[4 * kTile] = s.qx; col[5 * kTile] = s.qy; col[6 * kTile] = s.qz;
+    col[7 * kTile] = s.hx; col[8 * kTile] = s.hy;
+    col[9 * kTile] = s.vel.x; col[10 * kTile] = s.vel.y; col[11 * kTile] = s.vel.z;
+    col[12 * kTile] = s.om.x; col[13 * kTile] = s.om.y; col[14 * kTile] = s.om.z;
+    col[15 * kTile] = s.hvx; col[16 * kTile] = s.hvy;
     #pragma unroll
-    for (int k = 0; k < 4; k++) b[(S_ACT + k) * ld] = s.act[k];
-    b[21 * ld] = s.acc.x; b[22 * ld] = s.acc.y; b[23 * ld] = s.acc.z;
+    for (int k = 0; k < 4; k++) col[(S_ACT + k) * kTile] = s.act[k];
+    col[21 * kTile] = s.acc.x; col[22 * kTile] = s.acc.y; col[23 * kTile] = s.acc.z;
 }
-template <typename T> DSIM_DEV EnvConsts<T> load_consts(const KParams<T> &p, int i) {
+template <typename T> DSIM_DEV EnvConsts<T> consts_from(const T v[C_ROWS]) {
     EnvConsts<T> c;
-    T v[C_ROWS];
-    if (p.per_env_consts) {
-        #pragma unroll
-        for (int k = 0; k < C_ROWS; k++) v[k] = __ldg(p.consts + (size_t)k * p.ld + i);
-    } else {
-        #pragma unroll
-        for (int k = 0; k < C_ROWS; k++) v[k] = p.uconst[k];
-    }
     c.mB = v[C_MB]; c.cz = v[C_CZ]; c.IBx = v[C_IBX]; c.IBy = v[C_IBY]; c.IBz = v[C_IBZ];
     c.mD = v[C_MD]; c.zD = v[C_ZD]; c.IDx = v[C_IDX]; c.IDz = v[C_IDZ];
     c.Fs = v[C_FS]; c.F = v[C_F]; c.kq = v[C_KQ]; c.inv_tau = v[C_INVTAU];
     return c;
 }
-template <typename T> DSIM_DEV void load_params(const KParams<T> &p, int i, T prm[6]) {
-    if (p.per_env_consts) {
-        #pragma unroll
-        for (int k = 0; k < 6; k++) prm[k] = __ldg(p.params + (size_t)k * p.ld + i);
-    } else {
-        #pragma unroll
-        for (int k = 0; k < 6; k++) prm[k] = p.uparams[k];
-    }
+// `ro_col`: (row 0, this env) of the read-only page, shared or global
+template <typename T> DSIM_DEV EnvConsts<T> load_consts(const KParams<T> &p, const T *ro_col) {
+    T v[C_ROWS];
+    #pragma unroll
+    for (int k = 0; k < C_ROWS; k++) v[k] = p.per_env_consts ? ro_col[(RO_CONSTS + k) * kTile] : p.uconst[k];
+    return consts_from(v);
 }
-template <typename T> DSIM_DEV void load_ref(const KParams<T> &p, int i, V3<T> &ref_off, T &ref_yaw, double ref64[3]) {
-    if (p.ref_env) {
-        const T *r = p.ref_env + i;
-        ref_off = mk(r[0], r[(size_t)p.ld], r[2 * (size_t)p.ld]);
-        ref_yaw = r[3 * (size_t)p.ld];
+template <typename T> DSIM_DEV void load_params(const KParams<T> &p, const T *ro_col, T prm[6]) {
+    #pragma unroll
+    for (int k = 0; k < 6; k++) prm[k] = p.per_env_consts ? ro_col[(RO_PARAMS + k) * kTile] : p.uparams[k];
+}
+// `ref_col`: (row 0, this env) of the setpoint page (ignored when the reference is shared)
+template <typename T> DSIM_DEV void load_ref(const KParams<T> &p, const T *ref_col, V3<T> &ref_off, T &ref_yaw, double ref64[3]) {
+    if (p.refp) {
+        ref_off = mk(ref_col[0], ref_col[kTile], ref_col[2 * kTile]);
+        ref_yaw = ref_col[3 * kTile];
         ref64[0] = p.start[0] + (double)ref_off.x; ref64[1] = p.start[1] + (double)ref_off.y; ref64[2] = p.start[2] + (double)ref_off.z;
     } else {
         ref_off = mk(p.ref_off[0], p.ref_off[1], p.ref_off[2]);
@@ -121,74 +161,65 @@ template <typename T, int STRIDE = 0> struct ObsWriter {
     T *base; size_t stride;
     DSIM_DEV void operator()(int j, T v) const { if constexpr (STRIDE > 0) base[j * STRIDE] = v; else base[(size_t)j * stride] = v; }
 };
-template <typename T> DSIM_DEV ObsWriter<T> obs_writer(const KParams<T> &p, int i) {
-    ObsWriter<T> w;
-    if (p.obs_layout == DSIM_LAYOUT_SOA) { w.base = p.obs + i; w.stride = p.ld; }
-    else { w.base = p.obs + (size_t)i * p.obs_dim; w.stride = 1; }
-    return w;
-}
-
-constexpr int kObsPad = DSIM_MAX_OBS | 1;      // upper bound of the odd smem row pitch
-constexpr int kLate = 11;                      // ep_return, params[6], ref[4]: needed only after the physics
-
-// cooperative, fully coalesced copy of the CTA's observation tile (smem, row pitch Dp = D | 1) to obs[row0*D ...]
-// (row pitch D).  flat element e lives at tile[e + (Dp - D) * (e / D)]; DC > 0 makes D a compile-time constant.
-template <typename T, int DC>
-DSIM_DEV void copy_out_obs(const T *tile, T *gout, int Drt, int nvalid, int t) {
-    const int D = DC > 0 ? DC : Drt;
-    const int pad = (D | 1) - D;
-    const int E = nvalid * D;
-    if constexpr (std::is_same<T, float>::value) {
-        if ((E & 3) == 0) {                    // full CTAs: always; a ragged last CTA falls through to the scalar loop
-            float4 *g4 = reinterpret_cast<float4 *>(gout);
-            for (int e4 = t; e4 < (E >> 2); e4 += kStepBlock) {
-                const int e = 4 * e4;
-                float v[4];
-                #pragma unroll
-                for (int k = 0; k < 4; k++) v[k] = tile[(e + k) + pad * ((e + k) / D)];
-                g4[e4] = make_float4(v[0], v[1], v[2], v[3]);
-            }
-            return;
-        }
-    }
-    for (int e = t; e < E; e += kStepBlock) gout[e] = tile[e + pad * (e / D)];
-}
 
 template <typename T> constexpr int min_blocks() { return std::is_same<T, float>::value ? DSIM_MINB * 128 / DSIM_BLOCK : 1; }
 __host__ __device__ constexpr int obs_dim_of(int obs_id) {
     return obs_id == 0 ? 33 : obs_id == 1 ? 16 : obs_id == 2 ? 16 : obs_id == 3 ? 23 : obs_id == 4 ? 24 : obs_id == 5 ? 19 : obs_id == 6 ? 22 :
            obs_id == 7 ? 25 : obs_id == 8 ? 22 : obs_id == 9 ? 22 : obs_id == 10 ? 16 : obs_id == 11 ? 15 : obs_id == 13 ? 28 : obs_id == 14 ? 17 : 0;
 }
+// shared-memory slot of one warp: [RW page | RO page | setpoint page | observation block [32][obs_dim]]
+constexpr int kSlotObsOff = (RW_ROWS + RO_ROWS + REF_ROWS) * kTile;          // elements
+__host__ __device__ constexpr unsigned slot_bytes(int obs_dim, int elem) {
+    return (unsigned)((((kSlotObsOff + kTile * obs_dim) * elem) + 127) / 128 * 128);
+}
+
+// rare path, out of line: RLlib's reset_at() round trip (:334-351) folded into the step.  Works on the env's column of
+// the read-write page in shared memory (qpos / qvel rows and the step counter), so the hot path keeps no state
+// registers alive across the call.
+template <typename T, bool PEND>
+__device__ __noinline__ void resample_column(T *col, const ResetCfg<T> &rc, unsigned seed, unsigned env, unsigned *reset_count_slot) {
+    const unsigned rcnt = *reset_count_slot + 1u;
+    EnvState<T> s;
+    sample_state<T, PEND>(s, rc, seed, env, rcnt);
+    *reset_count_slot = rcnt;
+    col[0 * kTile] = s.pos.x; col[1 * kTile] = s.pos.y; col[2 * kTile] = s.pos.z;
+    col[3 * kTile] = s.qw; col[4 * kTile] = s.qx; col[5 * kTile] = s.qy; col[6 * kTile] = s.qz;
+    col[7 * kTile] = s.hx; col[8 * kTile] = s.hy;
+    col[9 * kTile] = s.vel.x; col[10 * kTile] = s.vel.y; col[11 * kTile] = s.vel.z;
+    col[12 * kTile] = s.om.x; col[13 * kTile] = s.om.y; col[14 * kTile] = s.om.z;
+    col[15 * kTile] = s.hvx; col[16 * kTile] = s.hvy;
+    col[RW_NUM_STEPS * kTile] = int_to_slot<T>(0);
+}
 
 // OBS / REW >= 0 are compile-time specialisations of the wrapper class / reward function (smaller code, no dispatch
 // branches, constant observation width); -1 reads the ids from the parameter block.
 template <typename T, bool PEND, int OBS, int REW>
-__global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const KParams<T> p) {
-    __shared__ T s_obs[kStepBlock * kObsPad];
-    __shared__ T s_late[kLate][kStepBlock];
-    __shared__ int s_ns[kStepBlock];
+__global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const __grid_constant__ KParams<T> p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[kStepWarps];
     constexpr int DC = (OBS >= 0 && PEND) ? obs_dim_of(OBS) : 0;
-    const int t = threadIdx.x, i = blockIdx.x * kStepBlock + t;
-    const bool active = i < p.n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int page = blockIdx.x * kStepWarps + warp;
+    if (page >= p.npages) return;                                  // warps are autonomous: no CTA-wide barrier below
+    const int i = page * kTile + lane;
+    const bool active = i < p.n;                                   // pad lanes of the last page compute, but publish nothing
     const int obs_id = OBS >= 0 ? OBS : p.obs_id, reward_id = REW >= 0 ? REW : p.reward_id;
-    const int D = DC > 0 ? DC : p.obs_dim, Dp = D | 1;
-    const bool staged = p.obs_layout == DSIM_LAYOUT_ENV_MAJOR;
-    if (active) {
-        __pipeline_memcpy_async(&s_ns[t], p.num_steps + i, sizeof(int));
-        __pipeline_memcpy_async(&s_late[0][t], p.ep_return + i, sizeof(T));
-        if (p.per_env_consts) {
-            #pragma unroll
-            for (int k = 0; k < 6; k++) __pipeline_memcpy_async(&s_late[1 + k][t], p.params + (size_t)k * p.ld + i, sizeof(T));
-        }
-        if (p.ref_env) {
-            #pragma unroll
-            for (int k = 0; k < 4; k++) __pipeline_memcpy_async(&s_late[7 + k][t], p.ref_env + (size_t)k * p.ld + i, sizeof(T));
-        }
-        __pipeline_commit();
+    const int D = DC > 0 ? DC : p.obs_dim;
+    T *slot = reinterpret_cast<T *>(smem_raw + (size_t)warp * p.smem_per_warp);
+    T *s_rw = slot, *s_ro = slot + RW_ROWS * kTile, *s_ref = slot + (RW_ROWS + RO_ROWS) * kTile, *s_obs = slot + kSlotObsOff;
+    uint64_t *bar = &s_bar[warp];
 
-        EnvState<T> s = load_state(p, i);
-        const EnvConsts<T> c = load_consts(p, i);
-        T a[4], ctrl[4];
+    // ---- page loads: HBM -> this warp's slot
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        constexpr uint32_t rwb = RW_ROWS * kTile * sizeof(T), rob = RO_ROWS * kTile * sizeof(T), rfb = REF_ROWS * kTile * sizeof(T);
+        mbar_arrive_expect_tx(bar, rwb + (p.per_env_consts ? rob : 0u) + (p.refp ? rfb : 0u));
+        bulk_g2s(s_rw, p.rw + (size_t)page * (RW_ROWS * kTile), rwb, bar);
+        if (p.per_env_consts) bulk_g2s(s_ro, p.ro + (size_t)page * (RO_ROWS * kTile), rob, bar);
+        if (p.refp) bulk_g2s(s_ref, p.refp + (size_t)page * (REF_ROWS * kTile), rfb, bar);
+    }
+    T a[4] = {T(0), T(0), T(0), T(0)};
+    if (active) {
         if constexpr (std::is_same<T, float>::value) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(p.actions) + i);
             a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
@@ -197,73 +228,78 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             const double2 v1 = __ldg(reinterpret_cast<const double2 *>(p.actions) + 2 * (size_t)i + 1);
             a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y;
         }
+    }
+    __syncwarp();                                                  // barrier init visible to the waiting lanes
+    mbar_wait(bar, 0);
+
+    // ---- physics
+    T *col = s_rw + lane;
+    const T *ro_col = s_ro + lane;
+    EnvState<T> s = load_state(col);
+    {
+        const EnvConsts<T> c = load_consts(p, ro_col);
+        T ctrl[4];
         #pragma unroll
         for (int k = 0; k < 4; k++) ctrl[k] = clamp_(T(0.1) + T(0.9) * a[k], T(0), T(1));   // :269 + ctrlrange (0,1) clamp of mj_fwdActuation
+        #pragma unroll 1
         for (int f = 0; f < p.frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
+    }
 
-        __pipeline_wait_prior(0);
-        int ns = s_ns[t] + (p.eval_only ? 0 : 1);
-        const unsigned env = p.env_base + (unsigned)i;
-        // MuJoCo's mj_checkPos/Vel/Acc warn and reset the whole MjData; here the one env is parked on a finite state for
-        // the outputs of this step, flagged truncated, counted, and re-sampled below.  Never silent.
-        const bool bad = !state_finite(s);
-        if (bad) {
-            s.pos = mk(T(0), T(0), T(0)); s.qw = T(1); s.qx = s.qy = s.qz = T(0); s.hx = s.hy = s.hvx = s.hvy = T(0);
-            s.vel = mk(T(0), T(0), T(0)); s.om = mk(T(0), T(0), T(0)); s.acc = mk(T(0), T(0), T(0));
-            #pragma unroll
-            for (int k = 0; k < 4; k++) s.act[k] = T(0);
-        }
-
-        V3<T> ref_off; T ref_yaw; double ref64[3];
-        if (p.ref_env) {
-            ref_off = mk(s_late[7][t], s_late[8][t], s_late[9][t]);
-            ref_yaw = s_late[10][t];
-            ref64[0] = p.start[0] + (double)ref_off.x; ref64[1] = p.start[1] + (double)ref_off.y; ref64[2] = p.start[2] + (double)ref_off.z;
-        } else {
-            ref_off = mk(p.ref_off[0], p.ref_off[1], p.ref_off[2]);
-            ref_yaw = p.ref_yaw;
-            ref64[0] = p.ref64[0]; ref64[1] = p.ref64[1]; ref64[2] = p.ref64[2];
-        }
-        T prm[6];
+    // ---- counters, termination, reward, observation
+    int ns = slot_to_int(col[RW_NUM_STEPS * kTile]) + (p.eval_only ? 0 : 1);
+    const unsigned env = p.env_base + (unsigned)i;
+    // MuJoCo's mj_checkPos/Vel/Acc warn and reset the whole MjData; here the one env is parked on a finite state for
+    // the outputs of this step, flagged truncated, counted, and re-sampled below.  Never silent.
+    const bool bad = !state_finite(s);
+    if (bad) {
+        s.pos = mk(T(0), T(0), T(0)); s.qw = T(1); s.qx = s.qy = s.qz = T(0); s.hx = s.hy = s.hvx = s.hvy = T(0);
+        s.vel = mk(T(0), T(0), T(0)); s.om = mk(T(0), T(0), T(0)); s.acc = mk(T(0), T(0), T(0));
         #pragma unroll
-        for (int k = 0; k < 6; k++) prm[k] = p.per_env_consts ? s_late[1 + k][t] : p.uparams[k];
-        const PostState<T> ps = post_state(s, ref_off, ref_yaw);
-        bool trunc = terminated(s.pos, p.start, ref64, p.max_distance, ns, p.max_steps) || bad;
-        const T rew = bad ? T(0) : reward_fn<T, PEND>(reward_id, s, ps, a, ns, prm, p.max_distance_t);
-        const V3<T> start_t = mk(p.start_t[0], p.start_t[1], p.start_t[2]);
-        if (staged) {
-            ObsWriter<T, 1> w; w.base = s_obs + t * Dp; w.stride = 1;
-            emit_obs<T, PEND>(obs_id, s, ps, start_t, ref_off, prm, w);
-        } else {
-            ObsWriter<T> w; w.base = p.obs + i; w.stride = p.ld;
-            emit_obs<T, PEND>(obs_id, s, ps, start_t, ref_off, prm, w);
-        }
+        for (int k = 0; k < 4; k++) s.act[k] = T(0);
+    }
+    V3<T> ref_off; T ref_yaw; double ref64[3];
+    load_ref(p, s_ref + lane, ref_off, ref_yaw, ref64);
+    T prm[6];
+    load_params(p, ro_col, prm);
+    const PostState<T> ps = post_state(s, ref_off, ref_yaw);
+    const bool trunc = terminated(s.pos, p.start, ref64, p.max_distance, ns, p.max_steps) || bad;
+    const T rew = bad ? T(0) : reward_fn<T, PEND>(reward_id, s, ps, a, ns, prm, p.max_distance_t);
+    {
+        ObsWriter<T, 1> w; w.base = s_obs + lane * D; w.stride = 1;
+        emit_obs<T, PEND>(obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
+    }
+    if (active) {
         p.reward[i] = rew;
         p.trunc[i] = trunc ? 1 : 0;
+    }
 
-        if (!p.eval_only) {
-            // would-be ground contact (the floor plane is out of reach in the BASELINE configs; detected, never ignored)
-            if (p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(p.stats + 4, 1.0);
-            T ret = s_late[0][t] + rew;
-            if (trunc) {
-                atomicAdd(p.stats + 0, (double)ret); atomicAdd(p.stats + 1, (double)ns); atomicAdd(p.stats + 2, 1.0);
-                if (bad) atomicAdd(p.stats + 3, 1.0);
-                ret = T(0);
-                if (p.auto_reset || bad) {   // native loop: the RLlib reset_at() round trip (:334-351) folded into the step
-                    const unsigned rcnt = p.reset_count[i] + 1u;
-                    sample_state<T, PEND>(s, p.rc, p.seed, env, rcnt);
-                    p.reset_count[i] = rcnt;
-                    ns = 0;
-                }
-            }
-            p.ep_return[i] = ret;
-            p.num_steps[i] = ns;
-            store_state(p, i, s);
+    if (!p.eval_only) {
+        // would-be ground contact (the floor plane is out of reach in the BASELINE configs; detected, never ignored)
+        if (active && p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(p.stats + 4, 1.0);
+        T ret = col[RW_EP_RETURN * kTile] + rew;
+        if (trunc && active) {
+            atomicAdd(p.stats + 0, (double)ret); atomicAdd(p.stats + 1, (double)ns); atomicAdd(p.stats + 2, 1.0);
+            if (bad) atomicAdd(p.stats + 3, 1.0);
         }
+        col[RW_EP_RETURN * kTile] = trunc ? T(0) : ret;
+        col[RW_NUM_STEPS * kTile] = int_to_slot<T>(ns);
+        store_state(col, s);
+        if (trunc && (p.auto_reset || bad)) resample_column<T, PEND>(col, p.rc, p.seed, env, p.reset_count + i);
     }
-    if (staged) {
-        __syncthreads();
-        const int row0 = blockIdx.x * kStepBlock;
-        copy_out_obs<T, DC>(s_obs, p.obs + (size_t)row0 * D, D, min(kStepBlock, p.n - row0), t);
+
+    // ---- publish: slot -> HBM
+    fence_async_smem();
+    __syncwarp();
+    const int nvalid = min(kTile, p.n - page * kTile);
+    const uint32_t obs_bytes = (uint32_t)(nvalid * D) * (uint32_t)sizeof(T);
+    T *gobs = p.obs + (size_t)page * kTile * D;
+    const bool obs_bulk = (obs_bytes & 15u) == 0;                  // always true for full pages
+    if (lane == 0) {
+        if (!p.eval_only) bulk_s2g(p.rw + (size_t)page * (RW_ROWS * kTile), s_rw, RW_ROWS * kTile * sizeof(T));
+        if (obs_bulk) bulk_s2g(gobs, s_obs, obs_bytes);
+        bulk_commit();
     }
+    if (!obs_bulk)                                                 // ragged last page whose byte count is not a multiple of 16
+        for (int e = lane; e < nvalid * D; e += kTile) gobs[e] = s_obs[e];
+    if (lane == 0) bulk_wait_read();                               // the slot must outlive the bulk reads
 }

@@ -54,9 +54,8 @@ base_config = {'seed': 42, 'frequency': 100, 'skip_steps': 1, 'reference': [0, 0
                'regen_env_at_steps': None, 'train_vis': 0, 'window_title': 'mujoco', 'controlled': False, 'mocaps': 1}
 
 PARAM_KEYS = ('mass', 'arm_len', 'motor_force', 'motor_tau', 'pendulum_len', 'weight_mass')
-_TORCH_DT = {_lib.DT_F32: 'float32', _lib.DT_F64: 'float64', _lib.DT_I32: 'int32', _lib.DT_U8: 'uint8', _lib.DT_U32: 'int32'}
-_NP_STR = {_lib.DT_F32: '<f4', _lib.DT_F64: '<f8', _lib.DT_I32: '<i4', _lib.DT_U8: '|u1', _lib.DT_U32: '<i4'}
-_ITEM = {_lib.DT_F32: 4, _lib.DT_F64: 8, _lib.DT_I32: 4, _lib.DT_U8: 1, _lib.DT_U32: 4}
+_NP_STR = {_lib.DT_F32: '<f4', _lib.DT_F64: '<f8', _lib.DT_I32: '<i4', _lib.DT_U8: '|u1', _lib.DT_U32: '<i4', _lib.DT_I64: '<i8'}
+_ITEM = {_lib.DT_F32: 4, _lib.DT_F64: 8, _lib.DT_I32: 4, _lib.DT_U8: 1, _lib.DT_U32: 4, _lib.DT_I64: 8}
 
 
 class _DevView:
@@ -146,7 +145,6 @@ class BaseDroneEnv(_VectorEnv):
         cfg.frequency = float(self.frequency)
         cfg.obs_id = int(self.OBS_ID)
         cfg.reward_id = int(self.reward_id)
-        cfg.obs_layout = _lib.LAYOUT_SOA if g('obs_layout', 'env_major') == 'soa' else _lib.LAYOUT_ENV_MAJOR
         cfg.per_env_reference = int(self.per_env_reference)
         cfg.auto_reset = int(self.auto_reset)
         cfg.random_start_pos = int(bool(self.random_start_pos))
@@ -197,19 +195,40 @@ class BaseDroneEnv(_VectorEnv):
         return _lib.check(self._h, rc)
 
     def tensor(self, buf_id):
-        """Zero-copy torch view of a handle-owned device buffer (include/dronesim_b200.h DSIM_BUF_*)."""
+        """Zero-copy torch view of a handle-owned device buffer (include/dronesim_b200.h DSIM_BUF_*).
+        Dense buffers come back as [cols] / [rows, cols].  PAGED buffers (state, num_steps, params, consts,
+        reference, ep_return) come back as [rows, npages, 32]: env i is element [..., i // 32, i % 32]."""
         if buf_id in self._views:
             return self._views[buf_id]
-        ptr, rows, cols, ld, dt = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
-        self._ck(self._L.dsim_buffer(self._h, buf_id, C.byref(ptr), C.byref(rows), C.byref(cols), C.byref(ld), C.byref(dt)))
+        ptr, rows, cols, ld, dt, pr = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32(), C.c_int64()
+        self._ck(self._L.dsim_buffer(self._h, buf_id, C.byref(ptr), C.byref(rows), C.byref(cols), C.byref(ld), C.byref(dt), C.byref(pr)))
         item = _ITEM[dt.value]
-        if rows.value == 1:
+        if pr.value:
+            T = _lib.TILE
+            view = _DevView(ptr.value, (rows.value, ld.value // T, T), (T * item, pr.value * T * item, item), dt.value, self)
+        elif rows.value == 1:
             view = _DevView(ptr.value, (cols.value,), None, dt.value, self)
         else:
             view = _DevView(ptr.value, (rows.value, cols.value), (ld.value * item, item), dt.value, self)
         t = self._torch.as_tensor(view, device=self._device)
         self._views[buf_id] = t
         return t
+
+    def rows(self, buf_id):
+        """Copy of a PAGED buffer as a dense [rows, num_drones] tensor."""
+        t = self.tensor(buf_id)
+        return t.reshape(t.shape[0], -1)[:, :self.num_drones]
+
+    def write_rows(self, buf_id, row0, values):
+        """values [k, num_drones] -> rows row0..row0+k of a PAGED buffer (in place on the device)."""
+        t = self.tensor(buf_id)
+        v = self._torch.as_tensor(values, device=self._device).to(t.dtype)
+        k, n, T = v.shape[0], self.num_drones, _lib.TILE
+        full, rem = n // T, n % T
+        if full:
+            t[row0:row0 + k, :full, :] = v[:, :full * T].reshape(k, full, T)
+        if rem:
+            t[row0:row0 + k, full, :rem] = v[:, full * T:]
 
     @property
     def obs_tensor(self):
@@ -225,14 +244,17 @@ class BaseDroneEnv(_VectorEnv):
 
     @property
     def state_tensor(self):
+        """[24, npages, 32] zero-copy view of the state rows (see `tensor`)."""
         return self.tensor(_lib.BUF_STATE)
 
     @property
     def num_steps_tensor(self):
-        return self.tensor(_lib.BUF_NUM_STEPS)
+        """[num_drones] int copy of BaseDroneEnv.num_steps."""
+        return self.rows(_lib.BUF_NUM_STEPS)[0]
 
     @property
     def reference_tensor(self):
+        """[4, npages, 32] zero-copy view of the per-env setpoints."""
         return self.tensor(_lib.BUF_REFERENCE)
 
     # ------------------------------------------------------------------ native (device tensor) loop
@@ -301,7 +323,7 @@ class BaseDroneEnv(_VectorEnv):
                 r = self.reference_tensor
                 off = self._reference.copy()
                 off[:3] -= np.asarray(self.start_pos[:3], dtype=np.float64)
-                r[:, :] = self._torch.as_tensor(off, dtype=r.dtype, device=self._device)[:, None]
+                r[:, :, :] = self._torch.as_tensor(off, dtype=r.dtype, device=self._device)[:, None, None]
             self._states_cache = None
 
     @property
@@ -369,7 +391,7 @@ class BaseDroneEnv(_VectorEnv):
         return list(self._last_obs)
 
     def _fetch_obs(self):
-        self._h_obs.copy_(self.obs_tensor if self._cfg.obs_layout == _lib.LAYOUT_ENV_MAJOR else self.obs_tensor.t(), non_blocking=True)
+        self._h_obs.copy_(self.obs_tensor, non_blocking=True)
         return self._obs_to_list()
 
     def vector_step(self, actions):
@@ -452,7 +474,7 @@ class BaseDroneEnv(_VectorEnv):
 
     def control_reference_tensor(self, axes):
         """(:151-172) per-env setpoint update from joystick-style axes: CUDA tensor [4, N] = (x, -y, -z, -yaw)."""
-        ld = self.reference_tensor.stride(0)
+        ld = self.reference_tensor.shape[1] * _lib.TILE
         buf = self._torch.zeros((4, ld), dtype=self.reference_tensor.dtype, device=self._device)
         buf[:, :self.num_drones] = axes
         self._ck(self._L.dsim_control_reference(self._h, C.c_void_p(buf.data_ptr()), self._stream()))
