@@ -52,20 +52,56 @@ enum { REF_ROWS = 4 };                        // per-env setpoint page (x, y, z 
 DSIM_HD size_t page_elem(int rows, int r, int i) { return (size_t)(i >> 5) * (size_t)(rows * kTile) + (size_t)(r * kTile + (i & 31)); }
 
 // ------------------------------------------------------------------ scalar helpers
-template <typename T> DSIM_DEV T sqrt_(T x) { if constexpr (std::is_same<T, float>::value) return sqrtf(x); else return sqrt(x); }
-// reciprocal without the IEEE-division slow path (MUFU.RCP + Newton step, correctly rounded for normal inputs)
-template <typename T> DSIM_DEV T rcp_(T x) { if constexpr (std::is_same<T, float>::value) return __frcp_rn(x); else return 1.0 / x; }
+// FP32 product path: single-MUFU approximations (rcp/sqrt/rsqrt .approx.ftz, <= 1-2 ulp) instead of the IEEE sequences
+// with their slow-path branches; the FP64 validation build keeps exact libm semantics.
+template <typename T> DSIM_DEV T sqrt_(T x) {
+    if constexpr (std::is_same<T, float>::value) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; } else return sqrt(x);
+}
+template <typename T> DSIM_DEV T rcp_(T x) {
+    if constexpr (std::is_same<T, float>::value) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; } else return 1.0 / x;
+}
 template <typename T> DSIM_DEV T floor_(T x) { if constexpr (std::is_same<T, float>::value) return floorf(x); else return floor(x); }
-template <typename T> DSIM_DEV T rsqrt_(T x) { if constexpr (std::is_same<T, float>::value) return rsqrtf(x); else return 1.0 / sqrt(x); }
+template <typename T> DSIM_DEV T rsqrt_(T x) {
+    if constexpr (std::is_same<T, float>::value) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; } else return 1.0 / sqrt(x);
+}
 template <typename T> DSIM_DEV T abs_(T x) { if constexpr (std::is_same<T, float>::value) return fabsf(x); else return fabs(x); }
 template <typename T> DSIM_DEV T max_(T a, T b) { if constexpr (std::is_same<T, float>::value) return fmaxf(a, b); else return fmax(a, b); }
 template <typename T> DSIM_DEV T min_(T a, T b) { if constexpr (std::is_same<T, float>::value) return fminf(a, b); else return fmin(a, b); }
-template <typename T> DSIM_DEV T atan2_(T y, T x) { if constexpr (std::is_same<T, float>::value) return atan2f(y, x); else return atan2(y, x); }
+// atan2: branch-free for FP32.  atan(t), t = min/max in [0,1], as t * P(t^2) (degree-8 least-squares Chebyshev fit,
+// max abs error 1.1e-7), then the octant / quadrant / sign fix-ups as selects.  atan2(0, 0) = 0 like libm.
+template <typename T> DSIM_DEV T atan2_(T y, T x) {
+    if constexpr (std::is_same<T, float>::value) {
+        const float ax = fabsf(x), ay = fabsf(y);
+        const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+        const float t = mn * rcp_(fmaxf(mx, 1e-37f)), s2 = t * t;
+        float r = 2.8340642988e-03f;
+        r = fmaf(r, s2, -1.6005030503e-02f); r = fmaf(r, s2, 4.2587607465e-02f); r = fmaf(r, s2, -7.4954454434e-02f);
+        r = fmaf(r, s2, 1.0636754098e-01f); r = fmaf(r, s2, -1.4202570512e-01f); r = fmaf(r, s2, 1.9992483579e-01f);
+        r = fmaf(r, s2, -3.3333066781e-01f); r = fmaf(r, s2, 9.9999998424e-01f);
+        r *= t;
+        r = ay > ax ? 1.57079632679f - r : r;
+        r = x < 0.f ? 3.14159265359f - r : r;
+        return copysignf(r, y);
+    } else return atan2(y, x);
+}
 template <typename T> DSIM_DEV T fmod_(T a, T b) { if constexpr (std::is_same<T, float>::value) return fmodf(a, b); else return fmod(a, b); }
 template <typename T> DSIM_DEV T log_(T x) { if constexpr (std::is_same<T, float>::value) return logf(x); else return log(x); }
 template <typename T> DSIM_DEV T cbrt_(T x) { if constexpr (std::is_same<T, float>::value) return cbrtf(x); else return cbrt(x); }
 template <typename T> DSIM_DEV void sincos_(T a, T *s, T *c) { if constexpr (std::is_same<T, float>::value) sincosf(a, s, c); else sincos(a, s, c); }
 template <typename T> DSIM_DEV bool finite_(T x) { return isfinite(x); }
+// sin / cos of the half rotation angle of one integration step (h |w| / 2, almost always << 1): Taylor polynomials on
+// |a| <= 0.8 (relative error < 1e-7 in FP32), libm beyond
+template <typename T> DSIM_DEV void sincos_small(T a, T *s, T *c) {
+    if constexpr (std::is_same<T, float>::value) {
+        if (fabsf(a) <= 0.8f) {
+            const float z = a * a;
+            float ps = fmaf(z, 2.7557319e-6f, -1.9841270e-4f); ps = fmaf(ps, z, 8.3333333e-3f); ps = fmaf(ps, z, -1.6666667e-1f);
+            *s = fmaf(ps * z, a, a);
+            float pc = fmaf(z, -2.7557319e-7f, 2.4801587e-5f); pc = fmaf(pc, z, -1.3888889e-3f); pc = fmaf(pc, z, 4.1666667e-2f); pc = fmaf(pc, z, -0.5f);
+            *c = fmaf(pc, z, 1.0f);
+        } else sincosf(a, s, c);
+    } else sincos(a, s, c);
+}
 template <typename T> DSIM_DEV T clamp_(T x, T lo, T hi) { return min_(max_(x, lo), hi); }
 // (a + pi) % (2 pi) - pi with Python's sign convention (rewards.py / observation_wrappers.py / scipy as_euler):
 // a - 2 pi floor((a + pi) / 2 pi); returns `a` itself when it already lies in [-pi, pi)
@@ -326,7 +362,7 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
         if (w2 >= T(1e-30)) {
             const T iw = rsqrt_(w2), wn = w2 * iw;
             T sh, ch;
-            sincos_(T(0.5) * h * wn, &sh, &ch);
+            sincos_small(T(0.5) * h * wn, &sh, &ch);
             rw = ch; rx_ = sh * s.om.x * iw; ry_ = sh * s.om.y * iw; rz_ = sh * s.om.z * iw;
         }
         s.qw = qw * rw - qx * rx_ - qy * ry_ - qz * rz_;
@@ -377,6 +413,16 @@ template <typename T> DSIM_DEV void box_muller(uint32_t x0, uint32_t x1, T &z0, 
 }
 template <typename T> DSIM_DEV T clipn(T z, T sigma) { const T v = z * sigma, lim = T(2) * sigma; return clamp_(v, -lim, lim); }
 
+// mujoco_rpy2quat (transformation.py:10-12): qz(yaw) * qy(pitch) * qx(roll)
+template <typename T> DSIM_DEV void rpy_to_quat(T roll, T pitch, T yaw, T &qw, T &qx, T &qy, T &qz) {
+    T sr, cr, sp, cp, sy, cy;
+    sincos_(T(0.5) * roll, &sr, &cr); sincos_(T(0.5) * pitch, &sp, &cp); sincos_(T(0.5) * yaw, &sy, &cy);
+    qw = cy * cp * cr + sy * sp * sr;
+    qx = cy * cp * sr - sy * sp * cr;
+    qy = cy * sp * cr + sy * cp * sr;
+    qz = sy * cp * cr - cy * sp * sr;
+}
+
 template <typename T> struct ResetCfg {
     T start_yaw, max_pos_offset;
     T angle_sigma[2], vel_sigma[3], ang_vel_sigma[3], pend_rp_sigma[2], pend_vel_sigma[2];
@@ -416,13 +462,7 @@ DSIM_DEV void sample_state(EnvState<T> &s, const ResetCfg<T> &rc, uint32_t seed,
             s.hvx = clipn(n0, rc.pend_vel_sigma[0]); s.hvy = clipn(n1, rc.pend_vel_sigma[1]);
         }
     }
-    // mujoco_rpy2quat: qz(yaw) * qy(pitch) * qx(roll)
-    T sr, cr, sp, cp, sy, cy;
-    sincos_(T(0.5) * roll, &sr, &cr); sincos_(T(0.5) * pitch, &sp, &cp); sincos_(T(0.5) * yaw, &sy, &cy);
-    s.qw = cy * cp * cr + sy * sp * sr;
-    s.qx = cy * cp * sr - sy * sp * cr;
-    s.qy = cy * sp * cr + sy * cp * sr;
-    s.qz = sy * cp * cr - cy * sp * sr;
+    rpy_to_quat(roll, pitch, yaw, s.qw, s.qx, s.qy, s.qz);
 }
 
 }  // namespace dsim

@@ -147,7 +147,7 @@ struct DsimHandle {
     int per_env_consts;
     double uconst[C_ROWS], uparams[6];
     double h;
-    int first_reset_done, smem_configured;
+    int first_reset_done, step_grid;
     int64_t launches;
     char err[512];
 };
@@ -191,7 +191,7 @@ template <typename T> static KParams<T> make_params(const DsimHandle *h, const v
     p.per_env_consts = h->per_env_consts; p.auto_reset = c.auto_reset; p.obs_id = c.obs_id; p.reward_id = c.reward_id;
     p.obs_dim = h->obs_dim; p.frame_skip = c.frame_skip;
     p.max_steps = (int)(c.max_steps > 2147483647LL ? 2147483647LL : c.max_steps);
-    p.smem_per_warp = slot_bytes(h->obs_dim, (int)sizeof(T));
+    p.smem_per_slot = slot_bytes(h->obs_dim, (int)sizeof(T));
     p.h = (T)h->h; p.max_distance_t = (T)c.max_distance; p.max_distance = c.max_distance;
     for (int k = 0; k < 3; k++) {
         p.ref_off[k] = (T)(c.reference[k] - c.start_pos[k]);
@@ -437,41 +437,52 @@ extern "C" int dsim_zero_act(DsimHandle *h, void *stream) {
     return DSIM_OK;
 }
 
-// step-kernel dispatch: compile-time specialisations for the BASELINE configs, generic kernel otherwise
-template <typename K> static cudaError_t launch_one(K kernel, int grid, unsigned smem, cudaStream_t st, const void *kp_ptr, bool configure) {
-    if (configure) {
+// step-kernel dispatch: compile-time specialisations for the BASELINE configs, generic kernel otherwise.  The kernel is
+// persistent: grid = min(CTAs needed, CTAs the GPU can hold at once), queried once per handle.
+template <typename K> static cudaError_t launch_one(DsimHandle *h, K kernel, unsigned smem, cudaStream_t st, const void *kp_ptr) {
+    if (!h->step_grid) {
         // opt in once to the largest slot any handle can ask for (the attribute is per function, not per handle)
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(slot_bytes(DSIM_MAX_OBS, 8) * kStepWarps));
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(slot_bytes(DSIM_MAX_OBS, 8) * kStages * kStepWarps));
         if (e != cudaSuccess) return e;
+        int sms = 0, per_sm = 0;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kStepBlock, smem)) != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        const int need = (h->npages + kStepWarps - 1) / kStepWarps, cap = sms * per_sm;
+        h->step_grid = need < cap ? need : cap;
     }
     void *args[] = {const_cast<void *>(kp_ptr)};
-    return cudaLaunchKernel((const void *)kernel, dim3(grid), dim3(kStepBlock), args, smem, st);
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3(h->step_grid); lc.blockDim = dim3(kStepBlock); lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // pairs with griddepcontrol.* in step_kernel
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    return cudaLaunchKernelExC(&lc, (const void *)kernel, args);
 }
-template <typename T> static cudaError_t launch_step(const DsimHandle *h, const KParams<T> &kp, cudaStream_t st, bool configure) {
-    const int grid = (h->npages + kStepWarps - 1) / kStepWarps;
-    const unsigned smem = kp.smem_per_warp * kStepWarps;
-    if (!h->cfg.pendulum) return launch_one(step_kernel<T, false, -1, -1>, grid, smem, st, &kp, configure);
+template <typename T> static cudaError_t launch_step(DsimHandle *h, const KParams<T> &kp, cudaStream_t st) {
+    const unsigned smem = kp.smem_per_slot * kStages * kStepWarps;
+    if (!h->cfg.pendulum) return launch_one(h, step_kernel<T, false, -1, -1>, smem, st, &kp);
     if constexpr (std::is_same<T, float>::value) {
         const int o = kp.obs_id, r = kp.reward_id;
-        if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2) return launch_one(step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2>, grid, smem, st, &kp, configure);   // C4 / C5
-        if (o == DSIM_OBS_LOCAL_RPY && r == 1) return launch_one(step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1>, grid, smem, st, &kp, configure);                 // C3
-        if (o == DSIM_OBS_BASE && r == 0) return launch_one(step_kernel<float, true, DSIM_OBS_BASE, 0>, grid, smem, st, &kp, configure);                           // C2
+        if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2>, smem, st, &kp);   // C4 / C5
+        if (o == DSIM_OBS_LOCAL_RPY && r == 1) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1>, smem, st, &kp);                 // C3
+        if (o == DSIM_OBS_BASE && r == 0) return launch_one(h, step_kernel<float, true, DSIM_OBS_BASE, 0>, smem, st, &kp);                           // C2
     }
-    return launch_one(step_kernel<T, true, -1, -1>, grid, smem, st, &kp, configure);
+    return launch_one(h, step_kernel<T, true, -1, -1>, smem, st, &kp);
 }
 static int step_impl(DsimHandle *h, const void *actions_dev, void *stream, int eval_only) {
     CK(cudaSetDevice(h->device));
-    const bool configure = !h->smem_configured;
     if (h->cfg.precision == DSIM_FP32) {
         auto kp = make_params<float>(h, actions_dev);
         if (eval_only) { kp.frame_skip = 0; kp.eval_only = 1; }
-        CK(launch_step<float>(h, kp, (cudaStream_t)stream, configure));
+        CK(launch_step<float>(h, kp, (cudaStream_t)stream));
     } else {
         auto kp = make_params<double>(h, actions_dev);
         if (eval_only) { kp.frame_skip = 0; kp.eval_only = 1; }
-        CK(launch_step<double>(h, kp, (cudaStream_t)stream, configure));
+        CK(launch_step<double>(h, kp, (cudaStream_t)stream));
     }
-    h->smem_configured = 1;
     h->launches++;
     CK(cudaGetLastError());
     return DSIM_OK;
@@ -479,11 +490,13 @@ static int step_impl(DsimHandle *h, const void *actions_dev, void *stream, int e
 
 extern "C" int dsim_step(DsimHandle *h, const void *actions_dev, void *stream) {
     if (!h || !actions_dev) return DSIM_EINVAL;
+    if ((uintptr_t)actions_dev & 15u) return fail(h, DSIM_EINVAL, "actions must be 16-byte aligned (they are moved with bulk copies)%s", "");
     return step_impl(h, actions_dev, stream, 0);
 }
 
 extern "C" int dsim_evaluate(DsimHandle *h, const void *actions_dev, void *stream) {
     if (!h || !actions_dev) return DSIM_EINVAL;
+    if ((uintptr_t)actions_dev & 15u) return fail(h, DSIM_EINVAL, "actions must be 16-byte aligned (they are moved with bulk copies)%s", "");
     return step_impl(h, actions_dev, stream, 1);
 }
 

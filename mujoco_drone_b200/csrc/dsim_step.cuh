@@ -77,7 +77,7 @@ template <typename T> struct KParams {
     T uparams[6];
     int per_env_consts, auto_reset, obs_id, reward_id, obs_dim, frame_skip, max_steps;
     int eval_only;            // 1: termination / reward / obs of the CURRENT state, nothing advanced or stored
-    unsigned smem_per_warp;   // bytes
+    unsigned smem_per_slot;   // bytes of one page slot (each warp owns kStages of them)
     T h, max_distance_t;
     T ref_off[3], ref_yaw, start_t[3];
     double start[3], ref64[3], max_distance;
@@ -167,139 +167,236 @@ __host__ __device__ constexpr int obs_dim_of(int obs_id) {
     return obs_id == 0 ? 33 : obs_id == 1 ? 16 : obs_id == 2 ? 16 : obs_id == 3 ? 23 : obs_id == 4 ? 24 : obs_id == 5 ? 19 : obs_id == 6 ? 22 :
            obs_id == 7 ? 25 : obs_id == 8 ? 22 : obs_id == 9 ? 22 : obs_id == 10 ? 16 : obs_id == 11 ? 15 : obs_id == 13 ? 28 : obs_id == 14 ? 17 : 0;
 }
-// shared-memory slot of one warp: [RW page | RO page | setpoint page | observation block [32][obs_dim]]
-constexpr int kSlotObsOff = (RW_ROWS + RO_ROWS + REF_ROWS) * kTile;          // elements
+// shared-memory slot of one page: [RW page | union(RO page + setpoint page + actions [32][4], observation block [32][obs_dim])].
+// The observation block overlays the read-only operands: they are dead (held in registers) when it is written.
+constexpr int kSlotObsOff = RW_ROWS * kTile;                                  // elements
+constexpr int kSlotActOff = (RW_ROWS + RO_ROWS + REF_ROWS) * kTile;
 __host__ __device__ constexpr unsigned slot_bytes(int obs_dim, int elem) {
-    return (unsigned)((((kSlotObsOff + kTile * obs_dim) * elem) + 127) / 128 * 128);
+    const int in_elems = (RO_ROWS + REF_ROWS + 4) * kTile, out_elems = kTile * obs_dim;
+    return (unsigned)((((kSlotObsOff + (in_elems > out_elems ? in_elems : out_elems)) * elem) + 127) / 128 * 128);
+}
+#ifndef DSIM_STAGES
+#define DSIM_STAGES 2
+#endif
+constexpr int kStages = DSIM_STAGES;                                                    // slots per warp: compute in one, prefetch into the other
+
+// rare path, out of line: RLlib's reset_at() round trip (:334-351) folded into the step, WARP-COOPERATIVE.  A page
+// typically has 0-2 truncated envs per step; letting each of them run sample_state on its own lane would cost the whole
+// warp ~1000 divergent instructions.  Instead all 32 lanes work on one truncated env at a time: lanes 0-4 draw the five
+// Philox blocks, lanes 0-7 turn them into the eight Box-Muller pairs, lane 8 does the radius / yaw uniforms, the results
+// are exchanged with shuffles and the env's own lane writes its column (qpos / qvel rows, step counter) of the read-write
+// page in shared memory.  Same draws, same arithmetic as sample_state (dsim_device.cuh) = BaseDroneEnv.sample_state.
+template <typename T> DSIM_DEV T shfl_(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <typename T, bool PEND>
+__device__ __noinline__ void resample_page(unsigned need, T *s_rw, const ResetCfg<T> &rc, unsigned seed, unsigned env0, unsigned *reset_count) {
+    const int lane = threadIdx.x & 31;
+    while (need) {
+        const int L = __ffs(need) - 1;
+        need &= need - 1;
+        const unsigned rcnt = reset_count[L] + 1u;
+        __syncwarp();
+        if (lane == L) reset_count[L] = rcnt;
+        EnvState<T> s;
+        s.pos = mk(T(0), T(0), T(0)); s.vel = mk(T(0), T(0), T(0)); s.om = mk(T(0), T(0), T(0));
+        s.hx = s.hy = s.hvx = s.hvy = T(0);
+        T roll = 0, pitch = 0, yaw = rc.start_yaw;
+        if (rc.random_start_pos) {
+            const U4 x = philox4x32(lane < 5 ? lane : 0, rcnt, 0, 0, seed, env0 + L);
+            // Box-Muller pair of lane q (0..7): block / half of sample_state's draw order
+            const int blk = lane == 0 || lane == 1 ? 0 : lane == 2 ? 1 : lane == 3 || lane == 4 ? 2 : lane == 5 || lane == 6 ? 3 : lane == 7 ? 4 : 1;
+            const bool hi = lane == 1 || lane == 2 || lane == 4 || lane == 6;             // (z, w) words instead of (x, y)
+            const uint32_t wx = __shfl_sync(0xffffffffu, x.x, blk), wy = __shfl_sync(0xffffffffu, x.y, blk);
+            const uint32_t wz = __shfl_sync(0xffffffffu, x.z, blk), ww = __shfl_sync(0xffffffffu, x.w, blk);
+            T z0, z1;
+            box_muller(hi ? wz : wx, hi ? ww : wy, z0, z1);
+            // lane 8 (blk 1, low words): radius and yaw uniforms
+            const T rad = rc.max_pos_offset * cbrt_(u01<T>(wx)), yw = T(kPi) - T(2 * kPi) * u01<T>(wy);
+            const T n0 = shfl_(z0, 0), n1 = shfl_(z1, 0), n2 = shfl_(z0, 1);
+            const T inn = rsqrt_(n0 * n0 + n1 * n1 + n2 * n2), r = shfl_(rad, 8);
+            s.pos = mk(r * (n0 * inn), r * (n1 * inn), r * (n2 * inn));
+            yaw = shfl_(yw, 8);
+            roll = clipn(shfl_(z0, 2), rc.angle_sigma[0]); pitch = clipn(shfl_(z1, 2), rc.angle_sigma[1]);
+            s.vel = mk(clipn(shfl_(z0, 3), rc.vel_sigma[0]), clipn(shfl_(z1, 3), rc.vel_sigma[1]), clipn(shfl_(z0, 4), rc.vel_sigma[2]));
+            s.om = mk(clipn(shfl_(z1, 4), rc.ang_vel_sigma[0]), clipn(shfl_(z0, 5), rc.ang_vel_sigma[1]), clipn(shfl_(z1, 5), rc.ang_vel_sigma[2]));
+            if (PEND) {
+                s.hx = clipn(shfl_(z0, 6), rc.pend_rp_sigma[0]); s.hy = clipn(shfl_(z1, 6), rc.pend_rp_sigma[1]);
+                s.hvx = clipn(shfl_(z0, 7), rc.pend_vel_sigma[0]); s.hvy = clipn(shfl_(z1, 7), rc.pend_vel_sigma[1]);
+            }
+        }
+        if (lane == L) {
+            rpy_to_quat(roll, pitch, yaw, s.qw, s.qx, s.qy, s.qz);
+            T *col = s_rw + L;
+            col[0 * kTile] = s.pos.x; col[1 * kTile] = s.pos.y; col[2 * kTile] = s.pos.z;
+            col[3 * kTile] = s.qw; col[4 * kTile] = s.qx; col[5 * kTile] = s.qy; col[6 * kTile] = s.qz;
+            col[7 * kTile] = s.hx; col[8 * kTile] = s.hy;
+            col[9 * kTile] = s.vel.x; col[10 * kTile] = s.vel.y; col[11 * kTile] = s.vel.z;
+            col[12 * kTile] = s.om.x; col[13 * kTile] = s.om.y; col[14 * kTile] = s.om.z;
+            col[15 * kTile] = s.hvx; col[16 * kTile] = s.hvy;
+            col[RW_NUM_STEPS * kTile] = int_to_slot<T>(0);
+        }
+    }
+    __syncwarp();
 }
 
-// rare path, out of line: RLlib's reset_at() round trip (:334-351) folded into the step.  Works on the env's column of
-// the read-write page in shared memory (qpos / qvel rows and the step counter), so the hot path keeps no state
-// registers alive across the call.
-template <typename T, bool PEND>
-__device__ __noinline__ void resample_column(T *col, const ResetCfg<T> &rc, unsigned seed, unsigned env, unsigned *reset_count_slot) {
-    const unsigned rcnt = *reset_count_slot + 1u;
-    EnvState<T> s;
-    sample_state<T, PEND>(s, rc, seed, env, rcnt);
-    *reset_count_slot = rcnt;
-    col[0 * kTile] = s.pos.x; col[1 * kTile] = s.pos.y; col[2 * kTile] = s.pos.z;
-    col[3 * kTile] = s.qw; col[4 * kTile] = s.qx; col[5 * kTile] = s.qy; col[6 * kTile] = s.qz;
-    col[7 * kTile] = s.hx; col[8 * kTile] = s.hy;
-    col[9 * kTile] = s.vel.x; col[10 * kTile] = s.vel.y; col[11 * kTile] = s.vel.z;
-    col[12 * kTile] = s.om.x; col[13 * kTile] = s.om.y; col[14 * kTile] = s.om.z;
-    col[15 * kTile] = s.hvx; col[16 * kTile] = s.hvy;
-    col[RW_NUM_STEPS * kTile] = int_to_slot<T>(0);
+// this env's raw action row from the slot.  asm volatile: a fresh shared-memory read at each call site (never CSE'd into
+// four registers that would live across the physics)
+template <typename T> DSIM_DEV void load_action(const T *row, T a[4]) {
+    if constexpr (std::is_same<T, float>::value) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]) : "r"(smem_u32(row)));
+    } else {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a[0]), "=d"(a[1]) : "r"(smem_u32(row)));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a[2]), "=d"(a[3]) : "r"(smem_u32(row) + 16u));
+    }
+}
+
+// lane 0: arm the slot's mbarrier and start the page loads HBM -> slot
+template <typename T> DSIM_DEV void issue_page_loads(const KParams<T> &p, int page, T *slot, uint64_t *bar) {
+    constexpr uint32_t rwb = RW_ROWS * kTile * sizeof(T), rob = RO_ROWS * kTile * sizeof(T), rfb = REF_ROWS * kTile * sizeof(T);
+    const uint32_t acb = (uint32_t)min(kTile, p.n - page * kTile) * 4u * (uint32_t)sizeof(T);   // the policy's [n][4] action rows of this page
+    mbar_arrive_expect_tx(bar, rwb + acb + (p.per_env_consts ? rob : 0u) + (p.refp ? rfb : 0u));
+    bulk_g2s(slot, p.rw + (size_t)page * (RW_ROWS * kTile), rwb, bar);
+    bulk_g2s(slot + kSlotActOff, p.actions + (size_t)page * (kTile * 4), acb, bar);
+    if (p.per_env_consts) bulk_g2s(slot + RW_ROWS * kTile, p.ro + (size_t)page * (RO_ROWS * kTile), rob, bar);
+    if (p.refp) bulk_g2s(slot + (RW_ROWS + RO_ROWS) * kTile, p.refp + (size_t)page * (REF_ROWS * kTile), rfb, bar);
 }
 
 // OBS / REW >= 0 are compile-time specialisations of the wrapper class / reward function (smaller code, no dispatch
 // branches, constant observation width); -1 reads the ids from the parameter block.
+// PERSISTENT: the grid is sized to the resident-CTA capacity of the GPU; every warp walks pages wid, wid + W, ... and
+// prefetches its next page into its second slot while it computes on the current one.
 template <typename T, bool PEND, int OBS, int REW>
 __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_bar[kStepWarps];
+    __shared__ __align__(8) uint64_t s_bar[kStepWarps][kStages];
     constexpr int DC = (OBS >= 0 && PEND) ? obs_dim_of(OBS) : 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int page = blockIdx.x * kStepWarps + warp;
-    if (page >= p.npages) return;                                  // warps are autonomous: no CTA-wide barrier below
-    const int i = page * kTile + lane;
-    const bool active = i < p.n;                                   // pad lanes of the last page compute, but publish nothing
+    const int wid = blockIdx.x * kStepWarps + warp, wstride = gridDim.x * kStepWarps;
+    // Programmatic dependent launch: the NEXT kernel of the stream may be scheduled onto SMs as soon as this grid's CTAs
+    // retire (its launch latency and this grid's tail overlap); this grid in turn touches no global memory before every
+    // kernel ahead of it in the stream has completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (wid >= p.npages) return;                                   // warps are autonomous: no CTA-wide barrier below
     const int obs_id = OBS >= 0 ? OBS : p.obs_id, reward_id = REW >= 0 ? REW : p.reward_id;
     const int D = DC > 0 ? DC : p.obs_dim;
-    T *slot = reinterpret_cast<T *>(smem_raw + (size_t)warp * p.smem_per_warp);
-    T *s_rw = slot, *s_ro = slot + RW_ROWS * kTile, *s_ref = slot + (RW_ROWS + RO_ROWS) * kTile, *s_obs = slot + kSlotObsOff;
-    uint64_t *bar = &s_bar[warp];
-
-    // ---- page loads: HBM -> this warp's slot
+    unsigned char *wslots = smem_raw + (size_t)warp * kStages * p.smem_per_slot;
     if (lane == 0) {
-        mbar_init(bar, 1);
-        constexpr uint32_t rwb = RW_ROWS * kTile * sizeof(T), rob = RO_ROWS * kTile * sizeof(T), rfb = REF_ROWS * kTile * sizeof(T);
-        mbar_arrive_expect_tx(bar, rwb + (p.per_env_consts ? rob : 0u) + (p.refp ? rfb : 0u));
-        bulk_g2s(s_rw, p.rw + (size_t)page * (RW_ROWS * kTile), rwb, bar);
-        if (p.per_env_consts) bulk_g2s(s_ro, p.ro + (size_t)page * (RO_ROWS * kTile), rob, bar);
-        if (p.refp) bulk_g2s(s_ref, p.refp + (size_t)page * (REF_ROWS * kTile), rfb, bar);
-    }
-    T a[4] = {T(0), T(0), T(0), T(0)};
-    if (active) {
-        if constexpr (std::is_same<T, float>::value) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(p.actions) + i);
-            a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-        } else {
-            const double2 v0 = __ldg(reinterpret_cast<const double2 *>(p.actions) + 2 * (size_t)i);
-            const double2 v1 = __ldg(reinterpret_cast<const double2 *>(p.actions) + 2 * (size_t)i + 1);
-            a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y;
-        }
+        #pragma unroll
+        for (int k = 0; k < kStages; k++) mbar_init(&s_bar[warp][k], 1);
+        issue_page_loads(p, wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0]);
     }
     __syncwarp();                                                  // barrier init visible to the waiting lanes
-    mbar_wait(bar, 0);
+    unsigned parity = 0;                                           // bit b: phase of this warp's barrier b
+    int buf = 0;
+    #pragma unroll 1
+    for (int page = wid; page < p.npages; page += wstride, buf ^= (kStages - 1)) {
+        const int i = page * kTile + lane;
+        const bool active = i < p.n;                               // pad lanes of the last page compute, but publish nothing
+        T *slot = reinterpret_cast<T *>(wslots + (size_t)buf * p.smem_per_slot);
+        T *s_rw = slot, *s_ro = slot + RW_ROWS * kTile, *s_ref = slot + (RW_ROWS + RO_ROWS) * kTile, *s_obs = slot + kSlotObsOff;
+        mbar_wait(&s_bar[warp][buf], (parity >> buf) & 1u);
+        parity ^= 1u << buf;
 
-    // ---- physics
-    T *col = s_rw + lane;
-    const T *ro_col = s_ro + lane;
-    EnvState<T> s = load_state(col);
-    {
-        const EnvConsts<T> c = load_consts(p, ro_col);
-        T ctrl[4];
-        #pragma unroll
-        for (int k = 0; k < 4; k++) ctrl[k] = clamp_(T(0.1) + T(0.9) * a[k], T(0), T(1));   // :269 + ctrlrange (0,1) clamp of mj_fwdActuation
-        #pragma unroll 1
-        for (int f = 0; f < p.frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
-    }
-
-    // ---- counters, termination, reward, observation
-    int ns = slot_to_int(col[RW_NUM_STEPS * kTile]) + (p.eval_only ? 0 : 1);
-    const unsigned env = p.env_base + (unsigned)i;
-    // MuJoCo's mj_checkPos/Vel/Acc warn and reset the whole MjData; here the one env is parked on a finite state for
-    // the outputs of this step, flagged truncated, counted, and re-sampled below.  Never silent.
-    const bool bad = !state_finite(s);
-    if (bad) {
-        s.pos = mk(T(0), T(0), T(0)); s.qw = T(1); s.qx = s.qy = s.qz = T(0); s.hx = s.hy = s.hvx = s.hvy = T(0);
-        s.vel = mk(T(0), T(0), T(0)); s.om = mk(T(0), T(0), T(0)); s.acc = mk(T(0), T(0), T(0));
-        #pragma unroll
-        for (int k = 0; k < 4; k++) s.act[k] = T(0);
-    }
-    V3<T> ref_off; T ref_yaw; double ref64[3];
-    load_ref(p, s_ref + lane, ref_off, ref_yaw, ref64);
-    T prm[6];
-    load_params(p, ro_col, prm);
-    const PostState<T> ps = post_state(s, ref_off, ref_yaw);
-    const bool trunc = terminated(s.pos, p.start, ref64, p.max_distance, ns, p.max_steps) || bad;
-    const T rew = bad ? T(0) : reward_fn<T, PEND>(reward_id, s, ps, a, ns, prm, p.max_distance_t);
-    {
-        ObsWriter<T, 1> w; w.base = s_obs + lane * D; w.stride = 1;
-        emit_obs<T, PEND>(obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
-    }
-    if (active) {
-        p.reward[i] = rew;
-        p.trunc[i] = trunc ? 1 : 0;
-    }
-
-    if (!p.eval_only) {
-        // would-be ground contact (the floor plane is out of reach in the BASELINE configs; detected, never ignored)
-        if (active && p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(p.stats + 4, 1.0);
-        T ret = col[RW_EP_RETURN * kTile] + rew;
-        if (trunc && active) {
-            atomicAdd(p.stats + 0, (double)ret); atomicAdd(p.stats + 1, (double)ns); atomicAdd(p.stats + 2, 1.0);
-            if (bad) atomicAdd(p.stats + 3, 1.0);
+        // ---- physics
+        T *col = s_rw + lane;
+        const T *ro_col = s_ro + lane;
+        const T *s_act = slot + kSlotActOff + 4 * lane;             // this env's raw action row (pad lanes: stale, finite or not — never published)
+        EnvState<T> s = load_state(col);
+        {
+            const EnvConsts<T> c = load_consts(p, ro_col);
+            T a[4], ctrl[4];
+            load_action(s_act, a);
+            #pragma unroll
+            for (int k = 0; k < 4; k++) ctrl[k] = clamp_(T(0.1) + T(0.9) * a[k], T(0), T(1));   // :269 + ctrlrange (0,1) clamp of mj_fwdActuation
+            #pragma unroll 1
+            for (int f = 0; f < p.frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
         }
-        col[RW_EP_RETURN * kTile] = trunc ? T(0) : ret;
-        col[RW_NUM_STEPS * kTile] = int_to_slot<T>(ns);
-        store_state(col, s);
-        if (trunc && (p.auto_reset || bad)) resample_column<T, PEND>(col, p.rc, p.seed, env, p.reset_count + i);
-    }
+        // ---- prefetch the next page into the other slot.  Its previous contents left with the bulk stores issued at the
+        // end of the previous iteration; by now their shared-memory reads have long completed, so the wait is free.
+        if (kStages == 2 && lane == 0 && page + wstride < p.npages) {
+            bulk_wait_read();
+            issue_page_loads(p, page + wstride, reinterpret_cast<T *>(wslots + (size_t)(buf ^ 1) * p.smem_per_slot), &s_bar[warp][buf ^ 1]);
+        }
 
-    // ---- publish: slot -> HBM
-    fence_async_smem();
-    __syncwarp();
-    const int nvalid = min(kTile, p.n - page * kTile);
-    const uint32_t obs_bytes = (uint32_t)(nvalid * D) * (uint32_t)sizeof(T);
-    T *gobs = p.obs + (size_t)page * kTile * D;
-    const bool obs_bulk = (obs_bytes & 15u) == 0;                  // always true for full pages
-    if (lane == 0) {
-        if (!p.eval_only) bulk_s2g(p.rw + (size_t)page * (RW_ROWS * kTile), s_rw, RW_ROWS * kTile * sizeof(T));
-        if (obs_bulk) bulk_s2g(gobs, s_obs, obs_bytes);
-        bulk_commit();
+        // ---- counters, termination, reward, observation
+        int ns = slot_to_int(col[RW_NUM_STEPS * kTile]) + (p.eval_only ? 0 : 1);
+        // MuJoCo's mj_checkPos/Vel/Acc warn and reset the whole MjData; here the one env is parked on a finite state for
+        // the outputs of this step, flagged truncated, counted, and re-sampled below.  Never silent.
+        const bool bad = !state_finite(s);
+        if (bad) {
+            s.pos = mk(T(0), T(0), T(0)); s.qw = T(1); s.qx = s.qy = s.qz = T(0); s.hx = s.hy = s.hvx = s.hvy = T(0);
+            s.vel = mk(T(0), T(0), T(0)); s.om = mk(T(0), T(0), T(0)); s.acc = mk(T(0), T(0), T(0));
+            #pragma unroll
+            for (int k = 0; k < 4; k++) s.act[k] = T(0);
+        }
+        V3<T> ref_off; T ref_yaw; double ref64[3];
+        load_ref(p, s_ref + lane, ref_off, ref_yaw, ref64);
+        T prm[6];
+        load_params(p, ro_col, prm);
+        const PostState<T> ps = post_state(s, ref_off, ref_yaw);
+        const bool trunc = terminated(s.pos, p.start, ref64, p.max_distance, ns, p.max_steps) || bad;
+        T a[4];
+        load_action(s_act, a);                                     // re-read instead of holding four registers across the physics
+        const T rew = bad ? T(0) : reward_fn<T, PEND>(reward_id, s, ps, a, ns, prm, p.max_distance_t);
+        __syncwarp();                                              // every lane has its read-only operands in registers:
+        if constexpr (DC > 0 && DC % 2 == 0 && std::is_same<T, float>::value) {
+            // the observation block may now overlay them.  Compile-time layout: components are gathered in registers and
+            // leave as 8- / 16-byte shared-memory stores (row pitch DC floats: conflict-free for DC = 22, 4-way for DC = 16
+            // instead of the 2- / 16-way conflicts of scalar stores)
+            float o[DC];
+            emit_obs<T, PEND>(obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, [&](int j, float v) { o[j] = v; });
+            float *row = s_obs + lane * DC;
+            if constexpr (DC % 4 == 0) {
+                #pragma unroll
+                for (int k = 0; k < DC / 4; k++) reinterpret_cast<float4 *>(row)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            } else {
+                #pragma unroll
+                for (int k = 0; k < DC / 2; k++) reinterpret_cast<float2 *>(row)[k] = make_float2(o[2 * k], o[2 * k + 1]);
+            }
+        } else {
+            ObsWriter<T, 1> w; w.base = s_obs + lane * D; w.stride = 1;
+            emit_obs<T, PEND>(obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
+        }
+        if (active) {
+            p.reward[i] = rew;
+            p.trunc[i] = trunc ? 1 : 0;
+        }
+
+        if (!p.eval_only) {
+            // would-be ground contact (the floor plane is out of reach in the BASELINE configs; detected, never ignored)
+            if (active && p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(p.stats + 4, 1.0);
+            T ret = col[RW_EP_RETURN * kTile] + rew;
+            if (trunc && active) {
+                atomicAdd(p.stats + 0, (double)ret); atomicAdd(p.stats + 1, (double)ns); atomicAdd(p.stats + 2, 1.0);
+                if (bad) atomicAdd(p.stats + 3, 1.0);
+            }
+            col[RW_EP_RETURN * kTile] = trunc ? T(0) : ret;
+            col[RW_NUM_STEPS * kTile] = int_to_slot<T>(ns);
+            store_state(col, s);
+        }
+        {
+            const unsigned need = __ballot_sync(0xffffffffu, !p.eval_only && active && trunc && (p.auto_reset || bad));
+            if (need) resample_page<T, PEND>(need, s_rw, p.rc, p.seed, p.env_base + (unsigned)(page * kTile), p.reset_count + page * kTile);
+        }
+
+        // ---- publish: slot -> HBM
+        fence_async_smem();
+        __syncwarp();
+        const int nvalid = min(kTile, p.n - page * kTile);
+        const uint32_t obs_bytes = (uint32_t)(nvalid * D) * (uint32_t)sizeof(T);
+        T *gobs = p.obs + (size_t)page * kTile * D;
+        const bool obs_bulk = (obs_bytes & 15u) == 0;              // always true for full pages
+        if (lane == 0) {
+            if (!p.eval_only) bulk_s2g(p.rw + (size_t)page * (RW_ROWS * kTile), s_rw, RW_ROWS * kTile * sizeof(T));
+            if (obs_bulk) bulk_s2g(gobs, s_obs, obs_bytes);
+            bulk_commit();
+        }
+        if (!obs_bulk)                                             // ragged last page whose byte count is not a multiple of 16
+            for (int e = lane; e < nvalid * D; e += kTile) gobs[e] = s_obs[e];
+        if (kStages == 1 && page + wstride < p.npages) {           // single slot: the next page can only come in once this one has left
+            __syncwarp();
+            if (lane == 0) { bulk_wait_read(); issue_page_loads(p, page + wstride, slot, &s_bar[warp][0]); }
+        }
     }
-    if (!obs_bulk)                                                 // ragged last page whose byte count is not a multiple of 16
-        for (int e = lane; e < nvalid * D; e += kTile) gobs[e] = s_obs[e];
-    if (lane == 0) bulk_wait_read();                               // the slot must outlive the bulk reads
+    if (lane == 0) bulk_wait_read();                               // the slots must outlive the bulk reads
 }

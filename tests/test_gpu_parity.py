@@ -289,6 +289,35 @@ def test_vector_env_protocol_and_auto_reset(oracle):
     env.close()
 
 
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_auto_reset_state_matches_oracle(oracle, precision):
+    """the warp-cooperative in-kernel reset (native loop) draws exactly BaseDroneEnv.sample_state's stream: the state an env
+    holds right after its truncation step == oracle.sample_state(seed, global env id, reset count).  Ragged env count,
+    sparse resets (distance) and whole-page resets (max_steps)."""
+    import torch
+    n = 203
+    env = _mk(num_drones=n, precision=precision, auto_reset=True, max_steps=6, max_distance=0.9, env_id_offset=77,
+              angle_variance=[0.3, 0.2], state_difficulty=0.4)
+    cfg = oracle.make_reset_cfg([0, 0, 15, 0], 0.4 * 2, [0.12, 0.08], [0.4] * 3, [0.4] * 3, [0.2] * 2, [0.2] * 2, True, True)
+    env.reset_tensor()
+    resets = np.zeros(n, dtype=np.int64)
+    tol = 1e-12 if precision == "fp64" else 2e-6
+    seen = 0
+    for t in range(14):
+        _, _, trunc = env.step_tensor(torch.rand((n, 4), device="cuda", dtype=torch.float64 if precision == "fp64" else torch.float32))
+        tr = trunc.cpu().numpy().astype(bool)
+        resets += tr
+        qp, qv, _, _, ns = env.get_state()
+        for i in np.nonzero(tr)[0]:
+            oq, ov = oracle.sample_state(cfg, env.seed_value, 77 + int(i), int(resets[i]))
+            np.testing.assert_allclose(qp[i], oq, atol=tol)
+            np.testing.assert_allclose(qv[i], ov, atol=tol)
+            assert ns[i] == 0
+            seen += 1
+    assert seen > n and (resets > 0).all()
+    env.close()
+
+
 def test_open_loop_trajectory_fp32_vs_oracle(oracle):
     """100 steps open loop near hover: FP32 kernel trajectory vs FP64 oracle, |d pos| <= 1e-3 m"""
     import torch
