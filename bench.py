@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads / hot-L2 measurements")
-    ap.add_argument("--preroll", type=int, default=160, help="untimed steps per replica before the warm-up (reach the steady-state reset rate)")
+    ap.add_argument("--preroll", type=int, default=1500, help="untimed steps per replica before the warm-up (reach the steady-state reset rate)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

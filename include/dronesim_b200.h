@@ -138,6 +138,7 @@ int dsim_sync(DsimHandle *h, void *stream);
 
 /* -- instrumentation */
 int64_t dsim_launch_count(const DsimHandle *h);                                 /* kernels launched by this handle */
+int dsim_debug_timeline(DsimHandle *h, uint64_t *out /*[npages][8] %globaltimer ns*/, int64_t capacity);   /* needs DSIM_TIMELINE=1 at create */
 int dsim_kernel_info(int which /*0 step fp32, 1 step fp64*/, int32_t *regs, int32_t *local_bytes, int32_t *max_threads);
 
 #ifdef __cplusplus

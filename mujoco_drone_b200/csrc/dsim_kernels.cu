@@ -142,7 +142,8 @@ struct DsimHandle {
     size_t rs;                        // sizeof(real)
     void *rw, *ro, *refp, *obs, *reward, *states33, *actions_stage;
     double *params64, *stats, *center_hw;
-    unsigned *reset_count;
+    unsigned long long *timeline;
+    unsigned *reset_count, *ticket;
     unsigned char *trunc;
     int per_env_consts;
     double uconst[C_ROWS], uparams[6];
@@ -203,6 +204,7 @@ template <typename T> static KParams<T> make_params(const DsimHandle *h, const v
     for (int k = 0; k < 3; k++) { p.rc.vel_sigma[k] = (T)c.vel_sigma[k]; p.rc.ang_vel_sigma[k] = (T)c.ang_vel_sigma[k]; }
     p.rc.random_start_pos = c.random_start_pos;
     p.seed = c.seed; p.env_base = (unsigned)c.env_id_offset;
+    p.timeline = h->timeline; p.ticket = h->ticket;
     return p;
 }
 
@@ -286,6 +288,8 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
     ALLOC(h->center_hw, 12 * sizeof(double));
     ALLOC(h->reset_count, ld * sizeof(unsigned));
     ALLOC(h->trunc, ld);
+    ALLOC(h->ticket, 256);
+    if (getenv("DSIM_TIMELINE")) ALLOC(h->timeline, (size_t)h->npages * 8 * sizeof(unsigned long long));   // debug instrumentation
 #undef ALLOC
     double chw[12];
     for (int k = 0; k < 6; k++) { chw[k] = cfg->param_center[k]; chw[6 + k] = cfg->param_halfwidth[k]; }
@@ -310,7 +314,7 @@ extern "C" void dsim_destroy(DsimHandle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->rw, h->ro, h->refp, h->obs, h->reward, h->states33, h->actions_stage,
-                    h->params64, h->stats, h->center_hw, h->reset_count, h->trunc};
+                    h->params64, h->stats, h->center_hw, h->reset_count, h->trunc, h->timeline, h->ticket};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -676,6 +680,17 @@ extern "C" int dsim_sync(DsimHandle *h, void *stream) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return DSIM_OK;
+}
+
+// debug: per-warp %globaltimer stamps of the last step launch (only when the handle was created with DSIM_TIMELINE set)
+extern "C" int dsim_debug_timeline(DsimHandle *h, uint64_t *out, int64_t capacity) {
+    if (!h || !out) return DSIM_EINVAL;
+    if (!h->timeline) return fail(h, DSIM_EUNSUPPORTED, "create the handle with DSIM_TIMELINE set in the environment%s", "");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    const int64_t cnt = (int64_t)h->npages * 8;
+    CK(cudaMemcpy(out, h->timeline, (size_t)(cnt < capacity ? cnt : capacity) * 8, cudaMemcpyDeviceToHost));
+    return (int)(cnt < capacity ? cnt : capacity) > 0 ? DSIM_OK : DSIM_EINVAL;
 }
 
 extern "C" int64_t dsim_launch_count(const DsimHandle *h) { return h ? h->launches : 0; }

@@ -83,6 +83,8 @@ template <typename T> struct KParams {
     double start[3], ref64[3], max_distance;
     ResetCfg<T> rc;
     unsigned seed, env_base;
+    unsigned *ticket;               // work-stealing page counter (0 between launches)
+    unsigned long long *timeline;   // debug: [gridDim * warps][8] %globaltimer stamps of the last launch, or nullptr
 };
 
 // integer rows of the read-write page are stored in a lane-sized slot (int32 for float pages, int64 for double)
@@ -175,57 +177,68 @@ __host__ __device__ constexpr unsigned slot_bytes(int obs_dim, int elem) {
     const int in_elems = (RO_ROWS + REF_ROWS + 4) * kTile, out_elems = kTile * obs_dim;
     return (unsigned)((((kSlotObsOff + (in_elems > out_elems ? in_elems : out_elems)) * elem) + 127) / 128 * 128);
 }
-#ifndef DSIM_STAGES
-#define DSIM_STAGES 2
-#endif
-constexpr int kStages = DSIM_STAGES;                                                    // slots per warp: compute in one, prefetch into the other
+constexpr int kStages = 2;                                                    // slots per warp: compute in one, prefetch into the other
 
 // rare path, out of line: RLlib's reset_at() round trip (:334-351) folded into the step, WARP-COOPERATIVE.  A page
-// typically has 0-2 truncated envs per step; letting each of them run sample_state on its own lane would cost the whole
-// warp ~1000 divergent instructions.  Instead all 32 lanes work on one truncated env at a time: lanes 0-4 draw the five
-// Philox blocks, lanes 0-7 turn them into the eight Box-Muller pairs, lane 8 does the radius / yaw uniforms, the results
-// are exchanged with shuffles and the env's own lane writes its column (qpos / qvel rows, step counter) of the read-write
-// page in shared memory.  Same draws, same arithmetic as sample_state (dsim_device.cuh) = BaseDroneEnv.sample_state.
+// has 0-2 truncated envs in most steps (and many right after a synchronised start); letting each of them run sample_state
+// on its own lane would cost the whole warp ~1000 divergent instructions per reset.  Instead the warp handles up to FOUR
+// truncated envs per pass: lane 8 e + q draws the Philox block and computes Box-Muller pair q (0..7) of env e (0..3), the
+// sixteen normals + two uniforms of each env are gathered with shuffles by the env's own lane, which assembles the state
+// and writes its column (qpos / qvel rows, step counter) of the read-write page in shared memory.
+// Same draws, same arithmetic as sample_state (dsim_device.cuh) = BaseDroneEnv.sample_state (:218-257).
 template <typename T> DSIM_DEV T shfl_(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 template <typename T, bool PEND>
 __device__ __noinline__ void resample_page(unsigned need, T *s_rw, const ResetCfg<T> &rc, unsigned seed, unsigned env0, unsigned *reset_count) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, e = lane >> 3, q = lane & 7;
     while (need) {
-        const int L = __ffs(need) - 1;
-        need &= need - 1;
-        const unsigned rcnt = reset_count[L] + 1u;
-        __syncwarp();
-        if (lane == L) reset_count[L] = rcnt;
-        EnvState<T> s;
-        s.pos = mk(T(0), T(0), T(0)); s.vel = mk(T(0), T(0), T(0)); s.om = mk(T(0), T(0), T(0));
-        s.hx = s.hy = s.hvx = s.hvy = T(0);
-        T roll = 0, pitch = 0, yaw = rc.start_yaw;
-        if (rc.random_start_pos) {
-            const U4 x = philox4x32(lane < 5 ? lane : 0, rcnt, 0, 0, seed, env0 + L);
-            // Box-Muller pair of lane q (0..7): block / half of sample_state's draw order
-            const int blk = lane == 0 || lane == 1 ? 0 : lane == 2 ? 1 : lane == 3 || lane == 4 ? 2 : lane == 5 || lane == 6 ? 3 : lane == 7 ? 4 : 1;
-            const bool hi = lane == 1 || lane == 2 || lane == 4 || lane == 6;             // (z, w) words instead of (x, y)
-            const uint32_t wx = __shfl_sync(0xffffffffu, x.x, blk), wy = __shfl_sync(0xffffffffu, x.y, blk);
-            const uint32_t wz = __shfl_sync(0xffffffffu, x.z, blk), ww = __shfl_sync(0xffffffffu, x.w, blk);
-            T z0, z1;
-            box_muller(hi ? wz : wx, hi ? ww : wy, z0, z1);
-            // lane 8 (blk 1, low words): radius and yaw uniforms
-            const T rad = rc.max_pos_offset * cbrt_(u01<T>(wx)), yw = T(kPi) - T(2 * kPi) * u01<T>(wy);
-            const T n0 = shfl_(z0, 0), n1 = shfl_(z1, 0), n2 = shfl_(z0, 1);
-            const T inn = rsqrt_(n0 * n0 + n1 * n1 + n2 * n2), r = shfl_(rad, 8);
-            s.pos = mk(r * (n0 * inn), r * (n1 * inn), r * (n2 * inn));
-            yaw = shfl_(yw, 8);
-            roll = clipn(shfl_(z0, 2), rc.angle_sigma[0]); pitch = clipn(shfl_(z1, 2), rc.angle_sigma[1]);
-            s.vel = mk(clipn(shfl_(z0, 3), rc.vel_sigma[0]), clipn(shfl_(z1, 3), rc.vel_sigma[1]), clipn(shfl_(z0, 4), rc.vel_sigma[2]));
-            s.om = mk(clipn(shfl_(z1, 4), rc.ang_vel_sigma[0]), clipn(shfl_(z0, 5), rc.ang_vel_sigma[1]), clipn(shfl_(z1, 5), rc.ang_vel_sigma[2]));
-            if (PEND) {
-                s.hx = clipn(shfl_(z0, 6), rc.pend_rp_sigma[0]); s.hy = clipn(shfl_(z1, 6), rc.pend_rp_sigma[1]);
-                s.hvx = clipn(shfl_(z0, 7), rc.pend_vel_sigma[0]); s.hvy = clipn(shfl_(z1, 7), rc.pend_vel_sigma[1]);
-            }
+        // the (up to) four lowest truncated lanes of this pass: P[k]; this lane computes for env P[e], and owns env `lane` if selected
+        int P[4], mine = -1, own = -1;
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            P[k] = need ? __ffs(need) - 1 : -1;
+            need &= need - 1;
+            if (k == e) mine = P[k];
+            if (P[k] == lane) own = k;
         }
-        if (lane == L) {
+        T z0 = T(0), z1 = T(0), rad = T(0), yw = T(0);
+        unsigned rcnt = 0;
+        if (mine >= 0) rcnt = reset_count[mine] + 1u;
+        __syncwarp();
+        if (mine >= 0 && rc.random_start_pos) {
+            // Box-Muller pair q: Philox block / word half of sample_state's draw order
+            const int blk = q <= 1 ? 0 : q == 2 ? 1 : q <= 4 ? 2 : q <= 6 ? 3 : 4;
+            const bool hi = q == 1 || q == 2 || q == 4 || q == 6;                 // (z, w) words instead of (x, y)
+            const U4 x = philox4x32(blk, rcnt, 0, 0, seed, env0 + mine);
+            box_muller(hi ? x.z : x.x, hi ? x.w : x.y, z0, z1);
+            if (q == 2) { rad = rc.max_pos_offset * cbrt_(u01<T>(x.x)); yw = T(kPi) - T(2 * kPi) * u01<T>(x.y); }   // block 1, low words
+        }
+        const int src = 8 * (own >= 0 ? own : 0);
+        const T n0 = shfl_(z0, src), n1 = shfl_(z1, src), n2 = shfl_(z0, src + 1);
+        const T rp0 = shfl_(z0, src + 2), rp1 = shfl_(z1, src + 2), r = shfl_(rad, src + 2), yaw_s = shfl_(yw, src + 2);
+        const T v0 = shfl_(z0, src + 3), v1 = shfl_(z1, src + 3), v2 = shfl_(z0, src + 4), w0 = shfl_(z1, src + 4);
+        const T w1 = shfl_(z0, src + 5), w2 = shfl_(z1, src + 5), h0 = shfl_(z0, src + 6), h1 = shfl_(z1, src + 6);
+        const T g0 = shfl_(z0, src + 7), g1 = shfl_(z1, src + 7);
+        const unsigned rc_own = __shfl_sync(0xffffffffu, rcnt, src);
+        if (own >= 0) {
+            EnvState<T> s;
+            s.pos = mk(T(0), T(0), T(0)); s.vel = mk(T(0), T(0), T(0)); s.om = mk(T(0), T(0), T(0));
+            s.hx = s.hy = s.hvx = s.hvy = T(0);
+            T roll = 0, pitch = 0, yaw = rc.start_yaw;
+            if (rc.random_start_pos) {
+                const T inn = rsqrt_(n0 * n0 + n1 * n1 + n2 * n2);
+                s.pos = mk(r * (n0 * inn), r * (n1 * inn), r * (n2 * inn));
+                yaw = yaw_s;
+                roll = clipn(rp0, rc.angle_sigma[0]); pitch = clipn(rp1, rc.angle_sigma[1]);
+                s.vel = mk(clipn(v0, rc.vel_sigma[0]), clipn(v1, rc.vel_sigma[1]), clipn(v2, rc.vel_sigma[2]));
+                s.om = mk(clipn(w0, rc.ang_vel_sigma[0]), clipn(w1, rc.ang_vel_sigma[1]), clipn(w2, rc.ang_vel_sigma[2]));
+                if (PEND) {
+                    s.hx = clipn(h0, rc.pend_rp_sigma[0]); s.hy = clipn(h1, rc.pend_rp_sigma[1]);
+                    s.hvx = clipn(g0, rc.pend_vel_sigma[0]); s.hvy = clipn(g1, rc.pend_vel_sigma[1]);
+                }
+            }
             rpy_to_quat(roll, pitch, yaw, s.qw, s.qx, s.qy, s.qz);
-            T *col = s_rw + L;
+            reset_count[lane] = rc_own;
+            T *col = s_rw + lane;
             col[0 * kTile] = s.pos.x; col[1 * kTile] = s.pos.y; col[2 * kTile] = s.pos.z;
             col[3 * kTile] = s.qw; col[4 * kTile] = s.qx; col[5 * kTile] = s.qy; col[6 * kTile] = s.qz;
             col[7 * kTile] = s.hx; col[8 * kTile] = s.hy;
@@ -234,8 +247,8 @@ __device__ __noinline__ void resample_page(unsigned need, T *s_rw, const ResetCf
             col[15 * kTile] = s.hvx; col[16 * kTile] = s.hvy;
             col[RW_NUM_STEPS * kTile] = int_to_slot<T>(0);
         }
+        __syncwarp();
     }
-    __syncwarp();
 }
 
 // this env's raw action row from the slot.  asm volatile: a fresh shared-memory read at each call site (never CSE'd into
@@ -262,21 +275,37 @@ template <typename T> DSIM_DEV void issue_page_loads(const KParams<T> &p, int pa
 
 // OBS / REW >= 0 are compile-time specialisations of the wrapper class / reward function (smaller code, no dispatch
 // branches, constant observation width); -1 reads the ids from the parameter block.
-// PERSISTENT: the grid is sized to the resident-CTA capacity of the GPU; every warp walks pages wid, wid + W, ... and
-// prefetches its next page into its second slot while it computes on the current one.
+// PERSISTENT + WORK-STEALING: the grid is sized to the resident-CTA capacity of the GPU (W warps).  Warp w starts on page
+// w; every further page comes from a global ticket counter (page = W + ticket), grabbed one iteration ahead so that the
+// page can be prefetched into the warp's second slot while the current one is being computed.  Pages are not equally
+// expensive (in-kernel resets) and W rarely divides the page count, so static striding leaves a long tail.  Every active
+// warp's last grab fails; the warp that draws the last ticket of the launch re-zeroes the counter (nobody grabs after it,
+// and the next launch only starts grabbing once this grid has completed), so launches and CUDA-graph replays need no host reset.
 template <typename T, bool PEND, int OBS, int REW>
 __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[kStepWarps][kStages];
     constexpr int DC = (OBS >= 0 && PEND) ? obs_dim_of(OBS) : 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wid = blockIdx.x * kStepWarps + warp, wstride = gridDim.x * kStepWarps;
+    const int wid = blockIdx.x * kStepWarps + warp, nwarps = gridDim.x * kStepWarps;
     // Programmatic dependent launch: the NEXT kernel of the stream may be scheduled onto SMs as soon as this grid's CTAs
     // retire (its launch latency and this grid's tail overlap); this grid in turn touches no global memory before every
     // kernel ahead of it in the stream has completed and flushed.
+    unsigned long long t_entry = 0;
+    if (p.timeline) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (wid >= p.npages) return;                                   // warps are autonomous: no CTA-wide barrier below
+    if (wid >= p.npages) return;
+    int tl_k = 1;
+    auto stamp = [&]() {
+        if (p.timeline && lane == 0 && tl_k < 8) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.timeline[(size_t)wid * 8 + tl_k++] = t;
+        }
+    };
+    if (p.timeline && lane == 0) p.timeline[(size_t)wid * 8] = t_entry;
+    stamp();                                                       // [1] dependency wait passed                                   // warps are autonomous: no CTA-wide barrier below
     const int obs_id = OBS >= 0 ? OBS : p.obs_id, reward_id = REW >= 0 ? REW : p.reward_id;
     const int D = DC > 0 ? DC : p.obs_dim;
     unsigned char *wslots = smem_raw + (size_t)warp * kStages * p.smem_per_slot;
@@ -288,14 +317,23 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     __syncwarp();                                                  // barrier init visible to the waiting lanes
     unsigned parity = 0;                                           // bit b: phase of this warp's barrier b
     int buf = 0;
+    const unsigned last_ticket = (unsigned)(max(p.npages - nwarps, 0) + min(nwarps, p.npages) - 1);
+    int page = wid;
     #pragma unroll 1
-    for (int page = wid; page < p.npages; page += wstride, buf ^= (kStages - 1)) {
+    while (page < p.npages) {
+        int next = 0;
+        if (lane == 0) {                                           // grab the page after this one (result first needed after the physics)
+            const unsigned tk = atomicAdd(p.ticket, 1u);
+            if (tk == last_ticket) *p.ticket = 0u;
+            next = nwarps + (int)tk;
+        }
         const int i = page * kTile + lane;
         const bool active = i < p.n;                               // pad lanes of the last page compute, but publish nothing
         T *slot = reinterpret_cast<T *>(wslots + (size_t)buf * p.smem_per_slot);
         T *s_rw = slot, *s_ro = slot + RW_ROWS * kTile, *s_ref = slot + (RW_ROWS + RO_ROWS) * kTile, *s_obs = slot + kSlotObsOff;
         mbar_wait(&s_bar[warp][buf], (parity >> buf) & 1u);
         parity ^= 1u << buf;
+        stamp();                                                   // [2], [4]: page landed
 
         // ---- physics
         T *col = s_rw + lane;
@@ -313,9 +351,9 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         }
         // ---- prefetch the next page into the other slot.  Its previous contents left with the bulk stores issued at the
         // end of the previous iteration; by now their shared-memory reads have long completed, so the wait is free.
-        if (kStages == 2 && lane == 0 && page + wstride < p.npages) {
+        if (lane == 0 && next < p.npages) {
             bulk_wait_read();
-            issue_page_loads(p, page + wstride, reinterpret_cast<T *>(wslots + (size_t)(buf ^ 1) * p.smem_per_slot), &s_bar[warp][buf ^ 1]);
+            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + (size_t)(buf ^ 1) * p.smem_per_slot), &s_bar[warp][buf ^ 1]);
         }
 
         // ---- counters, termination, reward, observation
@@ -391,12 +429,16 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             if (obs_bulk) bulk_s2g(gobs, s_obs, obs_bytes);
             bulk_commit();
         }
+        stamp();                                                   // [3], [5]: page published
         if (!obs_bulk)                                             // ragged last page whose byte count is not a multiple of 16
             for (int e = lane; e < nvalid * D; e += kTile) gobs[e] = s_obs[e];
-        if (kStages == 1 && page + wstride < p.npages) {           // single slot: the next page can only come in once this one has left
-            __syncwarp();
-            if (lane == 0) { bulk_wait_read(); issue_page_loads(p, page + wstride, slot, &s_bar[warp][0]); }
-        }
+        page = __shfl_sync(0xffffffffu, next, 0);
+        buf ^= 1;
     }
     if (lane == 0) bulk_wait_read();                               // the slots must outlive the bulk reads
+    if (p.timeline && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.timeline[(size_t)wid * 8 + 7] = t;                        // [7] exit
+    }
 }
