@@ -89,19 +89,6 @@ template <typename T> DSIM_DEV T log_(T x) { if constexpr (std::is_same<T, float
 template <typename T> DSIM_DEV T cbrt_(T x) { if constexpr (std::is_same<T, float>::value) return cbrtf(x); else return cbrt(x); }
 template <typename T> DSIM_DEV void sincos_(T a, T *s, T *c) { if constexpr (std::is_same<T, float>::value) sincosf(a, s, c); else sincos(a, s, c); }
 template <typename T> DSIM_DEV bool finite_(T x) { return isfinite(x); }
-// sin / cos of the half rotation angle of one integration step (h |w| / 2, almost always << 1): Taylor polynomials on
-// |a| <= 0.8 (relative error < 1e-7 in FP32), libm beyond
-template <typename T> DSIM_DEV void sincos_small(T a, T *s, T *c) {
-    if constexpr (std::is_same<T, float>::value) {
-        if (fabsf(a) <= 0.8f) {
-            const float z = a * a;
-            float ps = fmaf(z, 2.7557319e-6f, -1.9841270e-4f); ps = fmaf(ps, z, 8.3333333e-3f); ps = fmaf(ps, z, -1.6666667e-1f);
-            *s = fmaf(ps * z, a, a);
-            float pc = fmaf(z, -2.7557319e-7f, 2.4801587e-5f); pc = fmaf(pc, z, -1.3888889e-3f); pc = fmaf(pc, z, 4.1666667e-2f); pc = fmaf(pc, z, -0.5f);
-            *c = fmaf(pc, z, 1.0f);
-        } else sincosf(a, s, c);
-    } else sincos(a, s, c);
-}
 template <typename T> DSIM_DEV T clamp_(T x, T lo, T hi) { return min_(max_(x, lo), hi); }
 // (a + pi) % (2 pi) - pi with Python's sign convention (rewards.py / observation_wrappers.py / scipy as_euler):
 // a - 2 pi floor((a + pi) / 2 pi); returns `a` itself when it already lies in [-pi, pi)
@@ -204,10 +191,10 @@ template <typename T> DSIM_DEV V3<T> ldl3_solve(const Ldl3<T> &f, V3<T> b) {
 template <typename T, bool PEND, bool ADVANCE>
 DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T h) {
     // -- kinematics (mj_kinematics normalises the free-joint quaternion)
-    T qn = s.qw * s.qw + s.qx * s.qx + s.qy * s.qy + s.qz * s.qz;
-    T qi = rsqrt_(qn);
-    if (!(qn >= T(1e-30))) { s.qw = T(1); s.qx = s.qy = s.qz = T(0); qi = T(1); }
-    T qw = s.qw * qi, qx = s.qx * qi, qy = s.qy * qi, qz = s.qz * qi;
+    const T qn = s.qw * s.qw + s.qx * s.qx + s.qy * s.qy + s.qz * s.qz;
+    const bool qok = qn >= T(1e-30);                                         // mju_normalize4: a (near-)zero quaternion becomes identity
+    const T qi = rsqrt_(qn);
+    const T qw = qok ? s.qw * qi : T(1), qx = qok ? s.qx * qi : T(0), qy = qok ? s.qy * qi : T(0), qz = qok ? s.qz * qi : T(0);
     const M3<T> R = quat_to_mat(qw, qx, qy, qz);
     const V3<T> vb = tmul(R, s.vel);                                         // origin velocity, body coords
     const V3<T> gb = mk(T(-kGravity) * R.m[6], T(-kGravity) * R.m[7], T(-kGravity) * R.m[8]);   // R^T g
@@ -356,15 +343,31 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
         s.vel = s.vel + h * mul(R, a_i);
         s.om = s.om + h * al_i;
         s.pos = s.pos + h * s.vel;
-        // mju_quatIntegrate: q <- normalize(q) * axisangle(w/|w|, h|w|)
+        // mju_quatIntegrate: q <- normalize(q) * axisangle(w/|w|, h|w|) = normalize(q) * [cos(a), sin(a)/|w| * w], a = h|w|/2.
+        // FP32: even Taylor series in z = a^2 (no square root, no division, exact identity for w = 0 like MuJoCo's
+        // |w| < mjMINVAL branch); relative error < 1e-7 for a <= 0.8, i.e. |w| <= 160 rad/s at 100 Hz; libm beyond.
         const T w2 = dot(s.om, s.om);
-        T rw = T(1), rx_ = T(0), ry_ = T(0), rz_ = T(0);
-        if (w2 >= T(1e-30)) {
-            const T iw = rsqrt_(w2), wn = w2 * iw;
-            T sh, ch;
-            sincos_small(T(0.5) * h * wn, &sh, &ch);
-            rw = ch; rx_ = sh * s.om.x * iw; ry_ = sh * s.om.y * iw; rz_ = sh * s.om.z * iw;
+        T rw = T(1), kq = T(0);
+        if constexpr (std::is_same<T, float>::value) {
+            const float z = (0.25f * h * h) * w2;
+            if (z <= 0.64f) {
+                float ps = fmaf(z, 2.7557319e-6f, -1.9841270e-4f); ps = fmaf(ps, z, 8.3333333e-3f); ps = fmaf(ps, z, -1.6666667e-1f);
+                kq = (0.5f * h) * fmaf(ps, z, 1.0f);
+                float pc = fmaf(z, -2.7557319e-7f, 2.4801587e-5f); pc = fmaf(pc, z, -1.3888889e-3f); pc = fmaf(pc, z, 4.1666667e-2f); pc = fmaf(pc, z, -0.5f);
+                rw = fmaf(pc, z, 1.0f);
+            } else {
+                const float iw = rsqrt_(w2), wn = w2 * iw;
+                float sh;
+                sincosf(0.5f * h * wn, &sh, &rw);
+                kq = sh * iw;
+            }
+        } else if (w2 >= T(1e-30)) {
+            const T wn = sqrt_(w2);
+            T sh;
+            sincos_(T(0.5) * h * wn, &sh, &rw);
+            kq = sh / wn;
         }
+        const T rx_ = kq * s.om.x, ry_ = kq * s.om.y, rz_ = kq * s.om.z;
         s.qw = qw * rw - qx * rx_ - qy * ry_ - qz * rz_;
         s.qx = qw * rx_ + qx * rw + qy * rz_ - qz * ry_;
         s.qy = qw * ry_ - qx * rz_ + qy * rw + qz * rx_;

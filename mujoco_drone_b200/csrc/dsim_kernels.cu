@@ -178,6 +178,16 @@ extern "C" int dsim_obs_dim(int obs_id, int pendulum) {
 
 extern "C" const char *dsim_last_error(const DsimHandle *h) { return h ? h->err : g_create_err; }
 
+// largest double t with sqrt_rn(t) <= d: turns `sqrt(d2) > max_distance` into the bit-identical `d2 > t` (see terminated())
+static double max_distance_sq_threshold(double d) {
+    if (!(d >= 0)) return -1.0;                       // negative / NaN radius: everything is "too far" (sqrt(d2) > d always holds for d < 0)
+    if (isinf(d)) return d;
+    double t = d * d;
+    while (sqrt(t) > d) t = nextafter(t, 0.0);
+    while (sqrt(nextafter(t, INFINITY)) <= d) t = nextafter(t, INFINITY);
+    return t;
+}
+
 template <typename T> static KParams<T> make_params(const DsimHandle *h, const void *actions) {
     KParams<T> p;
     memset(&p, 0, sizeof p);
@@ -193,7 +203,7 @@ template <typename T> static KParams<T> make_params(const DsimHandle *h, const v
     p.obs_dim = h->obs_dim; p.frame_skip = c.frame_skip;
     p.max_steps = (int)(c.max_steps > 2147483647LL ? 2147483647LL : c.max_steps);
     p.smem_per_slot = slot_bytes(h->obs_dim, (int)sizeof(T));
-    p.h = (T)h->h; p.max_distance_t = (T)c.max_distance; p.max_distance = c.max_distance;
+    p.h = (T)h->h; p.max_distance_t = (T)c.max_distance; p.max_d2 = max_distance_sq_threshold(c.max_distance);
     for (int k = 0; k < 3; k++) {
         p.ref_off[k] = (T)(c.reference[k] - c.start_pos[k]);
         p.start_t[k] = (T)c.start_pos[k]; p.start[k] = c.start_pos[k]; p.ref64[k] = c.reference[k];

@@ -31,13 +31,16 @@ template <typename T> DSIM_DEV PostState<T> post_state(const EnvState<T> &s, V3<
 
 // default_termination_fcn (BaseDroneEnv.py:12-16) in FP64 on the stored state, operation order fixed
 // ((dx*dx + dy*dy) + dz*dz, no FMA contraction) so the truncation bit equals the CPU oracle's on identical inputs.
+// `max_d2` = the largest double whose correctly rounded square root is <= max_distance (computed on the host,
+// max_distance_sq_threshold): sqrt_rn is monotonic, so  sqrt_rn(d2) > max_distance  <=>  d2 > max_d2  bit for bit, and
+// the kernel needs no FP64 square root.
 template <typename T>
-DSIM_DEV bool terminated(V3<T> pos_off, const double start[3], const double ref[3], double max_distance, int num_steps, int max_steps) {
+DSIM_DEV bool terminated(V3<T> pos_off, const double start[3], const double ref[3], double max_d2, int num_steps, int max_steps) {
     const double dx = __dsub_rn(__dadd_rn(start[0], (double)pos_off.x), ref[0]);
     const double dy = __dsub_rn(__dadd_rn(start[1], (double)pos_off.y), ref[1]);
     const double dz = __dsub_rn(__dadd_rn(start[2], (double)pos_off.z), ref[2]);
     const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    return (__dsqrt_rn(d2) > max_distance) || (num_steps >= max_steps);
+    return (d2 > max_d2) || (num_steps >= max_steps);
 }
 
 template <typename T> DSIM_DEV T sq(T x) { return x * x; }

@@ -80,7 +80,7 @@ template <typename T> struct KParams {
     unsigned smem_per_slot;   // bytes of one page slot (each warp owns kStages of them)
     T h, max_distance_t;
     T ref_off[3], ref_yaw, start_t[3];
-    double start[3], ref64[3], max_distance;
+    double start[3], ref64[3], max_d2;         // max_d2: see terminated()
     ResetCfg<T> rc;
     unsigned seed, env_base;
     unsigned *ticket;               // work-stealing page counter (0 between launches)
@@ -152,11 +152,13 @@ template <typename T> DSIM_DEV void load_ref(const KParams<T> &p, const T *ref_c
         ref64[0] = p.ref64[0]; ref64[1] = p.ref64[1]; ref64[2] = p.ref64[2];
     }
 }
+// mj_checkPos / mj_checkVel: any NaN / Inf / |x| > mjMAXVAL (1e10) in qpos, qvel, act.  One sum of magnitudes: NaN and Inf
+// propagate, nothing cancels, and a NaN fails the comparison.
 template <typename T> DSIM_DEV bool state_finite(const EnvState<T> &s) {
-    const T a = s.pos.x + s.pos.y + s.pos.z + s.qw + s.qx + s.qy + s.qz + s.hx + s.hy;
-    const T b = s.vel.x + s.vel.y + s.vel.z + s.om.x + s.om.y + s.om.z + s.hvx + s.hvy + s.act[0] + s.act[1] + s.act[2] + s.act[3];
-    // MuJoCo's mj_check* also rejects |x| > mjMAXVAL (1e10)
-    return finite_(a) && finite_(b) && abs_(a) < T(1e10) && abs_(b) < T(1e10);
+    const T a = abs_(s.pos.x) + abs_(s.pos.y) + abs_(s.pos.z) + abs_(s.qw) + abs_(s.qx) + abs_(s.qy) + abs_(s.qz) + abs_(s.hx) + abs_(s.hy)
+              + abs_(s.vel.x) + abs_(s.vel.y) + abs_(s.vel.z) + abs_(s.om.x) + abs_(s.om.y) + abs_(s.om.z) + abs_(s.hvx) + abs_(s.hvy)
+              + abs_(s.act[0]) + abs_(s.act[1]) + abs_(s.act[2]) + abs_(s.act[3]);
+    return a < T(1e10);
 }
 // observation component sink: `base[j * stride]`; STRIDE > 0 fixes the stride at compile time
 template <typename T, int STRIDE = 0> struct ObsWriter {
@@ -340,6 +342,13 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         const T *ro_col = s_ro + lane;
         const T *s_act = slot + kSlotActOff + 4 * lane;             // this env's raw action row (pad lanes: stale, finite or not — never published)
         EnvState<T> s = load_state(col);
+        // ---- prefetch the next page into the other slot.  Its previous contents left with the bulk stores issued at the
+        // end of the previous iteration; their shared-memory reads complete within a few hundred cycles.
+        if (lane == 0 && next < p.npages) {
+            bulk_wait_read();
+            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + (size_t)(buf ^ 1) * p.smem_per_slot), &s_bar[warp][buf ^ 1]);
+        }
+
         {
             const EnvConsts<T> c = load_consts(p, ro_col);
             T a[4], ctrl[4];
@@ -349,13 +358,6 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             #pragma unroll 1
             for (int f = 0; f < p.frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
         }
-        // ---- prefetch the next page into the other slot.  Its previous contents left with the bulk stores issued at the
-        // end of the previous iteration; by now their shared-memory reads have long completed, so the wait is free.
-        if (lane == 0 && next < p.npages) {
-            bulk_wait_read();
-            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + (size_t)(buf ^ 1) * p.smem_per_slot), &s_bar[warp][buf ^ 1]);
-        }
-
         // ---- counters, termination, reward, observation
         int ns = slot_to_int(col[RW_NUM_STEPS * kTile]) + (p.eval_only ? 0 : 1);
         // MuJoCo's mj_checkPos/Vel/Acc warn and reset the whole MjData; here the one env is parked on a finite state for
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         T prm[6];
         load_params(p, ro_col, prm);
         const PostState<T> ps = post_state(s, ref_off, ref_yaw);
-        const bool trunc = terminated(s.pos, p.start, ref64, p.max_distance, ns, p.max_steps) || bad;
+        const bool trunc = terminated(s.pos, p.start, ref64, p.max_d2, ns, p.max_steps) || bad;
         T a[4];
         load_action(s_act, a);                                     // re-read instead of holding four registers across the physics
         const T rew = bad ? T(0) : reward_fn<T, PEND>(reward_id, s, ps, a, ns, prm, p.max_distance_t);
