@@ -1,0 +1,28 @@
+#!/bin/bash
+# Copy the judged evidence of one profiling pass from gpurun_out/ (scratch) into profiles/ (tracked):
+#   profiles/<tag>_launches.csv   ncu launch list (gpu__time_duration per launch, cold-cache, serialised)
+#   profiles/<tag>_step_kernel.txt  summary of the `ncu --set full` capture of the step kernel (raw metrics, stall
+#                                   reasons, opcode mix, top stalled SASS lines)
+# usage: tools/publish_profile.sh <tag>
+set -e
+TAG=$1
+mkdir -p profiles
+python - "$TAG" <<'PY'
+import csv, sys, collections
+tag = sys.argv[1]
+rows = [r for r in csv.reader(open(f"gpurun_out/launches_{tag}.csv")) if len(r) > 10 and r[0].isdigit()]
+with open(f"profiles/{tag}_launches.csv", "w") as f:
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  (python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras)\n")
+    f.write("id,kernel,grid,block,duration_ns\n")
+    for r in rows:
+        f.write(f"{r[0]},\"{r[4]}\",\"{r[8]}\",\"{r[7]}\",{r[-1]}\n")
+    tot = collections.Counter(); cnt = collections.Counter()
+    for r in rows:
+        k = r[4].split('(')[0]; tot[k] += float(r[-1]); cnt[k] += 1
+    s = sum(tot.values())
+    f.write("# share of summed device time per kernel\n")
+    for k, v in tot.most_common():
+        f.write(f"# {100 * v / s:5.1f}%  n={cnt[k]:4d}  avg {v / cnt[k] / 1e3:8.2f} us  {k}\n")
+PY
+python tools/ncu_summary.py gpurun_out/prof_$TAG.ncu-rep > profiles/${TAG}_step_kernel.txt
+tail -12 profiles/${TAG}_launches.csv
