@@ -408,18 +408,37 @@ DSIM_DEV U4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint3
     return o;
 }
 template <typename T> DSIM_DEV T u01(uint32_t x) { return (T(x >> 8) + T(0.5)) * T(1.0 / 16777216.0); }
+// Samplers.  FP32: MUFU-based log2 / sin / cos / exp2 (arguments are already range-reduced: u in (0,1), angle in (0, 2 pi)),
+// a few instructions each instead of libm's ~25 with slow-path branches; the draws are random numbers, ~1e-6 relative
+// accuracy is irrelevant for them and stays inside the stated FP32 reset tolerance.  FP64 keeps libm.
 template <typename T> DSIM_DEV void box_muller(uint32_t x0, uint32_t x1, T &z0, T &z1) {
-    const T r = sqrt_(T(-2) * log_(u01<T>(x0)));
-    T s, c;
-    sincos_(T(2 * kPi) * u01<T>(x1), &s, &c);
-    z0 = r * c; z1 = r * s;
+    if constexpr (std::is_same<T, float>::value) {
+        const float r = sqrt_(-1.3862943611f * __log2f(u01<float>(x0)));          // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
+        const float a = 6.2831853072f * u01<float>(x1);
+        z0 = r * __cosf(a); z1 = r * __sinf(a);
+    } else {
+        const T r = sqrt_(T(-2) * log_(u01<T>(x0)));
+        T s, c;
+        sincos_(T(2 * kPi) * u01<T>(x1), &s, &c);
+        z0 = r * c; z1 = r * s;
+    }
+}
+// cube root of a uniform in (0,1)
+template <typename T> DSIM_DEV T cbrt01(T u) {
+    if constexpr (std::is_same<T, float>::value) return exp2f(__log2f(u) * 0.33333333333f); else return cbrt(u);
 }
 template <typename T> DSIM_DEV T clipn(T z, T sigma) { const T v = z * sigma, lim = T(2) * sigma; return clamp_(v, -lim, lim); }
 
-// mujoco_rpy2quat (transformation.py:10-12): qz(yaw) * qy(pitch) * qx(roll)
+// mujoco_rpy2quat (transformation.py:10-12): qz(yaw) * qy(pitch) * qx(roll).  Reset path only (angles are sampled in
+// [-pi, pi], half angles in [-pi/2, pi/2]): FP32 uses the MUFU sin / cos (abs. error < 5e-7 on that range).
 template <typename T> DSIM_DEV void rpy_to_quat(T roll, T pitch, T yaw, T &qw, T &qx, T &qy, T &qz) {
     T sr, cr, sp, cp, sy, cy;
-    sincos_(T(0.5) * roll, &sr, &cr); sincos_(T(0.5) * pitch, &sp, &cp); sincos_(T(0.5) * yaw, &sy, &cy);
+    if constexpr (std::is_same<T, float>::value) {
+        sr = __sinf(0.5f * roll); cr = __cosf(0.5f * roll); sp = __sinf(0.5f * pitch); cp = __cosf(0.5f * pitch);
+        sy = __sinf(0.5f * yaw); cy = __cosf(0.5f * yaw);
+    } else {
+        sincos_(T(0.5) * roll, &sr, &cr); sincos_(T(0.5) * pitch, &sp, &cp); sincos_(T(0.5) * yaw, &sy, &cy);
+    }
     qw = cy * cp * cr + sy * sp * sr;
     qx = cy * cp * sr - sy * sp * cr;
     qy = cy * sp * cr + sy * cp * sr;
@@ -446,7 +465,7 @@ DSIM_DEV void sample_state(EnvState<T> &s, const ResetCfg<T> &rc, uint32_t seed,
         box_muller(x.x, x.y, n0, n1); box_muller(x.z, x.w, n2, n3);
         const T inn = rsqrt_(n0 * n0 + n1 * n1 + n2 * n2);
         x = philox4x32(1, count, 0, 0, seed, env);
-        const T r = rc.max_pos_offset * cbrt_(u01<T>(x.x));
+        const T r = rc.max_pos_offset * cbrt01(u01<T>(x.x));
         s.pos = mk(r * (n0 * inn), r * (n1 * inn), r * (n2 * inn));
         yaw = T(kPi) - T(2 * kPi) * u01<T>(x.y);
         box_muller(x.z, x.w, n0, n1);

@@ -212,7 +212,7 @@ __device__ __noinline__ void resample_page(unsigned need, T *s_rw, const ResetCf
             const bool hi = q == 1 || q == 2 || q == 4 || q == 6;                 // (z, w) words instead of (x, y)
             const U4 x = philox4x32(blk, rcnt, 0, 0, seed, env0 + mine);
             box_muller(hi ? x.z : x.x, hi ? x.w : x.y, z0, z1);
-            if (q == 2) { rad = rc.max_pos_offset * cbrt_(u01<T>(x.x)); yw = T(kPi) - T(2 * kPi) * u01<T>(x.y); }   // block 1, low words
+            if (q == 2) { rad = rc.max_pos_offset * cbrt01(u01<T>(x.x)); yw = T(kPi) - T(2 * kPi) * u01<T>(x.y); }   // block 1, low words
         }
         const int src = 8 * (own >= 0 ? own : 0);
         const T n0 = shfl_(z0, src), n1 = shfl_(z1, src), n2 = shfl_(z0, src + 1);

@@ -301,7 +301,7 @@ def test_auto_reset_state_matches_oracle(oracle, precision):
     cfg = oracle.make_reset_cfg([0, 0, 15, 0], 0.4 * 2, [0.12, 0.08], [0.4] * 3, [0.4] * 3, [0.2] * 2, [0.2] * 2, True, True)
     env.reset_tensor()
     resets = np.zeros(n, dtype=np.int64)
-    tol = 1e-12 if precision == "fp64" else 2e-6
+    tol = 1e-12 if precision == "fp64" else 1e-5      # FP32 reset path: MUFU log2/sin/cos/exp2 draws
     seen = 0
     for t in range(14):
         _, _, trunc = env.step_tensor(torch.rand((n, 4), device="cuda", dtype=torch.float64 if precision == "fp64" else torch.float32))

@@ -3,7 +3,7 @@
 for lib in mujoco_drone_b200/libdronesim_b200.so mujoco_drone_b200/variants/*.so; do
   for wl in c4 c4x4; do
     echo -n "$lib $wl "
-    DSIM_LIB=$PWD/$lib python bench.py --steps 400 --warmup 10 --workload $wl --no-cpu-baseline 2>&1 | python -c "
+    DSIM_LIB=$PWD/$lib python bench.py --steps 400 --warmup 10 $BENCH_EXTRA --workload $wl --no-cpu-baseline 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

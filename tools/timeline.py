@@ -16,8 +16,17 @@ env = bench.make_env(wl, n, 0, 0)
 env.reset_tensor()
 a = torch.rand((n, 4), device="cuda")
 flush = torch.zeros(256 * 1024 * 1024 // 4, device="cuda")
-for i in range(120):
+pre = int(sys.argv[3]) if len(sys.argv) > 3 else 1500
+for i in range(pre):
     env.step_tensor(a)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(200):
+    env.step_tensor(a)
+e1.record()
+torch.cuda.synchronize()
+print(f"back-to-back period (hot L2, {pre} pre-roll steps): {e0.elapsed_time(e1) * 1e3 / 200:.2f} us/step")
 res = []
 for rep in range(5):
     if mode == "cold":
@@ -34,8 +43,10 @@ for rep in range(5):
     t = t[act]
     t0 = t[:, 0].min()
     two = t[:, 4] > 0
+    three = t[:, 6] > 0
     def st(x):
-        return f"min {x.min() - t0:6d} med {int(np.median(x)) - t0:6d} max {x.max() - t0:6d}"
+        q = np.percentile(x - t0, [0, 50, 90, 99, 100]).astype(int)
+        return "min %6d med %6d p90 %6d p99 %6d max %6d" % tuple(q)
     print(f"--- rep {rep} ({mode}) event {e0.elapsed_time(e1) * 1e3:.1f} us; warps {len(t)} (two pages: {two.sum()}); ns since first CTA entry:")
     print("entry        ", st(t[:, 0]))
     print("dep wait done", st(t[:, 1]))
@@ -44,7 +55,7 @@ for rep in range(5):
     if two.any():
         print("page2 landed ", st(t[two, 4]))
         print("page2 publ.  ", st(t[two, 5]))
-    print("exit         ", st(t[:, 7]))
+    print("exit         ", st(t[:, 7]), f" (warps with >=3 pages: {int(three.sum())})")
     print("per-warp: load wait med", int(np.median(t[:, 2] - t[:, 1])), " page1 compute med", int(np.median(t[:, 3] - t[:, 2])),
           " page2 compute med", int(np.median(t[two, 5] - t[two, 4])) if two.any() else 0, " exit wait med", int(np.median(t[:, 7] - np.where(two, t[:, 5], t[:, 3]))))
 env.close()
