@@ -42,6 +42,11 @@ WORKLOADS = {
     "c4x4": dict(cls="LocalFrameRPYParamsEnv", reward="distance_energy_reward", envs_per_gpu=524288, alg_bytes=104 + 94 + 88 + 24,
                  cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True),
                  name="C4 env at 524288 envs/GPU (the per-GPU env count of config 5)"),
+    # BASELINE.json configs[4]: the full rollout loop, 4M envs over 8 GPUs = 524288 per GPU: RMA_full forward (random init,
+    # param_embed_dim 8, train_adaptation False) -> MyBetaDist sampling -> fused env step, CUDA-graph replayed
+    "c5": dict(cls="LocalFrameRPYParamsEnv", reward="distance_energy_reward", envs_per_gpu=524288, alg_bytes=104 + 94 + 88 + 24,
+               cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True), rollout=True,
+               name="C5: rollout loop = RMA_full policy (library GEMMs) + MyBetaDist sampling kernel + fused env-step kernel, 524288 envs/GPU (4M over 8 GPUs)"),
 }
 
 
@@ -84,16 +89,23 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def _poll(self):
+    def sample_now(self):
+        """one synchronous NVML sample (called from the launching thread inside the timed loop: the polling thread can be
+        starved by the GIL while the main thread is busy launching)"""
+        if self.nvml is None:
+            return
         nv = self.nvml
+        try:
+            clk = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.samples.append((time.time(), clk, rs))
+        except Exception:
+            pass
+
+    def _poll(self):
         while not self._stop:
-            try:
-                clk = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((time.time(), clk, rs))
-            except Exception:
-                pass
+            self.sample_now()
             time.sleep(0.0005)
 
     def _stop_nvml(self, t0, t1):
@@ -107,7 +119,7 @@ class ClockSampler:
         inside = [(c, r) for ts, c, r in self.samples if t0 <= ts <= t1]
         reasons = sorted({nm for _, r in inside for nm, b in bits.items() if r & b})
         return {"sm_mhz": float(np.median([c for c, _ in inside])) if inside else None, "sm_max_mhz": self.mx, "reasons": reasons,
-                "samples": len(inside), "source": "nvml polled continuously during the timed region"}
+                "samples": len(inside), "source": "nvml sampled from the launching thread every 32 steps of the timed region + a polling thread"}
 
     def stop(self, t0, t1):
         if self.nvml is not None:
@@ -213,6 +225,91 @@ def run_reference_arm(args, wl, rank, world):
     }))
 
 
+def run_rollout_workload(args, wl, rank, world, local_rank):
+    """config 5: policy + sampling + env step per "step", one CUDA graph replay each; single replica (its working set,
+    state + activations, is already larger than L2)"""
+    import torch
+    import torch.distributed as dist
+    import mujoco_drone_b200 as M
+    from mujoco_drone_b200 import dist as ddist
+    dev = torch.device("cuda", local_rank)
+    n = wl["envs_per_gpu"]
+    env = make_env(wl, n, rank * n, local_rank)
+    pol = M.policy.make_rma_full()
+    runner = M.rollout.RolloutRunner(env, pol, horizon=1, seed=42 + rank, policy_dtype=args.policy_dtype, use_graph=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    runner._capture()
+    for _ in range(min(args.preroll, 300) + max(args.warmup, 3)):
+        runner._graph.replay()
+        runner._obs_cur.copy_(runner._obs_next)
+    barrier()
+    l0 = env.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        if sampler is not None and i % 32 == 16:
+            sampler.sample_now()
+        runner._graph.replay()
+        runner._obs_cur.copy_(runner._obs_next)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    stats = ddist.allreduce_episode_stats(env.episode_stats(), device=dev)
+    # env-step kernel alone inside the same loop (for the roofline of the dominant hand-written kernel)
+    a = torch.rand((n, 4), device=dev)
+    for _ in range(5):
+        env.step_tensor(a)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(50):
+        env.step_tensor(a)
+    k1.record()
+    torch.cuda.synchronize(dev)
+    k_ms = k0.elapsed_time(k1) / 50
+    # end to end through host buffers: host actions in, host obs/reward/truncated out (policy on the host side of the boundary)
+    h_act = torch.rand((n, 4)).pin_memory()
+    h_obs, h_rew, h_tr = torch.empty((n, env.obs_dim)).pin_memory(), torch.empty((n,)).pin_memory(), torch.empty((n,), dtype=torch.uint8).pin_memory()
+    for _ in range(3):
+        env.step_host(h_act.numpy(), h_obs.numpy(), h_rew.numpy(), h_tr.numpy())
+    tt = time.perf_counter()
+    for _ in range(10):
+        env.step_host(h_act.numpy(), h_obs.numpy(), h_rew.numpy(), h_tr.numpy())
+    e2e = world * n * 10 / (time.perf_counter() - tt)
+    peak, peak_src = measured_peaks()
+    achieved = wl["alg_bytes"] * n / (k_ms * 1e-3) / 1e9
+    line = {
+        "metric": "env-steps/sec", "value": world * n * args.steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 env step; policy GEMMs " + args.policy_dtype, "data": "synthetic",
+        "config": {"workload": wl["name"], "envs_per_gpu": n, "total_envs": n * world, "policy": "RMA_full random init (6->32->8 | 28->256->128+BN | 128->128->8 | 128->128->128->1)",
+                   "sampling": "MyBetaDist, Philox Marsaglia-Tsang", "graph": "one CUDA graph replay per step",
+                   "l2": "inputs larger than L2 (env state + activations of 524288 envs)", "parallelism": f"env-sharded x{world}, no data-path collective"},
+        "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * (4 * env.obs_dim + 5),
+                "api": "dsim_step_host (C ABI), host-side policy boundary"},
+        "gpu_launches": int(env.launch_count() - l0),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "step_kernel<float,true> timed alone at this size", "algorithmic_bytes_per_env_step": wl["alg_bytes"], "peak_source": peak_src,
+                     "env_step_kernel_ms": k_ms, "share_of_loop": k_ms / (ms / args.steps)},
+        "clocks": clocks,
+        "episode_stats": {k: stats[k] for k in ("n_episodes", "mean_return", "mean_length", "n_nonfinite", "n_near_ground")},
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    env.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,6 +320,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads / hot-L2 measurements")
+    ap.add_argument("--policy-dtype", default="bf16", choices=["fp32", "tf32", "bf16"], help="c5: dtype of the policy GEMMs")
     ap.add_argument("--preroll", type=int, default=1500, help="untimed steps per replica before the warm-up (reach the steady-state reset rate)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -245,6 +343,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if wl.get("rollout"):
+        run_rollout_workload(args, wl, rank, world, local_rank)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     n = wl["envs_per_gpu"]                                    # weak scaling: fixed envs per GPU
     # L2-cold inputs without a flush kernel inside the timed region: R independent replicas of the workload (distinct
     # global env ids, so distinct Philox streams), stepped round-robin.  Their combined working set (state + constants +
@@ -269,9 +372,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def run_steps(k, envs_):
+    def run_steps(k, envs_, sampler_=None):
         """k vector_steps, round-robin over the replicas; setpoints re-drawn every 50 steps of each replica (C3)"""
         for i in range(k):
+            if sampler_ is not None and i % 32 == 16:
+                sampler_.sample_now()                          # clocks DURING the timed region (the queue of launches is far ahead of the GPU)
             e = envs_[i % len(envs_)]
             if axes is not None and (i // len(envs_)) % 50 == 0:
                 e.control_reference_tensor(axes)
@@ -288,7 +393,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()
-    run_steps(args.steps, envs)
+    run_steps(args.steps, envs, sampler)
     e1.record()
     barrier()
     t1 = time.time()

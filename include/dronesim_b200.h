@@ -136,6 +136,13 @@ int dsim_buffer(DsimHandle *h, int buf_id, void **dev_ptr, int64_t *rows, int64_
 int dsim_stats(DsimHandle *h, double out[8], int reset);                        /* episode statistics (device sync) */
 int dsim_sync(DsimHandle *h, void *stream);
 
+/* -- caller side of the path: MyBetaDist (distributions.py:6-38) on the policy head's logits.
+ *    logits [n][8] (alpha-logits then beta-logits, torch.chunk order), actions [n][4] in (0,1) (what dsim_step consumes),
+ *    logp [n] or NULL.  Philox stream keyed by (seed, env_id_offset + i), counter (.., step, ..): pass a new `step` each call. */
+int dsim_beta_policy(const void *logits_dev, int n, int precision, uint32_t seed, int64_t env_id_offset, uint32_t step,
+                     const uint32_t *step_dev /* NULL, or a device counter ADDED to `step` (CUDA-graph replays) */,
+                     int deterministic /* 1: Beta mean (deterministic_sample, :24-26) */, void *actions_dev, void *logp_dev, void *stream);
+
 /* -- instrumentation */
 int64_t dsim_launch_count(const DsimHandle *h);                                 /* kernels launched by this handle */
 int dsim_debug_timeline(DsimHandle *h, uint64_t *out /*[npages][8] %globaltimer ns*/, int64_t capacity);   /* needs DSIM_TIMELINE=1 at create */

@@ -15,6 +15,7 @@
 #include "dsim_device.cuh"
 #include "dsim_obs_reward.cuh"
 #include "dsim_params.cuh"
+#include "dsim_policy.cuh"
 
 using namespace dsim;
 
@@ -701,6 +702,20 @@ extern "C" int dsim_debug_timeline(DsimHandle *h, uint64_t *out, int64_t capacit
     const int64_t cnt = (int64_t)h->npages * 8;
     CK(cudaMemcpy(out, h->timeline, (size_t)(cnt < capacity ? cnt : capacity) * 8, cudaMemcpyDeviceToHost));
     return (int)(cnt < capacity ? cnt : capacity) > 0 ? DSIM_OK : DSIM_EINVAL;
+}
+
+// MyBetaDist sampling / mean + log-probability for the policy head's logits (distributions.py:6-38); no handle needed
+extern "C" int dsim_beta_policy(const void *logits_dev, int n, int precision, uint32_t seed, int64_t env_id_offset, uint32_t step,
+                                const uint32_t *step_dev, int deterministic, void *actions_dev, void *logp_dev, void *stream) {
+    if (!logits_dev || !actions_dev || n <= 0) return DSIM_EINVAL;
+    if (precision != DSIM_FP32 && precision != DSIM_FP64) return DSIM_EINVAL;
+    const int grid = (n + 127) / 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == DSIM_FP32)
+        beta_policy_kernel<float, 4><<<grid, 128, 0, st>>>(n, (const float *)logits_dev, seed, (uint32_t)env_id_offset, step, step_dev, deterministic, (float *)actions_dev, (float *)logp_dev);
+    else
+        beta_policy_kernel<double, 4><<<grid, 128, 0, st>>>(n, (const double *)logits_dev, seed, (uint32_t)env_id_offset, step, step_dev, deterministic, (double *)actions_dev, (double *)logp_dev);
+    return cudaGetLastError() == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
 }
 
 extern "C" int64_t dsim_launch_count(const DsimHandle *h) { return h ? h->launches : 0; }

@@ -1,0 +1,122 @@
+"""GPU-resident rollout loop: policy -> MyBetaDist -> vector_step, T steps, nothing leaves the device
+(what RLlib's sampler / the reference's rollout.py:55-86 do with Python lists and one MuJoCo call per step).
+
+    runner = RolloutRunner(env, policy, horizon=32)
+    batch = runner.run()            # dict of [T, N, ...] device tensors, GAE-ready
+
+Per step: RMA_full forward (library GEMMs) -> `dsim_beta_policy` (one kernel) -> `dsim_step` (one kernel), with the env's
+in-kernel auto-reset; `prev_actions` is zeroed where an episode just ended, like RLlib's view requirement at an episode
+start.  With `use_graph=True` one step is captured in a CUDA graph and replayed (the sampling kernel reads its step
+counter from device memory, the step kernel's work-stealing counter re-arms itself)."""
+import numpy as np
+
+
+class RolloutRunner:
+    def __init__(self, env, policy, horizon, seed=0, policy_dtype="fp32", use_graph=True, deterministic=False):
+        import torch
+        if not env.auto_reset:
+            raise ValueError("RolloutRunner needs an env created with auto_reset=True (the native loop)")
+        self.torch, self.env, self.policy, self.T = torch, env, policy, int(horizon)
+        self.N, self.D = env.num_drones, env.obs_dim
+        self.seed, self.deterministic = int(seed), bool(deterministic)
+        self.dev = env._device
+        dt = env.obs_tensor.dtype
+        if dt != torch.float32:
+            raise ValueError("RolloutRunner drives the FP32 product path")
+        self.policy_dtype = policy_dtype
+        T, N, D = self.T, self.N, self.D
+        z = dict(device=self.dev)
+        self.obs = torch.zeros((T + 1, N, D), dtype=dt, **z)
+        self.actions = torch.zeros((T, N, 4), dtype=dt, **z)
+        self.rewards = torch.zeros((T, N), dtype=dt, **z)
+        self.truncated = torch.zeros((T, N), dtype=torch.uint8, **z)
+        self.values = torch.zeros((T + 1, N), dtype=dt, **z)
+        self.logp = torch.zeros((T, N), dtype=dt, **z)
+        self.prev_actions = torch.zeros((N, 4), dtype=dt, **z)
+        # static single-step buffers (graph capture needs fixed addresses)
+        self._obs_cur = torch.zeros((N, D), dtype=dt, **z)
+        self._act = torch.zeros((N, 4), dtype=dt, **z)
+        self._logp = torch.zeros((N,), dtype=dt, **z)
+        self._val = torch.zeros((N,), dtype=dt, **z)
+        self._step_ctr = torch.zeros((1,), dtype=torch.int32, **z)
+        self.policy = policy.to(self.dev)
+        self.use_graph, self._graph = bool(use_graph), None
+        self.total_steps = 0
+        if policy_dtype == "tf32":
+            torch.backends.cuda.matmul.allow_tf32 = True
+        self._obs_cur.copy_(env.reset_tensor())
+
+    # one policy + sample + env step on the static buffers
+    def _forward(self):
+        torch = self.torch
+        with torch.no_grad():
+            if self.policy_dtype == "bf16":
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    logits, value = self.policy(self._obs_cur, self.prev_actions)
+                logits, value = logits.float(), value.float()
+            else:
+                logits, value = self.policy(self._obs_cur, self.prev_actions)
+        return logits, value
+
+    def _one_step(self):
+        from .policy import beta_policy
+        logits, value = self._forward()
+        self._val.copy_(value)
+        beta_policy(logits, self.seed, self.env.env_id_offset, 0, self.deterministic, actions_out=self._act, logp_out=self._logp,
+                    step_tensor=self._step_ctr)
+        self._step_ctr.add_(1)
+        obs, rew, trunc = self.env.step_tensor(self._act)
+        self._obs_next, self._rew, self._trunc = obs, rew, trunc
+        # first action of a new episode sees zeros as its previous action
+        self.prev_actions.copy_(self._act * (trunc == 0).to(self._act.dtype).unsqueeze(1))
+
+    def _capture(self):
+        torch = self.torch
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(3):                 # warm-up outside capture: lazy init, cuBLAS workspaces, smem attribute opt-in
+                self._one_step()
+                self._obs_cur.copy_(self._obs_next)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._one_step()
+        self._graph = g
+
+    def step(self, t):
+        """advance one env-step and record it at row t of the rollout buffers"""
+        if self.use_graph and self._graph is None:
+            self._capture()
+        self.obs[t].copy_(self._obs_cur)
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._one_step()
+        self.values[t].copy_(self._val)
+        self.actions[t].copy_(self._act)
+        self.logp[t].copy_(self._logp)
+        self.rewards[t].copy_(self._rew)
+        self.truncated[t].copy_(self._trunc)
+        self._obs_cur.copy_(self._obs_next)
+        self.total_steps += 1
+
+    def run(self):
+        """T steps; returns the [T(+1), N, ...] device tensors (bootstrap value of the last observation included)."""
+        for t in range(self.T):
+            self.step(t)
+        self.obs[self.T].copy_(self._obs_cur)
+        _, v = self._forward()
+        self.values[self.T].copy_(v)
+        return dict(obs=self.obs, actions=self.actions, rewards=self.rewards, truncated=self.truncated, values=self.values,
+                    action_logp=self.logp)
+
+    def to_reference_dataset(self, batch=None):
+        """the dump format of the reference's rollout.py:68-85: {'z': params, 'o': observations, 'a': actions, 't': truncated}
+        as host numpy arrays, env-major like its per-drone lists"""
+        b = batch or dict(obs=self.obs, actions=self.actions, truncated=self.truncated)
+        o = b["obs"][:self.T].permute(1, 0, 2).cpu().numpy().astype(np.float64)
+        return {"z": np.array([list(d.values()) for d in self.env.drone_params]), "o": o,
+                "a": b["actions"].permute(1, 0, 2).cpu().numpy().astype(np.float64),
+                "t": b["truncated"].permute(1, 0).cpu().numpy().astype(bool)}

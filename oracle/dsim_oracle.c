@@ -809,6 +809,47 @@ void orc_sample_params(const OrcResetCfg *c, uint32_t seed, uint32_t env, uint32
 }
 
 /* ------------------------------------------------------------------ batched CPU vec-env step */
+/* ------------------------------------------------------------------ MyBetaDist (distributions.py:6-38) on policy logits
+ * alpha / beta = log(exp(clamp(x, -50, 50)) + 1) + 1 (:12-13), chunked alpha-first (:16); sample = Beta(alpha, beta) as
+ * Ga / (Ga + Gb) with Marsaglia-Tsang gammas on the Philox stream (key = seed, env; counter = block, step, 2, variate);
+ * deterministic = mean (:24-26); logp = sum_k log pdf(clamp(x_k, 0.01, 0.99)) (:19-22). */
+static double gamma_mt(double a, uint32_t seed, uint32_t env, uint32_t step, uint32_t vi) {
+    double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (uint32_t blk = 0; blk < 8; blk++) {
+        uint32_t ctr[4] = {blk, step, 2u, vi}, key[2] = {seed, env}, x[4];
+        orc_philox4x32(ctr, key, x);
+        double z[2];
+        box_muller(x[0], x[1], &z[0], &z[1]);
+        for (int j = 0; j < 2; j++) {
+            double t = 1.0 + c * z[j];
+            if (t > 0) {
+                double v = t * t * t, u = u01(x[2 + j]);
+                if (log(u) < 0.5 * z[j] * z[j] + d - d * v + d * log(v)) return d * v;
+            }
+        }
+    }
+    return d;
+}
+static double softplus1(double x) { x = x < -50 ? -50 : (x > 50 ? 50 : x); return log(exp(x) + 1.0) + 1.0; }
+void orc_beta_policy(const double *logits, int n, int nact, uint32_t seed, uint32_t env0, uint32_t step, int deterministic,
+                     double *actions, double *logp) {
+    for (int i = 0; i < n; i++) {
+        double lp = 0;
+        for (int k = 0; k < nact; k++) {
+            double a = softplus1(logits[(size_t)i * 2 * nact + k]), b = softplus1(logits[(size_t)i * 2 * nact + nact + k]), s;
+            if (deterministic) s = a / (a + b);
+            else {
+                double ga = gamma_mt(a, seed, env0 + (uint32_t)i, step, (uint32_t)(2 * k)), gb = gamma_mt(b, seed, env0 + (uint32_t)i, step, (uint32_t)(2 * k + 1));
+                s = ga / (ga + gb);
+            }
+            actions[(size_t)i * nact + k] = s;
+            double xc = s < 1e-2 ? 1e-2 : (s > 1 - 1e-2 ? 1 - 1e-2 : s);
+            lp += lgamma(a + b) - lgamma(a) - lgamma(b) + (a - 1) * log(xc) + (b - 1) * log1p(-xc);
+        }
+        if (logp) logp[i] = lp;
+    }
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -117,6 +117,8 @@ def lib():
         L.orc_philox4x32.argtypes = [u32p, u32p, u32p]
         L.orc_sample_state.argtypes = [C.POINTER(OrcResetCfg), C.c_uint32, C.c_uint32, C.c_uint32, dp, dp]
         L.orc_sample_params.argtypes = [C.POINTER(OrcResetCfg), C.c_uint32, C.c_uint32, C.c_uint32, dp]
+        L.orc_beta_policy.argtypes = [dp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, dp, dp]
+        L.orc_beta_policy.restype = None
         L.orc_vector_step.argtypes = [C.c_int, C.POINTER(OrcModel), C.c_int, dp, dp, dp, dp,
                                       C.POINTER(C.c_int64), dp, dp, C.c_int, C.c_int, C.c_int,
                                       C.c_double, C.c_int64, dp, C.c_int, dp, C.POINTER(C.c_uint8), C.c_int]
@@ -303,3 +305,13 @@ class CpuVecEnv:
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def beta_policy(logits, seed, env0, step, deterministic=False):
+    """MyBetaDist (distributions.py:6-38) on [n, 2A] logits -> (actions [n, A], logp [n]); same Philox stream as the kernel."""
+    x = np.ascontiguousarray(logits, dtype=np.float64)
+    n, a2 = x.shape
+    act, lp = np.zeros((n, a2 // 2)), np.zeros(n)
+    lib().orc_beta_policy(_dp(x), int(n), int(a2 // 2), int(seed) & 0xFFFFFFFF, int(env0) & 0xFFFFFFFF, int(step), int(bool(deterministic)),
+                          _dp(act), _dp(lp))
+    return act, lp
