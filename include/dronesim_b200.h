@@ -143,6 +143,17 @@ int dsim_beta_policy(const void *logits_dev, int n, int precision, uint32_t seed
                      const uint32_t *step_dev /* NULL, or a device counter ADDED to `step` (CUDA-graph replays) */,
                      int deterministic /* 1: Beta mean (deterministic_sample, :24-26) */, void *actions_dev, void *logp_dev, void *stream);
 
+/* RMA_full inference (models/PPO/RMA/RMA_model.py:48-71,79-116, train_adaptation=False) as one fused tcgen05 kernel:
+ * obs [n][22] (16 states + 6 params, LocalFrameRPYParamsEnv rows) + previous action [n][4] -> Beta-head logits [n][8] and
+ * value [n].  Weights: a bf16 blob in the UMMA K-major canonical layout and an fp32 constants blob, both produced by
+ * mujoco_drone_b200/policy.py::pack_rma_full from the torch module (BatchNorm folded); sizes from dsim_policy_blob_sizes. */
+typedef struct DsimPolicy DsimPolicy;
+int dsim_policy_blob_sizes(int64_t *weight_elems, int64_t *const_elems);
+int dsim_policy_create(int device, const uint16_t *weights_host, const float *consts_host, DsimPolicy **out);
+void dsim_policy_destroy(DsimPolicy *h);
+int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev, int n, float *logits_dev, float *value_dev, void *stream);
+int dsim_policy_error(DsimPolicy *h);            /* 1: a launch hit a tensor-core barrier timeout (device sync) */
+
 /* -- instrumentation */
 int64_t dsim_launch_count(const DsimHandle *h);                                 /* kernels launched by this handle */
 int dsim_debug_timeline(DsimHandle *h, uint64_t *out /*[npages][8] %globaltimer ns*/, int64_t capacity);   /* needs DSIM_TIMELINE=1 at create */

@@ -22,7 +22,7 @@ EXPORTS = [
     "dsim_set_params", "dsim_get_params", "dsim_get_consts", "dsim_reset_all", "dsim_reset_masked", "dsim_reset_at",
     "dsim_forward", "dsim_zero_act", "dsim_step", "dsim_evaluate", "dsim_step_host", "dsim_set_reference", "dsim_control_reference",
     "dsim_set_state", "dsim_get_state", "dsim_compute_states", "dsim_buffer", "dsim_stats", "dsim_sync",
-    "dsim_launch_count", "dsim_kernel_info", "dsim_debug_timeline", "dsim_beta_policy",
+    "dsim_launch_count", "dsim_kernel_info", "dsim_debug_timeline", "dsim_beta_policy", "dsim_policy_blob_sizes", "dsim_policy_create", "dsim_policy_destroy", "dsim_policy_forward", "dsim_policy_error",
 ]
 
 
@@ -93,6 +93,12 @@ def load():
     L.dsim_launch_count.restype = C.c_int64
     L.dsim_debug_timeline.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int64]
     L.dsim_beta_policy.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.c_int64, C.c_uint32, vp, C.c_int, vp, vp, vp]
+    L.dsim_policy_blob_sizes.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.dsim_policy_create.argtypes = [C.c_int, vp, vp, C.POINTER(vp)]
+    L.dsim_policy_destroy.argtypes = [vp]
+    L.dsim_policy_destroy.restype = None
+    L.dsim_policy_forward.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
+    L.dsim_policy_error.argtypes = [vp]
     L.dsim_kernel_info.argtypes = [C.c_int, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     if L.dsim_abi_version() != ABI_VERSION:
         raise ImportError("libdronesim_b200.so ABI version mismatch; rebuild with `python -m mujoco_drone_b200.build`")

@@ -1,0 +1,406 @@
+// dsim_policy_mlp.cu — RMA_full policy inference (models/PPO/RMA/RMA_model.py:48-71, 79-116, train_adaptation=False)
+// as ONE fused tcgen05 kernel for sm_100a: obs + previous action in, Beta-head logits + value out, nothing in between
+// touches HBM.  SURVEY.md §8f-1 (the caller side of the env-step path, BASELINE config 5).
+//
+//   z   = E2 tanh(E1 e + e1) + e2                       6 -> 32 -> 8      (CUDA cores, per row)
+//   h1  = tanh(W1 [s, a_prev, z] + b1)                  28 -> 256         tcgen05, A from shared memory
+//   h2  = tanh(W2 h1 + b2)                              256 -> 128        tcgen05, A from TMEM
+//   (BatchNorm1d in eval mode is an affine map: folded into W3 / V1 on the host)
+//   l1  = tanh(W3' h2 + b3'),  logits = W4 l1 + b4      128 -> 128 -> 8
+//   v1  = tanh(V1' h2 + c1'),  v2 = tanh(V2 v1 + c2),  value = V3 v2 + c3
+//
+// One CTA per SM, persistent, 256 threads = two warpgroups.  All bf16 weights (180 KB, pre-packed on the host into the
+// UMMA K-major no-swizzle canonical layout) stay in shared memory for the life of the CTA.  Each warpgroup owns a tile of
+// 128 envs (thread = env row = TMEM lane) and half of the SM's tensor memory: a 128-column FP32 accumulator D and a
+// 128-column operand region A that holds the bf16 activations of the previous layer (tcgen05.mma with A in TMEM, the
+// FlashAttention-4 pattern), so activations go accumulator -> registers (bias, tanh, bf16 pack) -> TMEM and never to
+// shared memory or HBM.  While one warpgroup runs an epilogue on the CUDA cores the other one's MMAs occupy the tensor
+// core.  Accumulation is FP32; operands are bf16 (the same numerics as the torch autocast path it replaces).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/dronesim_b200.h"
+
+namespace {
+
+constexpr int S_DIM = 16, P_DIM = 6, A_DIM = 4, E_DIM = 8, OBS_DIM = S_DIM + P_DIM, ENC_H = 32;
+constexpr int K1 = 32;                                   // 28 inputs padded to a multiple of 16
+// packed bf16 weight blob (element offsets); each matrix [N][K] is stored as [K/8][N][8] (core matrices of 8 rows x 16 B)
+constexpr int W1_OFF = 0, W1_N = 256;                    // K = 32
+constexpr int W2_OFF = W1_OFF + 256 * 32, W2_N = 128;    // K = 256
+constexpr int W3_OFF = W2_OFF + 128 * 256, W3_N = 256;   // K = 128; rows 0-127 logits hidden (W3'), rows 128-255 value hidden (V1')
+constexpr int W4_OFF = W3_OFF + 256 * 128, W4_N = 16;    // K = 128; rows 0-7 real
+constexpr int V2_OFF = W4_OFF + 16 * 128, V2_N = 128;    // K = 128
+constexpr int W_ELEMS = V2_OFF + 128 * 128;              // 92160 bf16 = 180 KB
+// fp32 constants blob (float offsets)
+constexpr int C_B1 = 0, C_B2 = 256, C_B3 = 384, C_B4 = 640, C_C2 = 656, C_V3 = 784, C_C3 = 912, C_E1 = 913, C_E1B = C_E1 + ENC_H * P_DIM,
+              C_E2 = C_E1B + ENC_H, C_E2B = C_E2 + E_DIM * ENC_H, C_ELEMS = 1408;
+static_assert(C_E2B + E_DIM <= C_ELEMS, "constants blob too small");
+constexpr int X0_BYTES = 128 * K1 * 2;                   // per-warpgroup first-layer operand tile (canonical layout), 8 KB
+constexpr int SMEM_BYTES = W_ELEMS * 2 + C_ELEMS * 4 + 2 * X0_BYTES + 64;
+
+#define DEV __device__ __forceinline__
+DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp): K-major, SWIZZLE_NONE canonical layout ((8,n),2):((1,SBO),LBO) in
+// 16-byte units: 8 rows x 16 B core matrices, SBO = stride between 8-row groups, LBO = stride between the two K halves
+DEV uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           (1ull << 46);                                 // version = 1 (Blackwell), base_offset = 0, layout_type = SWIZZLE_NONE
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+DEV void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+DEV void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+DEV void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DEV void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+DEV void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+DEV void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+DEV void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// bounded wait: a descriptor bug must end in an error flag, never in a hung GPU
+DEV bool mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    for (int it = 0; it < (1 << 22); it++) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+DEV float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+DEV uint32_t pack_bf16(float lo, float hi) { uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+
+// TMEM -> registers: 32 consecutive FP32 columns of this thread's lane
+DEV void tmem_ld32(uint32_t taddr, float v[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                 "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                   "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                   "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+}
+DEV void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                   "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]);
+}
+// registers -> TMEM: 16 consecutive 32-bit columns (32 packed bf16) of this thread's lane
+DEV void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+                   "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+DEV void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct MlpParams {
+    const uint16_t *w;        // packed bf16 weights [W_ELEMS]
+    const float *c;           // fp32 constants [C_ELEMS]
+    const float *obs;         // [n][22]
+    const float *prev_action; // [n][4]
+    float *logits;            // [n][8]
+    float *value;             // [n]
+    int *error;               // set to 1 on a barrier timeout
+    int n, ntiles;
+};
+
+// epilogue: D[0..127] -> tanh(. + bias) -> bf16 -> A region at column `dst_col` (64 columns)
+DEV void epilogue_to_tmem(uint32_t tD, uint32_t tAdst, const float *bias) {
+    #pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+        float v[32];
+        tmem_ld32(tD + c, v);
+        uint32_t pk[16];
+        #pragma unroll
+        for (int j = 0; j < 16; j++) pk[j] = pack_bf16(tanh_fast(v[2 * j] + bias[c + 2 * j]), tanh_fast(v[2 * j + 1] + bias[c + 2 * j + 1]));
+        tmem_st16(tAdst + c / 2, pk);
+    }
+    tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint16_t *s_w = reinterpret_cast<uint16_t *>(smem);
+    float *s_c = reinterpret_cast<float *>(smem + W_ELEMS * 2);
+    unsigned char *s_x0 = smem + W_ELEMS * 2 + C_ELEMS * 4;                  // [2 warpgroups][8 KB]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_x0 + 2 * X0_BYTES);      // [2]
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
+    const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, wq = (tid >> 5) & 3;
+
+    // ---- one-time setup: weights + constants -> shared memory, TMEM allocation, barriers
+    {
+        const uint4 *gw = reinterpret_cast<const uint4 *>(p.w);
+        uint4 *sw = reinterpret_cast<uint4 *>(s_w);
+        for (int i = tid; i < W_ELEMS * 2 / 16; i += 256) sw[i] = __ldg(gw + i);
+        for (int i = tid; i < C_ELEMS; i += 256) s_c[i] = __ldg(p.c + i);
+    }
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid < 32) {                                                          // warp 0 allocates all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic smem writes -> visible to the tensor core's async proxy
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t lane_off = (uint32_t)(32 * wq) << 16;
+    const uint32_t tD = tmem_base + wg * 256 + lane_off;                     // accumulator, 128 columns
+    const uint32_t tA = tD + 128;                                            // operand region, 128 columns = 256 bf16 per lane
+    const uint32_t tD0 = tmem_base + wg * 256, tA0 = tD0 + 128;              // lane-0 addresses for the MMA operands
+    const uint32_t w_addr = smem_u32(s_w), x0_addr = smem_u32(s_x0 + wg * X0_BYTES);
+    uint64_t *bar = &s_bar[wg];
+    uint32_t parity = 0;
+    bool ok = true;
+
+    for (int tile = 2 * blockIdx.x + wg; tile < p.ntiles; tile += 2 * gridDim.x) {
+        const int row = tile * 128 + wt;
+        const bool live = row < p.n;
+        // ---- layer-0 operand: [s(16), a_prev(4), z(8), 0(4)] as bf16 into the canonical smem tile
+        {
+            float o[OBS_DIM], a[A_DIM];
+            #pragma unroll
+            for (int k = 0; k < OBS_DIM; k += 2) {
+                const float2 v = live ? __ldg(reinterpret_cast<const float2 *>(p.obs + (size_t)row * OBS_DIM + k)) : make_float2(0.f, 0.f);
+                o[k] = v.x; o[k + 1] = v.y;
+            }
+            {
+                const float4 v = live ? __ldg(reinterpret_cast<const float4 *>(p.prev_action) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+            }
+            float hdn[ENC_H];                                                // parameter encoder on the CUDA cores (448 MACs)
+            #pragma unroll
+            for (int j = 0; j < ENC_H; j++) {
+                float acc = s_c[C_E1B + j];
+                #pragma unroll
+                for (int k = 0; k < P_DIM; k++) acc = fmaf(s_c[C_E1 + j * P_DIM + k], o[S_DIM + k], acc);
+                hdn[j] = tanh_fast(acc);
+            }
+            float x[K1];
+            #pragma unroll
+            for (int k = 0; k < S_DIM; k++) x[k] = o[k];
+            #pragma unroll
+            for (int k = 0; k < A_DIM; k++) x[S_DIM + k] = a[k];
+            #pragma unroll
+            for (int e = 0; e < E_DIM; e++) {
+                float acc = s_c[C_E2B + e];
+                #pragma unroll
+                for (int j = 0; j < ENC_H; j++) acc = fmaf(s_c[C_E2 + e * ENC_H + j], hdn[j], acc);
+                x[S_DIM + A_DIM + e] = acc;
+            }
+            #pragma unroll
+            for (int k = S_DIM + A_DIM + E_DIM; k < K1; k++) x[k] = 0.f;
+            #pragma unroll
+            for (int kc = 0; kc < K1 / 8; kc++) {                            // element (row, k) at (k/8) * 2048 + row * 16 + (k%8) * 2
+                uint4 q;
+                q.x = pack_bf16(x[8 * kc + 0], x[8 * kc + 1]); q.y = pack_bf16(x[8 * kc + 2], x[8 * kc + 3]);
+                q.z = pack_bf16(x[8 * kc + 4], x[8 * kc + 5]); q.w = pack_bf16(x[8 * kc + 6], x[8 * kc + 7]);
+                *reinterpret_cast<uint4 *>(s_x0 + wg * X0_BYTES + kc * 2048 + wt * 16) = q;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fence_before_sync();
+        wg_sync(wg);
+
+        // ---- h1 = tanh(W1 x0 + b1): two N = 128 halves, A from shared memory
+        #pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            if (wt == 0) {
+                fence_after_sync();
+                #pragma unroll
+                for (int s = 0; s < K1 / 16; s++)
+                    mma_ss(tD0, umma_desc(x0_addr + s * 2 * 2048, 2048, 128),
+                           umma_desc(w_addr + (W1_OFF + (s * 2) * W1_N * 8 + half * 128 * 8) * 2, W1_N * 16, 128), umma_idesc(128), s > 0);
+                mma_commit(bar);
+            }
+            ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
+            fence_after_sync();
+            epilogue_to_tmem(tD, tA + half * 64, s_c + C_B1 + half * 128);
+            fence_before_sync();
+            wg_sync(wg);
+        }
+        // ---- h2 = tanh(W2 h1 + b2): K = 256, A from TMEM (operand region columns 0..127)
+        if (wt == 0) {
+            fence_after_sync();
+            #pragma unroll
+            for (int s = 0; s < 256 / 16; s++)
+                mma_ts(tD0, tA0 + s * 8, umma_desc(w_addr + (W2_OFF + (s * 2) * W2_N * 8) * 2, W2_N * 16, 128), umma_idesc(128), s > 0);
+            mma_commit(bar);
+        }
+        ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
+        fence_after_sync();
+        epilogue_to_tmem(tD, tA, s_c + C_B2);                                // h2 -> columns 0..63
+        fence_before_sync();
+        wg_sync(wg);
+        // ---- l1 = tanh(W3' h2 + b3') -> columns 64..127
+        if (wt == 0) {
+            fence_after_sync();
+            #pragma unroll
+            for (int s = 0; s < 128 / 16; s++)
+                mma_ts(tD0, tA0 + s * 8, umma_desc(w_addr + (W3_OFF + (s * 2) * W3_N * 8) * 2, W3_N * 16, 128), umma_idesc(128), s > 0);
+            mma_commit(bar);
+        }
+        ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
+        fence_after_sync();
+        epilogue_to_tmem(tD, tA + 64, s_c + C_B3);
+        fence_before_sync();
+        wg_sync(wg);
+        // ---- logits = W4 l1 + b4 (N = 16, 8 real)
+        if (wt == 0) {
+            fence_after_sync();
+            #pragma unroll
+            for (int s = 0; s < 128 / 16; s++)
+                mma_ts(tD0, tA0 + 64 + s * 8, umma_desc(w_addr + (W4_OFF + (s * 2) * W4_N * 8) * 2, W4_N * 16, 128), umma_idesc(16), s > 0);
+            mma_commit(bar);
+        }
+        ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
+        fence_after_sync();
+        {
+            float v[16];
+            tmem_ld16(tD, v);
+            if (live) {
+                float4 *out = reinterpret_cast<float4 *>(p.logits + (size_t)row * 8);
+                out[0] = make_float4(v[0] + s_c[C_B4 + 0], v[1] + s_c[C_B4 + 1], v[2] + s_c[C_B4 + 2], v[3] + s_c[C_B4 + 3]);
+                out[1] = make_float4(v[4] + s_c[C_B4 + 4], v[5] + s_c[C_B4 + 5], v[6] + s_c[C_B4 + 6], v[7] + s_c[C_B4 + 7]);
+            }
+        }
+        fence_before_sync();
+        wg_sync(wg);
+        // ---- v1 = tanh(V1' h2 + c1') -> columns 64..127 (l1 is dead)
+        if (wt == 0) {
+            fence_after_sync();
+            #pragma unroll
+            for (int s = 0; s < 128 / 16; s++)
+                mma_ts(tD0, tA0 + s * 8, umma_desc(w_addr + (W3_OFF + (s * 2) * W3_N * 8 + 128 * 8) * 2, W3_N * 16, 128), umma_idesc(128), s > 0);
+            mma_commit(bar);
+        }
+        ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
+        fence_after_sync();
+        epilogue_to_tmem(tD, tA + 64, s_c + C_B3 + 128);
+        fence_before_sync();
+        wg_sync(wg);
+        // ---- v2 = tanh(V2 v1 + c2); value = V3 v2 + c3
+        if (wt == 0) {
+            fence_after_sync();
+            #pragma unroll
+            for (int s = 0; s < 128 / 16; s++)
+                mma_ts(tD0, tA0 + 64 + s * 8, umma_desc(w_addr + (V2_OFF + (s * 2) * V2_N * 8) * 2, V2_N * 16, 128), umma_idesc(128), s > 0);
+            mma_commit(bar);
+        }
+        ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
+        fence_after_sync();
+        {
+            float val = s_c[C_C3];
+            #pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+                float v[32];
+                tmem_ld32(tD + c, v);
+                #pragma unroll
+                for (int j = 0; j < 32; j++) val = fmaf(s_c[C_V3 + c + j], tanh_fast(v[j] + s_c[C_C2 + c + j]), val);
+            }
+            if (live) p.value[row] = val;
+        }
+        fence_before_sync();
+        wg_sync(wg);                                                         // D and the operand region are free for the next tile
+    }
+    if (!ok) atomicExch(p.error, 1);
+    fence_before_sync();
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+}  // namespace
+
+struct DsimPolicy {
+    int device, sms;
+    uint16_t *w;
+    float *c;
+    int *error;
+    char err[256];
+};
+
+extern "C" int dsim_policy_blob_sizes(int64_t *weight_elems, int64_t *const_elems) {
+    if (weight_elems) *weight_elems = W_ELEMS;
+    if (const_elems) *const_elems = C_ELEMS;
+    return DSIM_OK;
+}
+
+extern "C" int dsim_policy_create(int device, const uint16_t *weights_host, const float *consts_host, DsimPolicy **out) {
+    if (!out || !weights_host || !consts_host) return DSIM_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DSIM_ECUDA;   // no CPU fallback
+    DsimPolicy *h = new (std::nothrow) DsimPolicy();
+    if (!h) return DSIM_ENOMEM;
+    memset(h, 0, sizeof *h);
+    h->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->w, (size_t)W_ELEMS * 2);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->c, (size_t)C_ELEMS * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->error, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->error, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(h->w, weights_host, (size_t)W_ELEMS * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->c, consts_host, (size_t)C_ELEMS * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rma_full_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+        if (h->w) cudaFree(h->w);
+        if (h->c) cudaFree(h->c);
+        if (h->error) cudaFree(h->error);
+        delete h;
+        return DSIM_ECUDA;
+    }
+    *out = h;
+    return DSIM_OK;
+}
+
+extern "C" void dsim_policy_destroy(DsimPolicy *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->w); cudaFree(h->c); cudaFree(h->error);
+    delete h;
+}
+
+extern "C" int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev, int n, float *logits_dev, float *value_dev, void *stream) {
+    if (!h || !obs_dev || !prev_action_dev || !logits_dev || !value_dev || n <= 0) return DSIM_EINVAL;
+    if (((uintptr_t)obs_dev & 7) || ((uintptr_t)prev_action_dev & 15) || ((uintptr_t)logits_dev & 15)) return DSIM_EINVAL;
+    if (cudaSetDevice(h->device) != cudaSuccess) return DSIM_ECUDA;
+    MlpParams p;
+    p.w = h->w; p.c = h->c; p.obs = obs_dev; p.prev_action = prev_action_dev; p.logits = logits_dev; p.value = value_dev; p.error = h->error;
+    p.n = n; p.ntiles = (n + 127) / 128;
+    const int pairs = (p.ntiles + 1) / 2;
+    const int grid = pairs < h->sms ? pairs : h->sms;
+    rma_full_forward_kernel<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
+}
+
+// 1 if any launch since creation hit a tensor-core barrier timeout (results of that launch are invalid); syncs the device
+extern "C" int dsim_policy_error(DsimPolicy *h) {
+    if (!h) return DSIM_EINVAL;
+    int v = 0;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return DSIM_ECUDA;
+    if (cudaMemcpy(&v, h->error, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return DSIM_ECUDA;
+    return v;
+}

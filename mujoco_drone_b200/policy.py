@@ -85,3 +85,102 @@ def make_rma_full(num_states=16, num_params=6, num_actions=4, param_embed_dim=8,
             f = self.hidden(torch.cat((s, prev_action, z), dim=-1)) if self.num_actions else self.hidden(torch.cat((s, z), dim=-1))
             return self.logits(f), self.value_branch(f).squeeze(1)                                                    # :106, :111-116
     return RMAFull()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Fused tcgen05 inference of RMA_full (csrc/dsim_policy_mlp.cu, C ABI dsim_policy_*)
+
+def _pack_umma_kmajor(w, n_pad, k_pad):
+    """torch Linear weight [N, K] -> bf16 bits in the UMMA K-major no-swizzle canonical layout [K/8][N][8]
+    (core matrices of 8 rows x 16 bytes; element (n, k) at ((k // 8) * N + n) * 8 + k % 8)."""
+    import torch
+    n, k = w.shape
+    wp = torch.zeros((n_pad, k_pad), dtype=torch.float32)
+    wp[:n, :k] = w.detach().float().cpu()
+    wp = wp.reshape(n_pad, k_pad // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+    return wp.view(torch.int16).flatten()
+
+
+def pack_rma_full(model):
+    """(weights int16[W_ELEMS], consts float32[C_ELEMS]) for dsim_policy_create from an RMAFull module (eval mode).
+    BatchNorm1d (running statistics) is an affine map h -> scale * h + shift: folded into the two layers that consume it."""
+    import torch
+    if model.num_states != 16 or model.num_params != 6 or model.num_actions != 4:
+        raise ValueError("the fused kernel is specialised for RMA_full with 16 states, 6 params, 4 actions (train_RMA.py:47-53)")
+    enc1, enc2 = model.param_encoder[0], model.param_encoder[2]
+    h1, h2, bn = model.hidden[0], model.hidden[2], model.hidden[4]
+    l1, l2 = model.logits[0], model.logits[2]
+    v1, v2, v3 = model.value_branch[0], model.value_branch[2], model.value_branch[4]
+    if enc2.out_features != 8 or h1.out_features != 256 or h2.out_features != 128 or l2.out_features != 8:
+        raise ValueError("unexpected RMA_full layer sizes")
+    with torch.no_grad():
+        scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().cpu()
+        shift = (bn.bias - bn.running_mean * bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().cpu()
+        w3 = l1.weight.float().cpu() * scale[None, :]
+        b3 = l1.bias.float().cpu() + l1.weight.float().cpu() @ shift
+        wv = v1.weight.float().cpu() * scale[None, :]
+        bv = v1.bias.float().cpu() + v1.weight.float().cpu() @ shift
+        blob = torch.cat([
+            _pack_umma_kmajor(h1.weight, 256, 32),
+            _pack_umma_kmajor(h2.weight, 128, 256),
+            _pack_umma_kmajor(torch.cat([w3, wv], 0), 256, 128),
+            _pack_umma_kmajor(l2.weight, 16, 128),
+            _pack_umma_kmajor(v2.weight, 128, 128),
+        ])
+        c = torch.zeros(1408, dtype=torch.float32)
+        f = lambda t: t.detach().float().cpu().flatten()
+        c[0:256] = f(h1.bias); c[256:384] = f(h2.bias); c[384:512] = b3; c[512:640] = bv
+        c[640:648] = f(l2.bias); c[656:784] = f(v2.bias); c[784:912] = f(v3.weight); c[912] = f(v3.bias)[0]
+        c[913:913 + 192] = f(enc1.weight); c[1105:1137] = f(enc1.bias); c[1137:1137 + 256] = f(enc2.weight); c[1393:1401] = f(enc2.bias)
+    return blob.contiguous(), c.contiguous()
+
+
+class FusedRMAFull:
+    """RMA_full forward as ONE tcgen05 kernel: `logits, value = fused(obs, prev_action)` on CUDA float32 tensors
+    ([n, 22], [n, 4]) -> ([n, 8], [n]).  bf16 operands, FP32 accumulation.  No CPU fallback."""
+
+    def __init__(self, model, device=0):
+        import torch
+        self._torch = torch
+        L = self._L = _lib.load()
+        we, ce = C.c_int64(), C.c_int64()
+        L.dsim_policy_blob_sizes(C.byref(we), C.byref(ce))
+        blob, consts = pack_rma_full(model)
+        assert blob.numel() == we.value and consts.numel() == ce.value, (blob.numel(), we.value, consts.numel(), ce.value)
+        self.device = torch.device("cuda", int(device))
+        h = C.c_void_p()
+        rc = L.dsim_policy_create(int(device), C.c_void_p(blob.data_ptr()), C.c_void_p(consts.data_ptr()), C.byref(h))
+        if rc != _lib.OK:
+            raise _lib.DsimError(rc, "dsim_policy_create failed (needs a CUDA device: there is no CPU fallback)")
+        self._h = h
+
+    def __call__(self, obs, prev_action, logits_out=None, value_out=None):
+        torch = self._torch
+        n = obs.shape[0]
+        if obs.shape != (n, 22) or prev_action.shape != (n, 4) or obs.dtype != torch.float32 or prev_action.dtype != torch.float32:
+            raise ValueError("FusedRMAFull expects float32 obs [n, 22] and prev_action [n, 4]")
+        obs, prev_action = obs.contiguous(), prev_action.contiguous()
+        logits = logits_out if logits_out is not None else torch.empty((n, 8), dtype=torch.float32, device=obs.device)
+        value = value_out if value_out is not None else torch.empty((n,), dtype=torch.float32, device=obs.device)
+        stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        rc = self._L.dsim_policy_forward(self._h, C.c_void_p(obs.data_ptr()), C.c_void_p(prev_action.data_ptr()), n,
+                                         C.c_void_p(logits.data_ptr()), C.c_void_p(value.data_ptr()), stream)
+        if rc != _lib.OK:
+            raise _lib.DsimError(rc, "dsim_policy_forward failed")
+        return logits, value
+
+    def check(self):
+        """raise if any launch hit a tensor-core barrier timeout (device sync)"""
+        if self._L.dsim_policy_error(self._h) != 0:
+            raise RuntimeError("fused RMA_full kernel reported a barrier timeout: results invalid")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.dsim_policy_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -140,3 +140,48 @@ def test_rollout_runner_graph_equals_eager_and_replays_through_the_env():
         env.close()
     # (i) graph vs eager: same policy, same seeds; the graph run is offset by its 3 warm-up steps, so compare distributions
     assert abs(out[True]["actions"].mean().item() - out[False]["actions"].mean().item()) < 0.05
+
+
+def test_umma_weight_packing_layout():
+    """host packer: element (n, k) of a [N, K] matrix lands at ((k // 8) * N + n) * 8 + k % 8 (UMMA K-major canonical layout)"""
+    import torch
+    import mujoco_drone_b200 as M
+    w = torch.arange(16 * 32, dtype=torch.float32).reshape(16, 32) / 8.0        # exactly representable in bf16? use small ints
+    w = torch.arange(16 * 32, dtype=torch.float32).reshape(16, 32) % 251
+    p = M.policy._pack_umma_kmajor(w, 16, 32).view(torch.bfloat16).float()
+    for n, k in [(0, 0), (3, 7), (5, 8), (15, 31), (9, 20)]:
+        assert p[((k // 8) * 16 + n) * 8 + k % 8].item() == w[n, k].item()
+    blob, c = M.policy.pack_rma_full(M.policy.make_rma_full())
+    assert blob.numel() == 92160 and c.numel() == 1408
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_fused_tcgen05_policy_matches_torch_fp32():
+    """the fused tcgen05 RMA_full kernel vs the plain PyTorch FP32 module (same weights, BatchNorm with non-trivial running
+    statistics).  Tolerance: bf16 operands with FP32 accumulation through 5 layers -> 3e-2 absolute on O(1) logits."""
+    import torch
+    import mujoco_drone_b200 as M
+    torch.manual_seed(0)
+    model = M.policy.make_rma_full().cuda()
+    bn = model.hidden[4]
+    with torch.no_grad():
+        bn.running_mean.copy_(torch.randn(128, device="cuda") * 0.2)
+        bn.running_var.copy_(torch.rand(128, device="cuda") + 0.5)
+        bn.weight.copy_(torch.rand(128, device="cuda") + 0.5)
+        bn.bias.copy_(torch.randn(128, device="cuda") * 0.1)
+        for lin in (model.logits[2], model.value_branch[4]):
+            lin.bias.copy_(torch.randn_like(lin.bias) * 0.3)
+    fused = M.policy.FusedRMAFull(model, device=0)
+    for n in (1, 127, 128, 300, 4096 + 37, 150000):
+        obs = torch.randn((n, 22), device="cuda")
+        obs[:, 16:] = torch.tensor([1.0, 0.17, 7.0, 0.01, 1.2, 0.3], device="cuda") * (1 + 0.1 * torch.randn((n, 6), device="cuda"))
+        prev = torch.rand((n, 4), device="cuda")
+        with torch.no_grad():
+            ref_l, ref_v = model(obs, prev)
+        lg, val = fused(obs, prev)
+        fused.check()
+        assert torch.isfinite(lg).all() and torch.isfinite(val).all()
+        assert (lg - ref_l).abs().max().item() < 3e-2, (n, (lg - ref_l).abs().max().item())
+        assert (val - ref_v).abs().max().item() < 3e-2, (n, (val - ref_v).abs().max().item())
+    fused.close()
