@@ -292,8 +292,8 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
     line = {
         "metric": "env-steps/sec", "value": world * n * args.steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 env step; policy GEMMs " + args.policy_dtype, "data": "synthetic",
-        "config": {"workload": wl["name"], "envs_per_gpu": n, "total_envs": n * world, "policy": "RMA_full random init (6->32->8 | 28->256->128+BN | 128->128->8 | 128->128->128->1)",
+        "dtype": "f32 env step; policy " + ("bf16 operands / f32 accumulate, fused tcgen05 kernel" if args.policy_dtype == "fused" else args.policy_dtype + " torch GEMMs"), "data": "synthetic",
+        "config": {"workload": wl["name"], "envs_per_gpu": n, "total_envs": n * world, "policy": "RMA_full random init (6->32->8 | 28->256->128+BN | 128->128->8 | 128->128->128->1), " + args.policy_dtype,
                    "sampling": "MyBetaDist, Philox Marsaglia-Tsang", "graph": "one CUDA graph replay per step",
                    "l2": "inputs larger than L2 (env state + activations of 524288 envs)", "parallelism": f"env-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * (4 * env.obs_dim + 5),
@@ -320,7 +320,8 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads / hot-L2 measurements")
-    ap.add_argument("--policy-dtype", default="bf16", choices=["fp32", "tf32", "bf16"], help="c5: dtype of the policy GEMMs")
+    ap.add_argument("--policy-dtype", default="fused", choices=["fp32", "tf32", "bf16", "fused"],
+                    help="c5 policy: fused = hand-written tcgen05 kernel (bf16 operands, FP32 accumulate); others = torch / cuBLAS")
     ap.add_argument("--preroll", type=int, default=1500, help="untimed steps per replica before the warm-up (reach the steady-state reset rate)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

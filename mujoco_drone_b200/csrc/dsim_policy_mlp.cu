@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -123,9 +124,17 @@ struct MlpParams {
     float *logits;            // [n][8]
     float *value;             // [n]
     int *error;               // set to 1 on a barrier timeout
+    long long *dbg;           // debug: clock64 stamps [2 warpgroups][32] of CTA 0's first tile, or nullptr
     int n, ntiles;
 };
 
+// packed activation: two accumulator values + bias -> bf16x2 -> tanh.approx.bf16x2.  One MUFU op yields two activations
+// already in the operand format (the special-function unit, 16 ops/clk/SM, is the epilogue's scarce pipe: ~900 tanh per row).
+DEV uint32_t tanh_pack(float lo, float hi) {
+    uint32_t r = pack_bf16(lo, hi);
+    asm("tanh.approx.bf16x2 %0, %0;" : "+r"(r));
+    return r;
+}
 // epilogue: D[0..127] -> tanh(. + bias) -> bf16 -> A region at column `dst_col` (64 columns)
 DEV void epilogue_to_tmem(uint32_t tD, uint32_t tAdst, const float *bias) {
     #pragma unroll 1
@@ -134,7 +143,7 @@ DEV void epilogue_to_tmem(uint32_t tD, uint32_t tAdst, const float *bias) {
         tmem_ld32(tD + c, v);
         uint32_t pk[16];
         #pragma unroll
-        for (int j = 0; j < 16; j++) pk[j] = pack_bf16(tanh_fast(v[2 * j] + bias[c + 2 * j]), tanh_fast(v[2 * j + 1] + bias[c + 2 * j + 1]));
+        for (int j = 0; j < 16; j++) pk[j] = tanh_pack(v[2 * j] + bias[c + 2 * j], v[2 * j + 1] + bias[c + 2 * j + 1]);
         tmem_st16(tAdst + c / 2, pk);
     }
     tmem_st_wait();
@@ -175,7 +184,10 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
     uint32_t parity = 0;
     bool ok = true;
 
+    int dbg_k = 0;
+    auto stamp = [&]() { if (p.dbg && blockIdx.x == 0 && wt == 0 && dbg_k < 32) p.dbg[wg * 32 + dbg_k++] = clock64(); };
     for (int tile = 2 * blockIdx.x + wg; tile < p.ntiles; tile += 2 * gridDim.x) {
+        stamp();
         const int row = tile * 128 + wt;
         const bool live = row < p.n;
         // ---- layer-0 operand: [s(16), a_prev(4), z(8), 0(4)] as bf16 into the canonical smem tile
@@ -235,11 +247,14 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
                            umma_desc(w_addr + (W1_OFF + (s * 2) * W1_N * 8 + half * 128 * 8) * 2, W1_N * 16, 128), umma_idesc(128), s > 0);
                 mma_commit(bar);
             }
+            stamp();
             ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
+            stamp();
             fence_after_sync();
             epilogue_to_tmem(tD, tA + half * 64, s_c + C_B1 + half * 128);
             fence_before_sync();
             wg_sync(wg);
+            stamp();
         }
         // ---- h2 = tanh(W2 h1 + b2): K = 256, A from TMEM (operand region columns 0..127)
         if (wt == 0) {
@@ -249,11 +264,14 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
                 mma_ts(tD0, tA0 + s * 8, umma_desc(w_addr + (W2_OFF + (s * 2) * W2_N * 8) * 2, W2_N * 16, 128), umma_idesc(128), s > 0);
             mma_commit(bar);
         }
+        stamp();
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
+        stamp();
         fence_after_sync();
         epilogue_to_tmem(tD, tA, s_c + C_B2);                                // h2 -> columns 0..63
         fence_before_sync();
         wg_sync(wg);
+        stamp();
         // ---- l1 = tanh(W3' h2 + b3') -> columns 64..127
         if (wt == 0) {
             fence_after_sync();
@@ -318,7 +336,11 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
                 float v[32];
                 tmem_ld32(tD + c, v);
                 #pragma unroll
-                for (int j = 0; j < 32; j++) val = fmaf(s_c[C_V3 + c + j], tanh_fast(v[j] + s_c[C_C2 + c + j]), val);
+                for (int j = 0; j < 32; j += 2) {
+                    const uint32_t t2 = tanh_pack(v[j] + s_c[C_C2 + c + j], v[j + 1] + s_c[C_C2 + c + j + 1]);
+                    val = fmaf(s_c[C_V3 + c + j], __uint_as_float(t2 << 16), val);
+                    val = fmaf(s_c[C_V3 + c + j + 1], __uint_as_float(t2 & 0xFFFF0000u), val);
+                }
             }
             if (live) p.value[row] = val;
         }
@@ -338,6 +360,7 @@ struct DsimPolicy {
     uint16_t *w;
     float *c;
     int *error;
+    long long *dbg;
     char err[256];
 };
 
@@ -362,6 +385,7 @@ extern "C" int dsim_policy_create(int device, const uint16_t *weights_host, cons
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->c, (size_t)C_ELEMS * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->error, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(h->error, 0, sizeof(int));
+    if (e == cudaSuccess && getenv("DSIM_MLP_DEBUG")) { e = cudaMalloc((void **)&h->dbg, 64 * sizeof(long long)); if (e == cudaSuccess) e = cudaMemset(h->dbg, 0, 64 * sizeof(long long)); }
     if (e == cudaSuccess) e = cudaMemcpy(h->w, weights_host, (size_t)W_ELEMS * 2, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->c, consts_host, (size_t)C_ELEMS * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rma_full_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -389,11 +413,17 @@ extern "C" int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const fl
     if (cudaSetDevice(h->device) != cudaSuccess) return DSIM_ECUDA;
     MlpParams p;
     p.w = h->w; p.c = h->c; p.obs = obs_dev; p.prev_action = prev_action_dev; p.logits = logits_dev; p.value = value_dev; p.error = h->error;
-    p.n = n; p.ntiles = (n + 127) / 128;
+    p.n = n; p.ntiles = (n + 127) / 128; p.dbg = h->dbg;
     const int pairs = (p.ntiles + 1) / 2;
     const int grid = pairs < h->sms ? pairs : h->sms;
     rma_full_forward_kernel<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
+}
+
+extern "C" int dsim_policy_debug(DsimPolicy *h, long long *out64) {
+    if (!h || !h->dbg || !out64) return DSIM_EINVAL;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out64, h->dbg, 64 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
 }
 
 // 1 if any launch since creation hit a tensor-core barrier timeout (results of that launch are invalid); syncs the device

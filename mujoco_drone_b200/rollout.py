@@ -40,6 +40,11 @@ class RolloutRunner:
         self._val = torch.zeros((N,), dtype=dt, **z)
         self._step_ctr = torch.zeros((1,), dtype=torch.int32, **z)
         self.policy = policy.to(self.dev)
+        self._fused = None
+        if policy_dtype == "fused":                    # hand-written tcgen05 kernel (csrc/dsim_policy_mlp.cu) instead of library GEMMs
+            from .policy import FusedRMAFull
+            self._fused = FusedRMAFull(self.policy, device=env.device_index)
+            self._logits = torch.zeros((N, 8), dtype=dt, **z)
         self.use_graph, self._graph = bool(use_graph), None
         self.total_steps = 0
         if policy_dtype == "tf32":
@@ -49,6 +54,8 @@ class RolloutRunner:
     # one policy + sample + env step on the static buffers
     def _forward(self):
         torch = self.torch
+        if self._fused is not None:
+            return self._fused(self._obs_cur, self.prev_actions, logits_out=self._logits, value_out=self._val)
         with torch.no_grad():
             if self.policy_dtype == "bf16":
                 with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -61,7 +68,8 @@ class RolloutRunner:
     def _one_step(self):
         from .policy import beta_policy
         logits, value = self._forward()
-        self._val.copy_(value)
+        if value.data_ptr() != self._val.data_ptr():
+            self._val.copy_(value)
         beta_policy(logits, self.seed, self.env.env_id_offset, 0, self.deterministic, actions_out=self._act, logp_out=self._logp,
                     step_tensor=self._step_ctr)
         self._step_ctr.add_(1)

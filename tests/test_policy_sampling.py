@@ -185,3 +185,27 @@ def test_fused_tcgen05_policy_matches_torch_fp32():
         assert (lg - ref_l).abs().max().item() < 3e-2, (n, (lg - ref_l).abs().max().item())
         assert (val - ref_v).abs().max().item() < 3e-2, (n, (val - ref_v).abs().max().item())
     fused.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_rollout_runner_with_fused_policy_kernel():
+    """config-5 loop with the hand-written tcgen05 policy kernel, CUDA-graph replayed: finite, in-range, and its logits
+    agree with the torch FP32 module evaluated on the recorded observations / previous actions"""
+    import torch
+    import mujoco_drone_b200 as M
+    n, T = 1000, 6
+    cfg = dict(M.base_config, num_drones=n, auto_reset=True, max_steps=64, param_difficulty=1.0, reward_fcn=M.rewards.distance_energy_reward)
+    env = M.observation_wrappers.LocalFrameRPYParamsEnv(cfg)
+    pol = M.policy.make_rma_full()
+    r = M.rollout.RolloutRunner(env, pol, horizon=T, seed=1, policy_dtype="fused", use_graph=True)
+    b = r.run()
+    r._fused.check()
+    assert ((b["actions"] > 0) & (b["actions"] < 1)).all() and torch.isfinite(b["values"]).all() and torch.isfinite(b["action_logp"]).all()
+    with torch.no_grad():
+        prev = torch.zeros((n, 4), device="cuda")
+        for t in range(T):
+            _, v = pol(b["obs"][t], prev)
+            assert (v - b["values"][t]).abs().max().item() < 3e-2
+            prev = b["actions"][t] * (b["truncated"][t] == 0).float().unsqueeze(1)
+    env.close()
