@@ -122,6 +122,11 @@ int dsim_step_host(DsimHandle *h, const float *actions_host /*[N][4]*/, float *o
 
 /* -- reference / setpoints: self.reference (:80), control_reference (:151-172) */
 int dsim_set_reference(DsimHandle *h, const double ref[4]);
+/* setpoint streams of evaluation.py:135-152 evaluated on the device: env i gets the trajectory point at t + i * phase_step.
+ * circle: params = {f, r, h}; step: params = {step_time}; ramp: params = {start_time, duration}; needs per_env_reference */
+enum { DSIM_TRAJ_CIRCLE = 0, DSIM_TRAJ_STEP = 1, DSIM_TRAJ_RAMP = 2 };
+int dsim_trajectory_reference(DsimHandle *h, int kind, double t, double phase_step, const double params[3],
+                              const double start_pos[4] /* step, ramp */, const double end_pos[4], void *stream);
 int dsim_control_reference(DsimHandle *h, const void *axes_dev /* real [4][ld] DENSE rows: joystick axes x,y,z,yaw after sign flips */, void *stream);
 
 /* -- state access for callers that poke MjData (BaseDroneEnv.py:342-346) and for parity tests.

@@ -8,6 +8,6 @@ constructing an env does (there is no CPU fallback).
 from . import _lib, rewards                                     # noqa: F401
 from .env import BaseDroneEnv, base_config, default_termination_fcn   # noqa: F401
 from . import observation_wrappers                                # noqa: F401
-from . import policy, rollout                                     # noqa: F401
+from . import policy, rollout, trajectories                       # noqa: F401
 
 __all__ = ["BaseDroneEnv", "base_config", "default_termination_fcn", "observation_wrappers", "rewards"]

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("DSIM_LIB") or os.path.join(_HERE, "libdronesim_b200.s
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ESHAPE = 0, -1, -2, -3, -4, -5
 FP32, FP64 = 0, 1
 ABI_VERSION = 2
+TRAJ_CIRCLE, TRAJ_STEP, TRAJ_RAMP = 0, 1, 2
 TILE = 32                     # envs per page (include/dronesim_b200.h: PAGED buffers)
 (BUF_STATE, BUF_NUM_STEPS, BUF_OBS, BUF_REWARD, BUF_TRUNCATED, BUF_PARAMS, BUF_CONSTS, BUF_REFERENCE,
  BUF_RESET_COUNT, BUF_STATES33, BUF_EP_RETURN, BUF_STATS) = range(12)
@@ -22,7 +23,7 @@ EXPORTS = [
     "dsim_set_params", "dsim_get_params", "dsim_get_consts", "dsim_reset_all", "dsim_reset_masked", "dsim_reset_at",
     "dsim_forward", "dsim_zero_act", "dsim_step", "dsim_evaluate", "dsim_step_host", "dsim_set_reference", "dsim_control_reference",
     "dsim_set_state", "dsim_get_state", "dsim_compute_states", "dsim_buffer", "dsim_stats", "dsim_sync",
-    "dsim_launch_count", "dsim_kernel_info", "dsim_debug_timeline", "dsim_beta_policy", "dsim_policy_blob_sizes", "dsim_policy_create", "dsim_policy_destroy", "dsim_policy_forward", "dsim_policy_error",
+    "dsim_launch_count", "dsim_kernel_info", "dsim_debug_timeline", "dsim_beta_policy", "dsim_trajectory_reference", "dsim_policy_blob_sizes", "dsim_policy_create", "dsim_policy_destroy", "dsim_policy_forward", "dsim_policy_error",
 ]
 
 
@@ -99,6 +100,7 @@ def load():
     L.dsim_policy_destroy.restype = None
     L.dsim_policy_forward.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
     L.dsim_policy_error.argtypes = [vp]
+    L.dsim_trajectory_reference.argtypes = [vp, C.c_int, C.c_double, C.c_double, dp, dp, dp, vp]
     L.dsim_kernel_info.argtypes = [C.c_int, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     if L.dsim_abi_version() != ABI_VERSION:
         raise ImportError("libdronesim_b200.so ABI version mismatch; rebuild with `python -m mujoco_drone_b200.build`")

@@ -127,6 +127,28 @@ __global__ void control_reference_kernel(int n, int ld, const T *axes, T *refp) 
     for (int k = 0; k < 3; k++) r[k] = clamp_(r[k], -lim[k], lim[k]);      // clip to start_pos +- (5,5,6); ref rows are offsets
     for (int k = 0; k < 4; k++) col[k * kTile] = r[k];
 }
+// setpoint streams on the device (evaluation.py:135-152 gen_circle / gen_step / gen_ramp_trajectory): env i follows the
+// trajectory at time t + i * phase_step, so a batch covers every phase of it; the setpoint page holds offsets from start_pos
+template <typename T>
+__global__ void trajectory_kernel(int n, T *refp, int kind, double t, double phase_step, double p0, double p1, double p2,
+                                  double s0, double s1, double s2, double s3, double e0, double e1, double e2, double e3,
+                                  double st0, double st1, double st2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ti = t + phase_step * i;
+    double r[4];
+    if (kind == DSIM_TRAJ_CIRCLE) {               // p0 = f, p1 = r, p2 = h  (:135-138)
+        r[0] = p1 * cos(2 * kPi * p0 * ti); r[1] = p1 * sin(2 * kPi * p0 * ti); r[2] = p2; r[3] = 0;
+    } else if (kind == DSIM_TRAJ_STEP) {          // p0 = step_time  (:141-144)
+        const bool a = ti < p0;
+        r[0] = a ? s0 : e0; r[1] = a ? s1 : e1; r[2] = a ? s2 : e2; r[3] = a ? s3 : e3;
+    } else {                                      // ramp: p0 = start_time, p1 = duration  (:147-152)
+        const double w = ti < p0 ? 0.0 : (ti - p0) / (p1 - p0);
+        r[0] = s0 + w * (e0 - s0); r[1] = s1 + w * (e1 - s1); r[2] = s2 + w * (e2 - s2); r[3] = s3 + w * (e3 - s3);
+    }
+    T *col = refp + page_elem(REF_ROWS, 0, i);
+    col[0] = (T)(r[0] - st0); col[kTile] = (T)(r[1] - st1); col[2 * kTile] = (T)(r[2] - st2); col[3 * kTile] = (T)r[3];
+}
 // one row of a paged buffer := value, for the first n envs
 template <typename T> __global__ void fill_row_kernel(int n, T *base, int page_rows, int row, T value) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -543,6 +565,25 @@ extern "C" int dsim_control_reference(DsimHandle *h, const void *axes_dev, void 
     const int grid = (h->n + 127) / 128;
     if (h->rs == 4) control_reference_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(h->n, h->ld, (const float *)axes_dev, (float *)h->refp);
     else control_reference_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(h->n, h->ld, (const double *)axes_dev, (double *)h->refp);
+    h->launches++;
+    CK(cudaGetLastError());
+    return DSIM_OK;
+}
+
+extern "C" int dsim_trajectory_reference(DsimHandle *h, int kind, double t, double phase_step, const double params[3],
+                                         const double start_pos[4], const double end_pos[4], void *stream) {
+    if (!h || !params) return DSIM_EINVAL;
+    if (!h->cfg.per_env_reference) return fail(h, DSIM_EUNSUPPORTED, "dsim_trajectory_reference needs per_env_reference=1%s", "");
+    if (kind < DSIM_TRAJ_CIRCLE || kind > DSIM_TRAJ_RAMP) return fail(h, DSIM_EINVAL, "unknown trajectory kind%s", "");
+    if (kind != DSIM_TRAJ_CIRCLE && (!start_pos || !end_pos)) return DSIM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const double z4[4] = {0, 0, 0, 0};
+    const double *s = start_pos ? start_pos : z4, *e = end_pos ? end_pos : z4, *c = h->cfg.start_pos;
+    const int grid = (h->n + 127) / 128;
+    if (h->rs == 4) trajectory_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(h->n, (float *)h->refp, kind, t, phase_step, params[0], params[1], params[2],
+                                                                                     s[0], s[1], s[2], s[3], e[0], e[1], e[2], e[3], c[0], c[1], c[2]);
+    else trajectory_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(h->n, (double *)h->refp, kind, t, phase_step, params[0], params[1], params[2],
+                                                                           s[0], s[1], s[2], s[3], e[0], e[1], e[2], e[3], c[0], c[1], c[2]);
     h->launches++;
     CK(cudaGetLastError());
     return DSIM_OK;

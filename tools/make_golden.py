@@ -218,6 +218,19 @@ try:
 except ValueError as ex:
     assert str(ex) == "Action dimension mismatch"
 
+# ---------------------------------------------------------------- trajectory generators (evaluation.py:135-152)
+# evaluation.py imports ray / pickle-loads checkpoints at module level: execute only the three generator definitions
+import ast
+_src = open("/root/reference/evaluation.py").read()
+_ns = {"np": np}
+for node in ast.parse(_src).body:
+    if isinstance(node, ast.FunctionDef) and node.name in ("gen_circle_trajectory", "gen_step_trajectory", "gen_ramp_trajectory"):
+        exec(compile(ast.Module([node], []), "evaluation.py", "exec"), _ns)
+tc, circ = _ns["gen_circle_trajectory"](T=3, f=0.7, r=1.5, h=14.5)
+ts, stp = _ns["gen_step_trajectory"](step_time=1.2, duration=3, start_pos=[0, 0, 15, 0], end_pos=[1, -1, 16, 0.5])
+tr, rmp = _ns["gen_ramp_trajectory"](start_time=0.8, duration=3, start_pos=[0, 0, 15, 0], end_pos=[1, -1, 16, 0.5])
+np.savez_compressed(os.path.join(OUT, "trajectories.npz"), t_circle=tc, circle=circ, t_step=ts, step=stp, t_ramp=tr, ramp=rmp)
+
 print("golden fixtures written to", OUT)
 for f in sorted(os.listdir(OUT)):
     print(f"  {f:24s} {os.path.getsize(os.path.join(OUT, f)) / 1024:8.1f} KiB")
