@@ -69,7 +69,15 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nvml = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.h = None
+            try:   # NVML ignores CUDA_VISIBLE_DEVICES: resolve the CUDA device through its UUID
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.samples, self._stop = [], False
             self.t = threading.Thread(target=self._poll, daemon=True)
@@ -106,7 +114,7 @@ class ClockSampler:
     def _poll(self):
         while not self._stop:
             self.sample_now()
-            time.sleep(0.0005)
+            time.sleep(0.001)
 
     def _stop_nvml(self, t0, t1):
         self._stop = True
@@ -119,7 +127,7 @@ class ClockSampler:
         inside = [(c, r) for ts, c, r in self.samples if t0 <= ts <= t1]
         reasons = sorted({nm for _, r in inside for nm, b in bits.items() if r & b})
         return {"sm_mhz": float(np.median([c for c, _ in inside])) if inside else None, "sm_max_mhz": self.mx, "reasons": reasons,
-                "samples": len(inside), "source": "nvml sampled from the launching thread every 32 steps of the timed region + a polling thread"}
+                "samples": len(inside), "source": "nvml: a polling thread (1 ms) during the timed region + one sample while the queued steps drain (NVML calls take ~ms: none between launches)"}
 
     def stop(self, t0, t1):
         if self.nvml is not None:
@@ -253,8 +261,6 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
     t0 = time.time()
     e0.record()
     for i in range(args.steps):
-        if sampler is not None and i % 32 == 16:
-            sampler.sample_now()
         runner._graph.replay()
         runner._obs_cur.copy_(runner._obs_next)
     e1.record()
@@ -319,6 +325,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every timed step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads / hot-L2 measurements")
     ap.add_argument("--policy-dtype", default="fused", choices=["fp32", "tf32", "bf16", "fused"],
                     help="c5 policy: fused = hand-written tcgen05 kernel (bf16 operands, FP32 accumulate); others = torch / cuBLAS")
@@ -376,8 +383,6 @@ def main():
     def run_steps(k, envs_, sampler_=None):
         """k vector_steps, round-robin over the replicas; setpoints re-drawn every 50 steps of each replica (C3)"""
         for i in range(k):
-            if sampler_ is not None and i % 32 == 16:
-                sampler_.sample_now()                          # clocks DURING the timed region (the queue of launches is far ahead of the GPU)
             e = envs_[i % len(envs_)]
             if axes is not None and (i // len(envs_)) % 50 == 0:
                 e.control_reference_tensor(axes)
@@ -389,17 +394,56 @@ def main():
     run_steps(args.preroll * R, envs)
     run_steps(max(args.warmup, 3) * R, envs)                  # every replica warmed up
     barrier()
+    # The timed region replays a CUDA graph of G consecutive steps (round-robin over the replicas): at ~15 us per step the
+    # Python / ctypes launch path (~10 us per call, worse with N processes sharing a host) would otherwise be what is
+    # measured.  Setpoint updates (C3) stay outside the graph, every 50 steps per replica as before.
+    G = R * max(1, 40 // R) if not args.no_graph else 0
+    graph = None
+    if G and args.steps >= G:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            run_steps(G, envs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        saved_axes, axes = axes, None                          # no setpoint kernels inside the captured steps
+        with torch.cuda.graph(graph):
+            run_steps(G, envs)
+        axes = saved_axes
+        # capture / instantiation left the GPU idle for tens of ms (its clocks drop to the idle state): replay untimed until
+        # it has been busy for ~50 ms again, so the timed region does not include the clock ramp
+        tw = time.perf_counter()
+        while time.perf_counter() - tw < 0.05:
+            for _ in range(8):
+                graph.replay()
+            torch.cuda.synchronize(dev)
+    barrier()
     l0 = sum(e.launch_count() for e in envs)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()
-    run_steps(args.steps, envs, sampler)
+    if graph is not None:
+        done = 0
+        while done + G <= args.steps:
+            if axes is not None and (done // R) % 50 < G // R:
+                for e in envs:
+                    e.control_reference_tensor(axes)
+            graph.replay()
+            done += G
+        graph_launches = done
+        run_steps(args.steps - done, envs, sampler)            # remainder, eager
+    else:
+        graph_launches = 0
+        run_steps(args.steps, envs, sampler)
     e1.record()
+    if sampler is not None:
+        sampler.sample_now()                                   # the queue of replays is still draining: GPU under the timed load
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
-    launches = sum(e.launch_count() for e in envs) - l0
+    launches = sum(e.launch_count() for e in envs) - l0 + graph_launches
     ms = e0.elapsed_time(e1)
     st = {k: sum(e.episode_stats()[k] for e in envs) for k in ddist.STAT_KEYS}
     stats = ddist.allreduce_episode_stats(st, device=dev)     # the path's only collective
@@ -465,6 +509,7 @@ def main():
         "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "envs_per_gpu": n, "total_envs": n * world, "frame_skip": 1, "timestep": 0.01,
                    "actions": "random U[0,1]^4 from an HBM-resident bank", "auto_reset": "in-kernel Philox", "preroll_steps_per_replica": args.preroll,
+                   "launch": (f"CUDA graph of {G} consecutive steps replayed" if graph is not None else "one Python/ctypes launch per step"),
                    "l2": (f"inputs larger than L2: {R} independent replicas of the batch stepped round-robin, {R * per_replica / 1e6:.0f} MB working set vs 126 MB L2"
                           if R > 1 else "not flushed (single replica)"),
                    "replicas": R,
