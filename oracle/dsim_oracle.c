@@ -813,22 +813,34 @@ void orc_sample_params(const OrcResetCfg *c, uint32_t seed, uint32_t env, uint32
  * alpha / beta = log(exp(clamp(x, -50, 50)) + 1) + 1 (:12-13), chunked alpha-first (:16); sample = Beta(alpha, beta) as
  * Ga / (Ga + Gb) with Marsaglia-Tsang gammas on the Philox stream (key = seed, env; counter = block, step, 2, variate);
  * deterministic = mean (:24-26); logp = sum_k log pdf(clamp(x_k, 0.01, 0.99)) (:19-22). */
-static double gamma_mt(double a, uint32_t seed, uint32_t env, uint32_t step, uint32_t vi) {
-    double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
-    for (uint32_t blk = 0; blk < 8; blk++) {
+static int mt_accept(double d, double c, double z, double u, double *out) {
+    double t = 1.0 + c * z;
+    if (!(t > 0)) return 0;
+    double v = t * t * t;
+    if (!(log(u) < 0.5 * z * z + d - d * v + d * log(v))) return 0;
+    *out = d * v;
+    return 1;
+}
+static double gamma_mt_retry(double d, double c, uint32_t seed, uint32_t env, uint32_t step, uint32_t vi) {
+    for (uint32_t blk = 1; blk < 8; blk++) {
         uint32_t ctr[4] = {blk, step, 2u, vi}, key[2] = {seed, env}, x[4];
         orc_philox4x32(ctr, key, x);
-        double z[2];
-        box_muller(x[0], x[1], &z[0], &z[1]);
-        for (int j = 0; j < 2; j++) {
-            double t = 1.0 + c * z[j];
-            if (t > 0) {
-                double v = t * t * t, u = u01(x[2 + j]);
-                if (log(u) < 0.5 * z[j] * z[j] + d - d * v + d * log(v)) return d * v;
-            }
-        }
+        double z0, z1, out;
+        box_muller(x[0], x[1], &z0, &z1);
+        if (mt_accept(d, c, z0, u01(x[2]), &out)) return out;
+        if (mt_accept(d, c, z1, u01(x[3]), &out)) return out;
     }
     return d;
+}
+/* one Philox block (counter block 0 of variate 2k) feeds the first attempt of both variates of action k */
+static void gamma_pair(double a, double b, uint32_t seed, uint32_t env, uint32_t step, uint32_t k, double *ga, double *gb) {
+    double da = a - 1.0 / 3.0, ca = 1.0 / sqrt(9.0 * da), db = b - 1.0 / 3.0, cb = 1.0 / sqrt(9.0 * db);
+    uint32_t ctr[4] = {0u, step, 2u, 2u * k}, key[2] = {seed, env}, x[4];
+    orc_philox4x32(ctr, key, x);
+    double z0, z1;
+    box_muller(x[0], x[1], &z0, &z1);
+    if (!mt_accept(da, ca, z0, u01(x[2]), ga)) *ga = gamma_mt_retry(da, ca, seed, env, step, 2u * k);
+    if (!mt_accept(db, cb, z1, u01(x[3]), gb)) *gb = gamma_mt_retry(db, cb, seed, env, step, 2u * k + 1u);
 }
 static double softplus1(double x) { x = x < -50 ? -50 : (x > 50 ? 50 : x); return log(exp(x) + 1.0) + 1.0; }
 void orc_beta_policy(const double *logits, int n, int nact, uint32_t seed, uint32_t env0, uint32_t step, int deterministic,
@@ -839,7 +851,8 @@ void orc_beta_policy(const double *logits, int n, int nact, uint32_t seed, uint3
             double a = softplus1(logits[(size_t)i * 2 * nact + k]), b = softplus1(logits[(size_t)i * 2 * nact + nact + k]), s;
             if (deterministic) s = a / (a + b);
             else {
-                double ga = gamma_mt(a, seed, env0 + (uint32_t)i, step, (uint32_t)(2 * k)), gb = gamma_mt(b, seed, env0 + (uint32_t)i, step, (uint32_t)(2 * k + 1));
+                double ga, gb;
+                gamma_pair(a, b, seed, env0 + (uint32_t)i, step, (uint32_t)k, &ga, &gb);
                 s = ga / (ga + gb);
             }
             actions[(size_t)i * nact + k] = s;
