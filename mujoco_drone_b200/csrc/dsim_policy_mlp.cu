@@ -55,6 +55,9 @@ DEV uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_byte
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128
 __host__ __device__ constexpr uint32_t umma_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
 
+// next K-step of the same operand: only the 14-bit start-address field moves (no carry out of it for our < 227 KB layout)
+DEV uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+
 DEV void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
@@ -68,6 +71,12 @@ DEV void mma_commit(uint64_t *bar) {
 }
 DEV void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 DEV void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Ping-pong schedule (named barriers 3 + w): the special-function unit (tanh) is the scarce pipe of this kernel and both
+// warpgroups run the same program, so left alone they fall into lock-step, fight over the SFU in their epilogues and
+// leave the tensor core idle meanwhile.  A warpgroup may only run an epilogue while it holds the turn; it passes the turn
+// to the other warpgroup when done, which forces the two to alternate: one in its epilogue, the other issuing MMAs.
+DEV void turn_wait(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 3) : "memory"); }
+DEV void turn_pass(int wg) { asm volatile("bar.arrive %0, 256;" ::"r"((wg ^ 1) + 3) : "memory"); }
 DEV void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 DEV void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -121,6 +130,7 @@ struct MlpParams {
     const float *c;           // fp32 constants [C_ELEMS]
     const float *obs;         // [n][22]
     const float *prev_action; // [n][4]
+    const unsigned char *reset_mask;   // [n] or nullptr: rows with mask != 0 see a zero previous action (episode start)
     float *logits;            // [n][8]
     float *value;             // [n]
     int *error;               // set to 1 on a barrier timeout
@@ -184,6 +194,23 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
     uint32_t parity = 0;
     bool ok = true;
 
+    // input rows are software-pipelined: nxt_* hold the obs / previous action of the tile this warpgroup will process next
+    float nxt_o[OBS_DIM], nxt_a[A_DIM];
+    auto load_row = [&](int tile_) {
+        const int r_ = tile_ * 128 + wt;
+        const bool live_ = tile_ < p.ntiles && r_ < p.n;
+        #pragma unroll
+        for (int k = 0; k < OBS_DIM; k += 2) {
+            const float2 v = live_ ? __ldg(reinterpret_cast<const float2 *>(p.obs + (size_t)r_ * OBS_DIM + k)) : make_float2(0.f, 0.f);
+            nxt_o[k] = v.x; nxt_o[k + 1] = v.y;
+        }
+        const bool fresh = live_ && p.reset_mask && p.reset_mask[r_];
+        const float4 v = (live_ && !fresh) ? __ldg(reinterpret_cast<const float4 *>(p.prev_action) + r_) : make_float4(0.f, 0.f, 0.f, 0.f);
+        nxt_a[0] = v.x; nxt_a[1] = v.y; nxt_a[2] = v.z; nxt_a[3] = v.w;
+    };
+    load_row(2 * blockIdx.x + wg);
+    constexpr int kTurnsPerTile = 6;                                       // epilogues that take a turn (the 16-column logits read does not)
+    if (wg == 1) turn_pass(1);                                             // warpgroup 0 holds the first turn
     int dbg_k = 0;
     auto stamp = [&]() { if (p.dbg && blockIdx.x == 0 && wt == 0 && dbg_k < 32) p.dbg[wg * 32 + dbg_k++] = clock64(); };
     for (int tile = 2 * blockIdx.x + wg; tile < p.ntiles; tile += 2 * gridDim.x) {
@@ -194,14 +221,10 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
         {
             float o[OBS_DIM], a[A_DIM];
             #pragma unroll
-            for (int k = 0; k < OBS_DIM; k += 2) {
-                const float2 v = live ? __ldg(reinterpret_cast<const float2 *>(p.obs + (size_t)row * OBS_DIM + k)) : make_float2(0.f, 0.f);
-                o[k] = v.x; o[k + 1] = v.y;
-            }
-            {
-                const float4 v = live ? __ldg(reinterpret_cast<const float4 *>(p.prev_action) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
-                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-            }
+            for (int k = 0; k < OBS_DIM; k++) o[k] = nxt_o[k];
+            #pragma unroll
+            for (int k = 0; k < A_DIM; k++) a[k] = nxt_a[k];
+            load_row(tile + 2 * (int)gridDim.x);                           // prefetch: in flight during this tile's seven MMA / epilogue rounds
             float hdn[ENC_H];                                                // parameter encoder on the CUDA cores (448 MACs)
             #pragma unroll
             for (int j = 0; j < ENC_H; j++) {
@@ -241,17 +264,19 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
         for (int half = 0; half < 2; half++) {
             if (wt == 0) {
                 fence_after_sync();
+                const uint64_t da = umma_desc(x0_addr, 2048, 128), db = umma_desc(w_addr + (W1_OFF + half * 128 * 8) * 2, W1_N * 16, 128);
                 #pragma unroll
                 for (int s = 0; s < K1 / 16; s++)
-                    mma_ss(tD0, umma_desc(x0_addr + s * 2 * 2048, 2048, 128),
-                           umma_desc(w_addr + (W1_OFF + (s * 2) * W1_N * 8 + half * 128 * 8) * 2, W1_N * 16, 128), umma_idesc(128), s > 0);
+                    mma_ss(tD0, desc_advance(da, s * 2 * 2048), desc_advance(db, s * 2 * W1_N * 16), umma_idesc(128), s > 0);
                 mma_commit(bar);
             }
             stamp();
             ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
             stamp();
             fence_after_sync();
+            turn_wait(wg);
             epilogue_to_tmem(tD, tA + half * 64, s_c + C_B1 + half * 128);
+            turn_pass(wg);
             fence_before_sync();
             wg_sync(wg);
             stamp();
@@ -259,38 +284,42 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
         // ---- h2 = tanh(W2 h1 + b2): K = 256, A from TMEM (operand region columns 0..127)
         if (wt == 0) {
             fence_after_sync();
-            #pragma unroll
-            for (int s = 0; s < 256 / 16; s++)
-                mma_ts(tD0, tA0 + s * 8, umma_desc(w_addr + (W2_OFF + (s * 2) * W2_N * 8) * 2, W2_N * 16, 128), umma_idesc(128), s > 0);
+            const uint64_t db = umma_desc(w_addr + W2_OFF * 2, W2_N * 16, 128);
+            #pragma unroll 4
+            for (int s = 0; s < 256 / 16; s++) mma_ts(tD0, tA0 + s * 8, desc_advance(db, s * 2 * W2_N * 16), umma_idesc(128), s > 0);
             mma_commit(bar);
         }
         stamp();
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
         stamp();
         fence_after_sync();
+        turn_wait(wg);
         epilogue_to_tmem(tD, tA, s_c + C_B2);                                // h2 -> columns 0..63
+        turn_pass(wg);
         fence_before_sync();
         wg_sync(wg);
         stamp();
         // ---- l1 = tanh(W3' h2 + b3') -> columns 64..127
         if (wt == 0) {
             fence_after_sync();
-            #pragma unroll
-            for (int s = 0; s < 128 / 16; s++)
-                mma_ts(tD0, tA0 + s * 8, umma_desc(w_addr + (W3_OFF + (s * 2) * W3_N * 8) * 2, W3_N * 16, 128), umma_idesc(128), s > 0);
+            const uint64_t db = umma_desc(w_addr + W3_OFF * 2, W3_N * 16, 128);
+            #pragma unroll 4
+            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + s * 8, desc_advance(db, s * 2 * W3_N * 16), umma_idesc(128), s > 0);
             mma_commit(bar);
         }
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
         fence_after_sync();
+        turn_wait(wg);
         epilogue_to_tmem(tD, tA + 64, s_c + C_B3);
+        turn_pass(wg);
         fence_before_sync();
         wg_sync(wg);
         // ---- logits = W4 l1 + b4 (N = 16, 8 real)
         if (wt == 0) {
             fence_after_sync();
-            #pragma unroll
-            for (int s = 0; s < 128 / 16; s++)
-                mma_ts(tD0, tA0 + 64 + s * 8, umma_desc(w_addr + (W4_OFF + (s * 2) * W4_N * 8) * 2, W4_N * 16, 128), umma_idesc(16), s > 0);
+            const uint64_t db = umma_desc(w_addr + W4_OFF * 2, W4_N * 16, 128);
+            #pragma unroll 4
+            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + 64 + s * 8, desc_advance(db, s * 2 * W4_N * 16), umma_idesc(16), s > 0);
             mma_commit(bar);
         }
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
@@ -309,26 +338,29 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
         // ---- v1 = tanh(V1' h2 + c1') -> columns 64..127 (l1 is dead)
         if (wt == 0) {
             fence_after_sync();
-            #pragma unroll
-            for (int s = 0; s < 128 / 16; s++)
-                mma_ts(tD0, tA0 + s * 8, umma_desc(w_addr + (W3_OFF + (s * 2) * W3_N * 8 + 128 * 8) * 2, W3_N * 16, 128), umma_idesc(128), s > 0);
+            const uint64_t db = umma_desc(w_addr + (W3_OFF + 128 * 8) * 2, W3_N * 16, 128);
+            #pragma unroll 4
+            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + s * 8, desc_advance(db, s * 2 * W3_N * 16), umma_idesc(128), s > 0);
             mma_commit(bar);
         }
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
         fence_after_sync();
+        turn_wait(wg);
         epilogue_to_tmem(tD, tA + 64, s_c + C_B3 + 128);
+        turn_pass(wg);
         fence_before_sync();
         wg_sync(wg);
         // ---- v2 = tanh(V2 v1 + c2); value = V3 v2 + c3
         if (wt == 0) {
             fence_after_sync();
-            #pragma unroll
-            for (int s = 0; s < 128 / 16; s++)
-                mma_ts(tD0, tA0 + 64 + s * 8, umma_desc(w_addr + (V2_OFF + (s * 2) * V2_N * 8) * 2, V2_N * 16, 128), umma_idesc(128), s > 0);
+            const uint64_t db = umma_desc(w_addr + V2_OFF * 2, V2_N * 16, 128);
+            #pragma unroll 4
+            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + 64 + s * 8, desc_advance(db, s * 2 * V2_N * 16), umma_idesc(128), s > 0);
             mma_commit(bar);
         }
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
         fence_after_sync();
+        turn_wait(wg);
         {
             float val = s_c[C_C3];
             #pragma unroll 1
@@ -344,8 +376,19 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
             }
             if (live) p.value[row] = val;
         }
+        turn_pass(wg);
         fence_before_sync();
         wg_sync(wg);                                                         // D and the operand region are free for the next tile
+    }
+    {   // the two warpgroups may own different numbers of tiles: keep passing the turn for the other one's remaining epilogues
+        const int first = 2 * blockIdx.x, stride = 2 * gridDim.x;
+        const int mine = (first + wg < p.ntiles) ? (p.ntiles - 1 - (first + wg)) / stride + 1 : 0;
+        const int other = (first + (wg ^ 1) < p.ntiles) ? (p.ntiles - 1 - (first + (wg ^ 1))) / stride + 1 : 0;
+        // turns alternate 0,1,0,1,...: after my last epilogue the other warpgroup still needs (its epilogues - mine) grants, minus
+        // the one warpgroup 1 handed out before the loop
+        int extra = (other - mine) * kTurnsPerTile;
+        for (int k = 0; k < extra; k++) { turn_wait(wg); turn_pass(wg); }
+        if (wg == 0) turn_wait(0);                                         // balance the grant warpgroup 1 handed out before the loop
     }
     if (!ok) atomicExch(p.error, 1);
     fence_before_sync();
@@ -407,12 +450,13 @@ extern "C" void dsim_policy_destroy(DsimPolicy *h) {
     delete h;
 }
 
-extern "C" int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev, int n, float *logits_dev, float *value_dev, void *stream) {
+extern "C" int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev, const uint8_t *reset_mask_dev, int n,
+                                   float *logits_dev, float *value_dev, void *stream) {
     if (!h || !obs_dev || !prev_action_dev || !logits_dev || !value_dev || n <= 0) return DSIM_EINVAL;
     if (((uintptr_t)obs_dev & 7) || ((uintptr_t)prev_action_dev & 15) || ((uintptr_t)logits_dev & 15)) return DSIM_EINVAL;
     if (cudaSetDevice(h->device) != cudaSuccess) return DSIM_ECUDA;
     MlpParams p;
-    p.w = h->w; p.c = h->c; p.obs = obs_dev; p.prev_action = prev_action_dev; p.logits = logits_dev; p.value = value_dev; p.error = h->error;
+    p.w = h->w; p.c = h->c; p.obs = obs_dev; p.prev_action = prev_action_dev; p.reset_mask = reset_mask_dev; p.logits = logits_dev; p.value = value_dev; p.error = h->error;
     p.n = n; p.ntiles = (n + 127) / 128; p.dbg = h->dbg;
     const int pairs = (p.ntiles + 1) / 2;
     const int grid = pairs < h->sms ? pairs : h->sms;

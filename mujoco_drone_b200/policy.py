@@ -154,7 +154,7 @@ class FusedRMAFull:
             raise _lib.DsimError(rc, "dsim_policy_create failed (needs a CUDA device: there is no CPU fallback)")
         self._h = h
 
-    def __call__(self, obs, prev_action, logits_out=None, value_out=None):
+    def __call__(self, obs, prev_action, logits_out=None, value_out=None, reset_mask=None):
         torch = self._torch
         n = obs.shape[0]
         if obs.shape != (n, 22) or prev_action.shape != (n, 4) or obs.dtype != torch.float32 or prev_action.dtype != torch.float32:
@@ -163,7 +163,10 @@ class FusedRMAFull:
         logits = logits_out if logits_out is not None else torch.empty((n, 8), dtype=torch.float32, device=obs.device)
         value = value_out if value_out is not None else torch.empty((n,), dtype=torch.float32, device=obs.device)
         stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
-        rc = self._L.dsim_policy_forward(self._h, C.c_void_p(obs.data_ptr()), C.c_void_p(prev_action.data_ptr()), n,
+        if reset_mask is not None and (reset_mask.dtype != torch.uint8 or reset_mask.numel() != n or not reset_mask.is_contiguous()):
+            raise ValueError("reset_mask must be a contiguous uint8 tensor [n]")
+        rc = self._L.dsim_policy_forward(self._h, C.c_void_p(obs.data_ptr()), C.c_void_p(prev_action.data_ptr()),
+                                         C.c_void_p(reset_mask.data_ptr()) if reset_mask is not None else None, n,
                                          C.c_void_p(logits.data_ptr()), C.c_void_p(value.data_ptr()), stream)
         if rc != _lib.OK:
             raise _lib.DsimError(rc, "dsim_policy_forward failed")

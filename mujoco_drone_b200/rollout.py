@@ -49,13 +49,17 @@ class RolloutRunner:
         self.total_steps = 0
         if policy_dtype == "tf32":
             torch.backends.cuda.matmul.allow_tf32 = True
-        self._obs_cur.copy_(env.reset_tensor())
+        # the policy reads the env's observation buffer in place: the step kernel overwrites it only after the policy and the
+        # sampling kernel of the same step have run (stream order)
+        self._obs_cur = env.reset_tensor()
+        self._mask = env.truncated_tensor
+        self._mask.fill_(1)                             # every env starts an episode: zero previous action
 
     # one policy + sample + env step on the static buffers
     def _forward(self):
         torch = self.torch
-        if self._fused is not None:
-            return self._fused(self._obs_cur, self.prev_actions, logits_out=self._logits, value_out=self._val)
+        if self._fused is not None:   # reads the env's own observation / truncated buffers and last step's actions: no copies, no masking kernels
+            return self._fused(self._obs_cur, self._act, logits_out=self._logits, value_out=self._val, reset_mask=self._mask)
         with torch.no_grad():
             if self.policy_dtype == "bf16":
                 with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -75,8 +79,8 @@ class RolloutRunner:
         self._step_ctr.add_(1)
         obs, rew, trunc = self.env.step_tensor(self._act)
         self._obs_next, self._rew, self._trunc = obs, rew, trunc
-        # first action of a new episode sees zeros as its previous action
-        self.prev_actions.copy_(self._act * (trunc == 0).to(self._act.dtype).unsqueeze(1))
+        if self._fused is None:   # first action of a new episode sees zeros as its previous action
+            self.prev_actions.copy_(self._act * (trunc == 0).to(self._act.dtype).unsqueeze(1))
 
     def _capture(self):
         torch = self.torch
@@ -85,7 +89,6 @@ class RolloutRunner:
         with torch.cuda.stream(s):
             for _ in range(3):                 # warm-up outside capture: lazy init, cuBLAS workspaces, smem attribute opt-in
                 self._one_step()
-                self._obs_cur.copy_(self._obs_next)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
@@ -107,7 +110,6 @@ class RolloutRunner:
         self.logp[t].copy_(self._logp)
         self.rewards[t].copy_(self._rew)
         self.truncated[t].copy_(self._trunc)
-        self._obs_cur.copy_(self._obs_next)
         self.total_steps += 1
 
     def run(self):
