@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[3]: RMA domain randomisation, 1M envs over 8 GPUs = 131072 per GPU (train_RMA.py:66-75)
     "c4": dict(cls="LocalFrameRPYParamsEnv", reward="distance_energy_reward", envs_per_gpu=131072, alg_bytes=104 + 94 + 88 + 24,
+               traffic=25.94e6 + 0.02e6, traffic_src="profiles/r01t_step_kernel_steady_state.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full; the 19.7 MB of algorithmic writes stay in the 126 MB L2 past the end of the kernel)",
                cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True),
                name="C4: LocalFrameRPYParamsEnv(22 obs)+distance_energy_reward, per-env randomised params, 131072 envs/GPU (1M over 8 GPUs)"),
     # configs[1]: BaseDroneEnv, 4096 envs, default (hover-at-reference) reward, raw 33-float obs
@@ -371,7 +372,8 @@ def main():
     bank = torch.rand((nbank, n, 4), device=dev, generator=g)   # synthetic random actions ~U[0,1]^4, resident in HBM
     axes = None
     if wl["cfg"].get("per_env_reference"):
-        axes = (torch.rand((4, n), device=dev, generator=g) * 2 - 1).mul(100).round().div(100)   # joystick.py:36 rounds to 2 decimals
+        ld = (n + 31) // 32 * 32
+        axes = (torch.rand((4, ld), device=dev, generator=g) * 2 - 1).mul(100).round().div(100).contiguous()   # joystick.py:36 rounds to 2 decimals
 
     def barrier():
         if world > 1:
@@ -515,8 +517,9 @@ def main():
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * (4 * env.obs_dim + 4 + 1),
                 "steps": e2e_steps, "api": "dsim_step_host (C ABI) with pinned host buffers"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": "step_kernel<float,true>", "algorithmic_bytes_per_env_step": wl["alg_bytes"], "peak_source": peak_src},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": wl.get("traffic"),
+                     "traffic_source": wl.get("traffic_src"), "kernel": "step_kernel<float,true>", "algorithmic_bytes_per_launch": wl["alg_bytes"] * n,
+                     "algorithmic_bytes_per_env_step": wl["alg_bytes"], "peak_source": peak_src},
         "clocks": clocks,
         "episode_stats": {k: stats[k] for k in ("n_episodes", "mean_return", "mean_length", "n_nonfinite", "n_near_ground")},
     }

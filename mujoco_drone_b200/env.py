@@ -473,11 +473,16 @@ class BaseDroneEnv(_VectorEnv):
         raise NotImplementedError("joystick polling (pygame) is out of scope; use control_reference_tensor(axes)")
 
     def control_reference_tensor(self, axes):
-        """(:151-172) per-env setpoint update from joystick-style axes: CUDA tensor [4, N] = (x, -y, -z, -yaw)."""
-        ld = self.reference_tensor.shape[1] * _lib.TILE
-        buf = self._torch.zeros((4, ld), dtype=self.reference_tensor.dtype, device=self._device)
-        buf[:, :self.num_drones] = axes
-        self._ck(self._L.dsim_control_reference(self._h, C.c_void_p(buf.data_ptr()), self._stream()))
+        """(:151-172) per-env setpoint update from joystick-style axes: CUDA tensor [4, N] = (x, -y, -z, -yaw).
+        A contiguous [4, ld] tensor (ld = npages * 32) of the env's dtype is consumed in place, anything else is staged."""
+        r = self.reference_tensor
+        ld = r.shape[1] * _lib.TILE
+        if not (axes.is_cuda and axes.dtype == r.dtype and axes.is_contiguous() and tuple(axes.shape) == (4, ld)):
+            buf = self._torch.zeros((4, ld), dtype=r.dtype, device=self._device)
+            buf[:, :self.num_drones] = axes
+            axes = buf
+        self._ck(self._L.dsim_control_reference(self._h, C.c_void_p(axes.data_ptr()), self._stream()))
+        self._states_cache = None
 
     def render(self, *a, **k):
         return None
