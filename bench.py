@@ -360,7 +360,7 @@ def main():
     # global env ids, so distinct Philox streams), stepped round-robin.  Their combined working set (state + constants +
     # observations + actions per replica) is > 2x the 126 MB L2, so every timed step streams its batch from HBM.
     obs_dim_guess = {"BaseDroneEnv": 33, "LocalFrameRPYEnv": 16}.get(wl["cls"], 22)
-    per_replica = n * (26 * 4 + 19 * 4 + 4 * 4 + obs_dim_guess * 4 + 16 + 5)
+    per_replica = n * (27 * 4 + 19 * 4 + 4 * 4 + obs_dim_guess * 4 + 16 + 5)
     R = 1 if args.no_flush else min(32, max(2, -(-2 * 132_000_000 // per_replica) + 1))
     envs = [make_env(wl, n, (rank * R + r) * n, local_rank) for r in range(R)]
     env = envs[0]

@@ -14,10 +14,11 @@
  * precision == DSIM_FP64.  Per-env data lives in PAGES of 32 envs (one warp of the step kernel); a page of a buffer
  * with R rows is the contiguous block real[R][32], so ONE 1D bulk copy (TMA) moves a warp's whole working set:
  *     element (row r, env i)  =  base[(i / 32) * R * 32 + r * 32 + (i % 32)]          ("PAGED", R = page_rows)
- *   read-write page (R = 26):  rows 0-23 state = MuJoCo's qpos[9], qvel[8], act[4], sensordata[3] per drone
+ *   read-write page (R = 27):  rows 0-23 state = MuJoCo's qpos[9], qvel[8], act[4], sensordata[3] per drone
  *           (BaseDroneEnv.py:367-375): 0-2 position OFFSET from start_pos[0:3] | 3-6 quat (w,x,y,z) | 7-8 hinge angles
  *           | 9-11 world linear velocity | 12-14 body angular velocity | 15-16 hinge rates | 17-20 `act` | 21-23 accelerometer;
- *           row 24 BaseDroneEnv.num_steps (integer of the width of `real`), row 25 running episode return
+ *           row 24 BaseDroneEnv.num_steps (integer of the width of `real`), row 25 running episode return,
+ *           row 26 reset count (integer; Philox epoch of the env's reset stream)
  *   read-only page  (R = 19):  rows 0-12 compiled rigid-body constants, rows 13-18 raw drone_params
  *   setpoint page   (R = 4):   x, y, z offsets from start_pos and yaw (only read when per_env_reference)
  *   ld = num_envs rounded up to a multiple of 32.
@@ -46,7 +47,7 @@ enum {
     DSIM_BUF_PARAMS = 5,     /* real  PAGED 6 rows of the read-only page         BaseDroneEnv.drone_params (:117) */
     DSIM_BUF_CONSTS = 6,     /* real  PAGED 13 rows of the read-only page        (MjModel of env_gen.py) */
     DSIM_BUF_REFERENCE = 7,  /* real  PAGED 4 rows: per-env setpoint (xyz offset from start_pos, yaw); only if per_env_reference */
-    DSIM_BUF_RESET_COUNT = 8,/* uint32[N] Philox epoch of each env's reset stream */
+    DSIM_BUF_RESET_COUNT = 8,/* int   PAGED 1 row: Philox epoch of each env's reset stream */
     DSIM_BUF_STATES33 = 9,   /* real  [N][33|29] get_drone_states() rows, filled by dsim_compute_states */
     DSIM_BUF_EP_RETURN = 10, /* real  PAGED 1 row: running return of the current episode */
     DSIM_BUF_STATS = 11      /* double[8]: sum_return, sum_length, n_episodes, n_nonfinite, n_near_ground, 0,0,0 */

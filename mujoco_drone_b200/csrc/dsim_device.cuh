@@ -44,8 +44,9 @@ enum { C_MB = 0, C_CZ, C_IBX, C_IBY, C_IBZ, C_MD, C_ZD, C_IDX, C_IDZ, C_FS, C_F,
 // contiguous 1D bulk-copy (TMA, cp.async.bulk) between HBM and a warp's shared-memory slot; inside the slot every
 // row is a conflict-free 128-byte (FP32) line and each row is reached with an immediate offset from one base.
 constexpr int kTile = 32;
-// read-write page: MuJoCo state (qpos, qvel, act, sensordata) + BaseDroneEnv.num_steps + running episode return
-enum { RW_NUM_STEPS = S_ROWS, RW_EP_RETURN = S_ROWS + 1, RW_ROWS = S_ROWS + 2 };
+// read-write page: MuJoCo state (qpos, qvel, act, sensordata) + BaseDroneEnv.num_steps + running episode return + the
+// env's reset count (Philox epoch of its reset stream: rides with the page so the reset path has no global round trip)
+enum { RW_NUM_STEPS = S_ROWS, RW_EP_RETURN = S_ROWS + 1, RW_RESET_COUNT = S_ROWS + 2, RW_ROWS = S_ROWS + 3 };
 // read-only page: compiled rigid-body constants + raw drone_params (rewritten only by regen / set_params)
 enum { RO_CONSTS = 0, RO_PARAMS = C_ROWS, RO_ROWS = C_ROWS + 6 };
 enum { REF_ROWS = 4 };                        // per-env setpoint page (x, y, z offsets from start_pos, yaw)

@@ -57,9 +57,9 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const KParams<T> p, const
     if (mask && !mask[i]) return;
     T *col = p.rw + page_elem(RW_ROWS, 0, i);
     EnvState<T> s = load_state(col);
-    const unsigned rcnt = first ? 0u : p.reset_count[i] + 1u;
+    const unsigned rcnt = first ? 0u : (unsigned)slot_to_int(col[RW_RESET_COUNT * kTile]) + 1u;
     sample_state<T, PEND>(s, p.rc, p.seed, p.env_base + (unsigned)i, rcnt);
-    p.reset_count[i] = rcnt;
+    col[RW_RESET_COUNT * kTile] = int_to_slot<T>((int)rcnt);
     col[RW_NUM_STEPS * kTile] = int_to_slot<T>(0);
     col[RW_EP_RETURN * kTile] = T(0);
     store_state(col, s);
@@ -166,7 +166,7 @@ struct DsimHandle {
     void *rw, *ro, *refp, *obs, *reward, *states33, *actions_stage;
     double *params64, *stats, *center_hw;
     unsigned long long *timeline;
-    unsigned *reset_count, *ticket;
+    unsigned *ticket;
     unsigned char *trunc;
     int per_env_consts;
     double uconst[C_ROWS], uparams[6];
@@ -216,7 +216,7 @@ template <typename T> static KParams<T> make_params(const DsimHandle *h, const v
     memset(&p, 0, sizeof p);
     const DsimConfig &c = h->cfg;
     p.n = h->n; p.npages = h->npages;
-    p.rw = (T *)h->rw; p.ro = (const T *)h->ro; p.reset_count = h->reset_count;
+    p.rw = (T *)h->rw; p.ro = (const T *)h->ro;
     p.refp = c.per_env_reference ? (T *)h->refp : nullptr;
     p.obs = (T *)h->obs; p.reward = (T *)h->reward;
     p.trunc = h->trunc; p.stats = h->stats; p.actions = (const T *)actions;
@@ -319,7 +319,6 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
     ALLOC(h->params64, 6 * ld * sizeof(double));
     ALLOC(h->stats, 8 * sizeof(double));
     ALLOC(h->center_hw, 12 * sizeof(double));
-    ALLOC(h->reset_count, ld * sizeof(unsigned));
     ALLOC(h->trunc, ld);
     ALLOC(h->ticket, 256);
     if (getenv("DSIM_TIMELINE")) ALLOC(h->timeline, (size_t)h->npages * 8 * sizeof(unsigned long long));   // debug instrumentation
@@ -347,7 +346,7 @@ extern "C" void dsim_destroy(DsimHandle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->rw, h->ro, h->refp, h->obs, h->reward, h->states33, h->actions_stage,
-                    h->params64, h->stats, h->center_hw, h->reset_count, h->trunc, h->timeline, h->ticket};
+                    h->params64, h->stats, h->center_hw, h->trunc, h->timeline, h->ticket};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete h;
 }
@@ -710,7 +709,7 @@ extern "C" int dsim_buffer(DsimHandle *h, int id, void **ptr, int64_t *rows, int
     case DSIM_BUF_OBS: *ptr = h->obs; *rows = n; *cols = h->obs_dim; *ld = h->obs_dim; *dtype = rdt; break;
     case DSIM_BUF_REWARD: *ptr = h->reward; *rows = 1; *cols = n; *ld = L; *dtype = rdt; break;
     case DSIM_BUF_TRUNCATED: *ptr = h->trunc; *rows = 1; *cols = n; *ld = L; *dtype = DSIM_DT_U8; break;
-    case DSIM_BUF_RESET_COUNT: *ptr = h->reset_count; *rows = 1; *cols = n; *ld = L; *dtype = DSIM_DT_U32; break;
+    case DSIM_BUF_RESET_COUNT: *ptr = rw + RW_RESET_COUNT * row_bytes; *rows = 1; *cols = n; *ld = L; *dtype = idt; *page_rows = RW_ROWS; break;
     case DSIM_BUF_STATES33: *ptr = h->states33; *rows = n; *cols = h->state_width; *ld = h->state_width; *dtype = rdt; break;
     case DSIM_BUF_STATS: *ptr = h->stats; *rows = 1; *cols = 8; *ld = 8; *dtype = DSIM_DT_F64; break;
     default: return fail(h, DSIM_EINVAL, "unknown buffer id%s", "");

@@ -68,7 +68,6 @@ template <typename T> struct KParams {
     T *rw;                    // [npages][RW_ROWS][32]
     const T *ro;              // [npages][RO_ROWS][32]
     T *refp;                  // [npages][REF_ROWS][32] (per-env setpoints) or nullptr
-    unsigned *reset_count;    // [npages * 32]
     T *obs, *reward;          // [n][obs_dim], [n]
     unsigned char *trunc;
     double *stats;
@@ -190,7 +189,7 @@ constexpr int kStages = 2;                                                    //
 // Same draws, same arithmetic as sample_state (dsim_device.cuh) = BaseDroneEnv.sample_state (:218-257).
 template <typename T> DSIM_DEV T shfl_(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 template <typename T, bool PEND>
-__device__ __noinline__ void resample_page(unsigned need, T *s_rw, const ResetCfg<T> &rc, unsigned seed, unsigned env0, unsigned *reset_count) {
+__device__ __noinline__ void resample_page(unsigned need, T *s_rw, const ResetCfg<T> &rc, unsigned seed, unsigned env0) {
     const int lane = threadIdx.x & 31, e = lane >> 3, q = lane & 7;
     while (need) {
         // the (up to) four lowest truncated lanes of this pass: P[k]; this lane computes for env P[e], and owns env `lane` if selected
@@ -204,8 +203,7 @@ __device__ __noinline__ void resample_page(unsigned need, T *s_rw, const ResetCf
         }
         T z0 = T(0), z1 = T(0), rad = T(0), yw = T(0);
         unsigned rcnt = 0;
-        if (mine >= 0) rcnt = reset_count[mine] + 1u;
-        __syncwarp();
+        if (mine >= 0) rcnt = (unsigned)slot_to_int(s_rw[RW_RESET_COUNT * kTile + mine]) + 1u;
         if (mine >= 0 && rc.random_start_pos) {
             // Box-Muller pair q: Philox block / word half of sample_state's draw order
             const int blk = q <= 1 ? 0 : q == 2 ? 1 : q <= 4 ? 2 : q <= 6 ? 3 : 4;
@@ -239,7 +237,7 @@ __device__ __noinline__ void resample_page(unsigned need, T *s_rw, const ResetCf
                 }
             }
             rpy_to_quat(roll, pitch, yaw, s.qw, s.qx, s.qy, s.qz);
-            reset_count[lane] = rc_own;
+            s_rw[RW_RESET_COUNT * kTile + lane] = int_to_slot<T>((int)rc_own);
             T *col = s_rw + lane;
             col[0 * kTile] = s.pos.x; col[1 * kTile] = s.pos.y; col[2 * kTile] = s.pos.z;
             col[3 * kTile] = s.qw; col[4 * kTile] = s.qx; col[5 * kTile] = s.qy; col[6 * kTile] = s.qz;
@@ -416,7 +414,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         }
         {
             const unsigned need = __ballot_sync(0xffffffffu, !p.eval_only && active && trunc && (p.auto_reset || bad));
-            if (need) resample_page<T, PEND>(need, s_rw, p.rc, p.seed, p.env_base + (unsigned)(page * kTile), p.reset_count + page * kTile);
+            if (need) resample_page<T, PEND>(need, s_rw, p.rc, p.seed, p.env_base + (unsigned)(page * kTile));
         }
 
         // ---- publish: slot -> HBM

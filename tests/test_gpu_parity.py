@@ -273,7 +273,6 @@ def test_vector_env_protocol_and_auto_reset(oracle):
     # native loop
     env = _mk("LocalFrameRPYParamsEnv", num_drones=n, max_steps=9, max_distance=1.5, auto_reset=True)
     env.reset_tensor()
-    rc = env.tensor(M._lib.BUF_RESET_COUNT)
     counters = np.zeros(n, dtype=np.int64)
     resets = np.zeros(n, dtype=np.int64)
     for t in range(40):
@@ -282,7 +281,7 @@ def test_vector_env_protocol_and_auto_reset(oracle):
         counters = np.where(tr, 0, counters + 1)
         resets += tr
         assert (env.num_steps == counters).all()
-        assert (rc.cpu().numpy()[:n] == resets).all()
+        assert (env.rows(M._lib.BUF_RESET_COUNT)[0].cpu().numpy() == resets).all()
     assert resets.sum() > n
     st = env.episode_stats()
     assert st["n_episodes"] == resets.sum() and st["n_nonfinite"] == 0
