@@ -12,7 +12,8 @@ import numpy as np
 
 
 class RolloutRunner:
-    def __init__(self, env, policy, horizon, seed=0, policy_dtype="fp32", use_graph=True, deterministic=False):
+    def __init__(self, env, policy, horizon, seed=0, policy_dtype="fp32", use_graph=True, deterministic=False, history_len=0,
+                 history_states=16):
         import torch
         if not env.auto_reset:
             raise ValueError("RolloutRunner needs an env created with auto_reset=True (the native loop)")
@@ -39,6 +40,13 @@ class RolloutRunner:
         self._logp = torch.zeros((N,), dtype=dt, **z)
         self._val = torch.zeros((N,), dtype=dt, **z)
         self._step_ctr = torch.zeros((1,), dtype=torch.int32, **z)
+        # 32-step (state, previous action) windows of the adaptation module / state estimators (RMA_model.py:41-43 obs_history
+        # "-31:0", action_history "-32:-1"; StateEstimatorLSTM.py:239-244): a time-major device ring buffer, one row per step
+        self.history_len, self.history_states = int(history_len), int(history_states)
+        if self.history_len:
+            self._hist = torch.zeros((self.history_len, N, self.history_states + 4), dtype=dt, **z)
+            self._hist_age = torch.zeros((N,), dtype=torch.int32, **z)      # steps since the env's episode started (caps the valid window)
+            self._hist_pos = 0
         self.policy = policy.to(self.dev)
         self._fused = None
         if policy_dtype == "fused":                    # hand-written tcgen05 kernel (csrc/dsim_policy_mlp.cu) instead of library GEMMs
@@ -101,6 +109,8 @@ class RolloutRunner:
         if self.use_graph and self._graph is None:
             self._capture()
         self.obs[t].copy_(self._obs_cur)
+        if self.history_len:
+            self._record_history()
         if self._graph is not None:
             self._graph.replay()
         else:
@@ -111,6 +121,34 @@ class RolloutRunner:
         self.rewards[t].copy_(self._rew)
         self.truncated[t].copy_(self._trunc)
         self.total_steps += 1
+
+    def _record_history(self):
+        """append (current state part of the observation, PREVIOUS action) of every env; the previous action of an episode's
+        first step is zero and the env's valid window restarts there (RLlib zero-pads views before an episode start)"""
+        torch = self.torch
+        fresh = self._mask if self._fused is not None else None
+        prev = self._act if self._fused is not None else self.prev_actions
+        if fresh is None:                                       # torch policies: prev_actions is already zeroed at episode starts
+            started = (self.prev_actions.abs().sum(1) == 0)
+        else:
+            started = fresh != 0
+        row = self._hist[self._hist_pos]
+        row[:, :self.history_states] = self._obs_cur[:, :self.history_states]
+        row[:, self.history_states:] = torch.where(started.unsqueeze(1), torch.zeros_like(prev), prev)
+        self._hist_age = torch.where(started, torch.ones_like(self._hist_age), torch.clamp(self._hist_age + 1, max=self.history_len))
+        self._hist_pos = (self._hist_pos + 1) % self.history_len
+
+    def history(self):
+        """[N, history_len, states + 4] windows, oldest first, ending at the most recently recorded step; entries from before
+        the env's current episode are zero (what RLlib's ViewRequirement hands the adaptation module / estimators)"""
+        torch = self.torch
+        if not self.history_len:
+            raise ValueError("create the runner with history_len > 0")
+        order = [(self._hist_pos + k) % self.history_len for k in range(self.history_len)]
+        h = self._hist[order].permute(1, 0, 2).clone()           # [N, L, F], oldest first
+        k = torch.arange(self.history_len, device=self.dev).unsqueeze(0)
+        valid = k >= (self.history_len - self._hist_age.unsqueeze(1))
+        return h * valid.unsqueeze(2).to(h.dtype)
 
     def run(self):
         """T steps; returns the [T(+1), N, ...] device tensors (bootstrap value of the last observation included)."""

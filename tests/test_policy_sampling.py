@@ -209,3 +209,32 @@ def test_rollout_runner_with_fused_policy_kernel():
             assert (v - b["values"][t]).abs().max().item() < 3e-2
             prev = b["actions"][t] * (b["truncated"][t] == 0).float().unsqueeze(1)
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+@pytest.mark.parametrize("mode", ["fp32", "fused"])
+def test_rollout_history_windows(mode):
+    """32-step (state, previous action) windows (RMA_model.py:41-43): rebuilt on the host from the recorded rollout"""
+    import torch
+    import mujoco_drone_b200 as M
+    n, T, L = 200, 14, 6
+    cfg = dict(M.base_config, num_drones=n, auto_reset=True, max_steps=5, param_difficulty=1.0, reward_fcn=M.rewards.distance_energy_reward)
+    env = M.observation_wrappers.LocalFrameRPYParamsEnv(cfg)
+    r = M.rollout.RolloutRunner(env, M.policy.make_rma_full(), horizon=T, seed=2, policy_dtype=mode, use_graph=False, history_len=L)
+    b = r.run()
+    h = r.history().cpu().numpy()
+    obs, act, tr = b["obs"].cpu().numpy(), b["actions"].cpu().numpy(), b["truncated"].cpu().numpy().astype(bool)
+    exp = np.zeros((n, L, 20), dtype=np.float32)
+    for i in range(n):
+        rows = []
+        for t in range(T):                                     # row t = (obs[t][:16], action[t-1] or 0 at an episode start)
+            start = t == 0 or tr[t - 1, i]
+            prev = np.zeros(4, np.float32) if start else act[t - 1, i]
+            if start:
+                rows = []
+            rows.append(np.concatenate([obs[t, i, :16], prev]))
+        rows = rows[-L:]
+        exp[i, L - len(rows):] = np.array(rows)
+    np.testing.assert_allclose(h, exp, atol=1e-6)
+    env.close()
