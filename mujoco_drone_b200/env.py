@@ -206,7 +206,7 @@ class BaseDroneEnv(_VectorEnv):
         if pr.value:
             T = _lib.TILE
             view = _DevView(ptr.value, (rows.value, ld.value // T, T), (T * item, pr.value * T * item, item), dt.value, self)
-        elif rows.value == 1:
+        elif rows.value == 1 and buf_id not in (_lib.BUF_OBS, _lib.BUF_STATES33):      # vectors; [1, D] stays 2-D for num_drones == 1
             view = _DevView(ptr.value, (cols.value,), None, dt.value, self)
         else:
             view = _DevView(ptr.value, (rows.value, cols.value), (ld.value * item, item), dt.value, self)

@@ -358,3 +358,72 @@ def test_large_batch_properties():
     assert env.episode_stats()["n_nonfinite"] == 0
     assert env.launch_count() > 0
     env.close()
+
+
+@pytest.mark.parametrize("n", [1, 33, 4097])
+def test_tiny_and_ragged_batches_match_oracle(oracle, n):
+    """edge sizes: one env, one env past a page boundary (the last page's observation block is not a multiple of 16 bytes:
+    scalar copy-out instead of the bulk store), one past 128 pages"""
+    import torch
+    import mujoco_drone_b200 as M
+    rng = np.random.default_rng(n)
+    qpos, qvel, act, actions, params = _rand_inputs(rng, n)
+    env = _mk("LocalFrameRPYParamsEnv", num_drones=n, precision="fp64", max_distance=100, reward_fcn=M.rewards.distance_energy_reward)
+    _set(env, qpos, qvel, act, params)
+    obs, rew, trunc = env.step_tensor(torch.as_tensor(actions, device="cuda"))
+    qp, qv, ac, sens, ns = env.get_state()
+    prm = env.drone_params
+    o, r = obs.cpu().numpy(), rew.cpu().numpy()
+    for i in sorted(set([0, n - 1, n // 2, max(n - 2, 0)])):
+        m = oracle.compile_model(np.array(list(prm[i].values())), True, 100, True)
+        oqp, oqv, oact, osens = oracle.step(m, qpos[i], qvel[i], act[i], 0.1 + 0.9 * actions[i], 1)
+        np.testing.assert_allclose(qp[i], oqp, atol=1e-11)
+        np.testing.assert_allclose(qv[i], oqv, atol=1e-10)
+        st = oracle.drone_state(m, qp[i], qv[i], ac[i], sens[i], [0, 0, 15, 0])
+        np.testing.assert_allclose(o[i], oracle.obs(oracle.OBS_IDS["LocalFrameRPYParamsEnv"], st, [0, 0, 15, 0]), atol=1e-9)
+        assert abs(r[i] - oracle.reward(oracle.REWARD_IDS["distance_energy_reward"], st, actions[i], 1, [0, 0, 15, 0], 100.0)) < 1e-9
+    assert (ns == 1).all() and obs.shape == (n, 22)
+    env.close()
+
+
+def test_non_finite_state_is_counted_and_recovered():
+    """MuJoCo's mj_checkPos/Vel analogue: an env whose state goes non-finite is flagged truncated, counted in
+    n_nonfinite, parked on finite outputs and re-sampled (even without auto_reset) - never silently propagated"""
+    import torch
+    import mujoco_drone_b200 as M
+    n = 70
+    env = _mk("LocalFrameRPYParamsEnv", num_drones=n, auto_reset=False, max_steps=10 ** 6, max_distance=100)
+    env.vector_reset()
+    qp, qv, act, _, _ = env.get_state()
+    qv[3, 0] = np.nan
+    qv[40, 4] = np.inf
+    qp[65, 2] = 1e12
+    env.set_state(qp, qv, act)
+    obs, rew, trunc = env.step_tensor(torch.full((n, 4), 0.5, device="cuda"))
+    tr = trunc.cpu().numpy().astype(bool)
+    assert set(np.nonzero(tr)[0]) == {3, 40, 65}
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    st = env.episode_stats()
+    assert st["n_nonfinite"] == 3 and st["n_episodes"] == 3
+    qp2, qv2, _, _, ns = env.get_state()
+    assert np.isfinite(qp2).all() and np.isfinite(qv2).all() and (ns[[3, 40, 65]] == 0).all() and (np.delete(ns, [3, 40, 65]) == 1).all()
+    obs, rew, trunc = env.step_tensor(torch.full((n, 4), 0.5, device="cuda"))
+    assert not trunc.any() and torch.isfinite(obs).all()
+    env.close()
+
+
+def test_million_env_batch_runs_and_stays_consistent():
+    """BASELINE config 4 on ONE GPU (1 048 576 envs): indices beyond 2^20, 32768 pages through the work-stealing
+    scheduler; every env is stepped exactly once per launch (step counters), outputs finite"""
+    import torch
+    import mujoco_drone_b200 as M
+    n = 1 << 20
+    env = _mk("LocalFrameRPYParamsEnv", num_drones=n, param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, auto_reset=True,
+              reward_fcn=M.rewards.distance_energy_reward)
+    env.reset_tensor()
+    a = torch.rand((n, 4), device="cuda")
+    for _ in range(5):
+        obs, rew, trunc = env.step_tensor(a)
+    assert (env.num_steps_tensor == 5).all()
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and not trunc.any()
+    env.close()
