@@ -109,10 +109,13 @@ template <typename T> DSIM_DEV V3<T> cross(V3<T> a, V3<T> b) { return mk(a.y * b
 // rotation matrix (row-major, body -> world) of a UNIT quaternion (w,x,y,z)
 template <typename T> struct M3 { T m[9]; };
 template <typename T> DSIM_DEV M3<T> quat_to_mat(T w, T x, T y, T z) {
+    // unit quaternion: diagonal as 1 - 2 (.. + ..), products shared through the doubled components (24 operations)
+    const T tx = x + x, ty = y + y, tz = z + z;
+    const T xx = x * tx, yy = y * ty, zz = z * tz, xy = x * ty, xz = x * tz, yz = y * tz, wx = w * tx, wy = w * ty, wz = w * tz;
     M3<T> R;
-    R.m[0] = w * w + x * x - y * y - z * z; R.m[1] = 2 * (x * y - w * z);           R.m[2] = 2 * (x * z + w * y);
-    R.m[3] = 2 * (x * y + w * z);           R.m[4] = w * w - x * x + y * y - z * z; R.m[5] = 2 * (y * z - w * x);
-    R.m[6] = 2 * (x * z - w * y);           R.m[7] = 2 * (y * z + w * x);           R.m[8] = w * w - x * x - y * y + z * z;
+    R.m[0] = T(1) - (yy + zz); R.m[1] = xy - wz;          R.m[2] = xz + wy;
+    R.m[3] = xy + wz;          R.m[4] = T(1) - (xx + zz); R.m[5] = yz - wx;
+    R.m[6] = xz - wy;          R.m[7] = yz + wx;          R.m[8] = T(1) - (xx + yy);
     return R;
 }
 template <typename T> DSIM_DEV V3<T> mul(const M3<T> &R, V3<T> v) {
@@ -162,8 +165,9 @@ template <typename T> DSIM_DEV FluidBox<T> fluid_box(T mass, T Ix, T Iy, T Iz) {
     return f;
 }
 template <typename T> DSIM_DEV void fluid_apply(const FluidBox<T> &b, V3<T> w, V3<T> v, V3<T> &f, V3<T> &t) {
-    f = mk(-b.kv * v.x - b.fq[0] * abs_(v.x) * v.x, -b.kv * v.y - b.fq[1] * abs_(v.y) * v.y, -b.kv * v.z - b.fq[2] * abs_(v.z) * v.z);
-    t = mk(-b.kw * w.x - b.tq[0] * abs_(w.x) * w.x, -b.kw * w.y - b.tq[1] * abs_(w.y) * w.y, -b.kw * w.z - b.tq[2] * abs_(w.z) * w.z);
+    // viscous + quadratic drag per axis: -k u - q |u| u = -u (k + q |u|): one FMA and one multiply per component
+    f = mk(-v.x * (b.kv + b.fq[0] * abs_(v.x)), -v.y * (b.kv + b.fq[1] * abs_(v.y)), -v.z * (b.kv + b.fq[2] * abs_(v.z)));
+    t = mk(-w.x * (b.kw + b.tq[0] * abs_(w.x)), -w.y * (b.kw + b.tq[1] * abs_(w.y)), -w.z * (b.kw + b.tq[2] * abs_(w.z)));
 }
 
 // symmetric 3x3 SPD solve through LDL^T (factor once, three right-hand sides per substep)

@@ -5,18 +5,23 @@
 // (:275-284) -> _get_obs (observation_wrappers.py), plus the RLlib reset_at() round trip (:334-351) folded in
 // when auto_reset is on.
 //
-// Execution plan (sm_100a): one WARP owns one page of 32 envs, one env per lane; warps never synchronise with
-// each other.
-//   * lane 0 arms the warp's mbarrier and issues 1D bulk copies (cp.async.bulk, the TMA engine: SASS UBLKCP) that
-//     bring the warp's read-write page (state + step counter + episode return), read-only page (compiled constants +
-//     raw parameters) and setpoint page from HBM into the warp's shared-memory slot: three instructions move ~6 KB,
-//     no per-row address arithmetic, no registers held while the data is in flight;
+// Execution plan (sm_100a): one WARP owns one page of 32 envs at a time, one env per lane; warps never synchronise with
+// each other (no __syncthreads).
+//   * PERSISTENT + WORK STEALING: the grid holds as many CTAs as the GPU keeps resident; a warp starts on page `wid` and
+//     draws further pages from a global ticket counter (asked for after the physics of the current page).
+//   * lane 0 arms a slot's mbarrier and issues 1D bulk copies (cp.async.bulk, the TMA engine: SASS UBLKCP) that bring the
+//     page's read-write rows (state, step counter, episode return, reset count), read-only rows (compiled constants + raw
+//     parameters), setpoint rows and its 512 bytes of actions from HBM into one of the warp's TWO shared-memory slots:
+//     four instructions move ~7 KB, no per-row address arithmetic, no registers held while data is in flight, and the
+//     next page is in flight while the current one is computed;
 //   * every lane reads its own column with immediate-offset LDS (row pitch = 32 lanes: conflict-free), runs the
 //     physics / termination / reward / observation in registers, and writes the new column and its policy-ready
-//     observation row back into the slot;
+//     observation row back into the slot (the observation block overlays the dead read-only operands);
 //   * after fence.proxy.async + __syncwarp lane 0 sends the read-write page and the warp's contiguous [32][obs_dim]
-//     observation block back with two bulk stores and waits only for their shared-memory reads.
-//   * rare paths (Philox re-sampling) are one out-of-line call so they do not inflate the hot path's registers/I-cache.
+//     observation block back with two bulk stores; their shared-memory reads are waited for only when the slot is reused;
+//   * truncated envs are re-sampled by the whole warp, four at a time (resample_page), out of line so the rare path does
+//     not inflate the hot path's registers / I-cache;
+//   * programmatic dependent launch overlaps the next step's launch latency with this step's tail.
 #pragma once
 
 #ifndef DSIM_BLOCK
@@ -87,8 +92,6 @@ template <typename T> struct KParams {
 };
 
 // integer rows of the read-write page are stored in a lane-sized slot (int32 for float pages, int64 for double)
-template <typename T> struct IntOf { typedef int type; };
-template <> struct IntOf<double> { typedef long long type; };
 template <typename T> DSIM_DEV int slot_to_int(T v) {
     if constexpr (std::is_same<T, float>::value) return __float_as_int(v); else return (int)__double_as_longlong(v);
 }
