@@ -159,6 +159,7 @@ template <typename T> __global__ void fill_row_kernel(int n, T *base, int page_r
 }  // namespace
 
 // ====================================================================== host side
+constexpr int kHostChunks = 8;
 struct DsimHandle {
     DsimConfig cfg;
     int device, n, ld, npages, obs_dim, state_width;
@@ -171,7 +172,10 @@ struct DsimHandle {
     int per_env_consts;
     double uconst[C_ROWS], uparams[6];
     double h;
-    int first_reset_done, step_grid;
+    int first_reset_done, step_grid, step_cap;
+    cudaStream_t hs[3];                // host entry point: copy-in, compute, copy-out streams (created on first use)
+    cudaEvent_t ev_in[kHostChunks], ev_k[kHostChunks], ev_a, ev_b;
+    int host_pipeline_ready;
     int64_t launches;
     char err[512];
 };
@@ -345,6 +349,11 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
 extern "C" void dsim_destroy(DsimHandle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->host_pipeline_ready) {
+        for (int i = 0; i < 3; i++) cudaStreamDestroy(h->hs[i]);
+        for (int i = 0; i < kHostChunks; i++) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
+        cudaEventDestroy(h->ev_a); cudaEventDestroy(h->ev_b);
+    }
     void *ptrs[] = {h->rw, h->ro, h->refp, h->obs, h->reward, h->states33, h->actions_stage,
                     h->params64, h->stats, h->center_hw, h->trunc, h->timeline, h->ticket};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -475,7 +484,7 @@ extern "C" int dsim_zero_act(DsimHandle *h, void *stream) {
 
 // step-kernel dispatch: compile-time specialisations for the BASELINE configs, generic kernel otherwise.  The kernel is
 // persistent: grid = min(CTAs needed, CTAs the GPU can hold at once), queried once per handle.
-template <typename K> static cudaError_t launch_one(DsimHandle *h, K kernel, unsigned smem, cudaStream_t st, const void *kp_ptr) {
+template <typename K> static cudaError_t launch_one(DsimHandle *h, K kernel, unsigned smem, cudaStream_t st, const void *kp_ptr, int pages) {
     if (!h->step_grid) {
         // opt in once to the largest slot any handle can ask for (the attribute is per function, not per handle)
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(slot_bytes(DSIM_MAX_OBS, 8) * kStages * kStepWarps));
@@ -486,11 +495,14 @@ template <typename K> static cudaError_t launch_one(DsimHandle *h, K kernel, uns
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         const int need = (h->npages + kStepWarps - 1) / kStepWarps, cap = sms * per_sm;
         h->step_grid = need < cap ? need : cap;
+        h->step_cap = cap;
     }
+    int grid = h->step_grid;
+    if (pages != h->npages) { const int need = (pages + kStepWarps - 1) / kStepWarps; grid = need < h->step_cap ? need : h->step_cap; }
     void *args[] = {const_cast<void *>(kp_ptr)};
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof lc);
-    lc.gridDim = dim3(h->step_grid); lc.blockDim = dim3(kStepBlock); lc.dynamicSmemBytes = smem; lc.stream = st;
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(kStepBlock); lc.dynamicSmemBytes = smem; lc.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // pairs with griddepcontrol.* in step_kernel
     at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -499,14 +511,15 @@ template <typename K> static cudaError_t launch_one(DsimHandle *h, K kernel, uns
 }
 template <typename T> static cudaError_t launch_step(DsimHandle *h, const KParams<T> &kp, cudaStream_t st) {
     const unsigned smem = kp.smem_per_slot * kStages * kStepWarps;
-    if (!h->cfg.pendulum) return launch_one(h, step_kernel<T, false, -1, -1>, smem, st, &kp);
+    const int pages = kp.npages - kp.page0;
+    if (!h->cfg.pendulum) return launch_one(h, step_kernel<T, false, -1, -1>, smem, st, &kp, pages);
     if constexpr (std::is_same<T, float>::value) {
         const int o = kp.obs_id, r = kp.reward_id;
-        if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2>, smem, st, &kp);   // C4 / C5
-        if (o == DSIM_OBS_LOCAL_RPY && r == 1) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1>, smem, st, &kp);                 // C3
-        if (o == DSIM_OBS_BASE && r == 0) return launch_one(h, step_kernel<float, true, DSIM_OBS_BASE, 0>, smem, st, &kp);                           // C2
+        if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2>, smem, st, &kp, pages);   // C4 / C5
+        if (o == DSIM_OBS_LOCAL_RPY && r == 1) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1>, smem, st, &kp, pages);                 // C3
+        if (o == DSIM_OBS_BASE && r == 0) return launch_one(h, step_kernel<float, true, DSIM_OBS_BASE, 0>, smem, st, &kp, pages);                           // C2
     }
-    return launch_one(h, step_kernel<T, true, -1, -1>, smem, st, &kp);
+    return launch_one(h, step_kernel<T, true, -1, -1>, smem, st, &kp, pages);
 }
 static int step_impl(DsimHandle *h, const void *actions_dev, void *stream, int eval_only) {
     CK(cudaSetDevice(h->device));
@@ -536,18 +549,68 @@ extern "C" int dsim_evaluate(DsimHandle *h, const void *actions_dev, void *strea
     return step_impl(h, actions_dev, stream, 1);
 }
 
+// vector_step with HOST buffers.  Large batches are stepped in kHostChunks page ranges on three internal streams so that
+// the PCIe legs overlap the kernel: H2D actions(k+1) | step kernel(k) | D2H observations(k-1).  The observation read-back
+// (88 B per env for the 22-float wrappers) is what bounds this path; reward / truncated go back in one copy each at the end.
+static int step_host_pipeline_init(DsimHandle *h) {
+    if (h->host_pipeline_ready) return DSIM_OK;
+    for (int i = 0; i < 3; i++) CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
+    for (int i = 0; i < kHostChunks; i++) {
+        CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    h->host_pipeline_ready = 1;
+    return DSIM_OK;
+}
+
 extern "C" int dsim_step_host(DsimHandle *h, const float *actions_host, float *obs_host, float *reward_host, uint8_t *trunc_host, void *stream) {
     if (!h || !actions_host) return DSIM_EINVAL;
     if (h->cfg.precision != DSIM_FP32) return fail(h, DSIM_EUNSUPPORTED, "dsim_step_host moves float32 buffers; use dsim_step with precision=FP64%s", "");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMemcpyAsync(h->actions_stage, actions_host, (size_t)h->n * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = dsim_step(h, h->actions_stage, stream);
+    const int chunks = h->npages >= 2048 ? kHostChunks : 1;                 // >= 65536 envs: worth pipelining
+    if (chunks == 1) {
+        CK(cudaMemcpyAsync(h->actions_stage, actions_host, (size_t)h->n * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+        int rc = dsim_step(h, h->actions_stage, stream);
+        if (rc) return rc;
+        if (obs_host) CK(cudaMemcpyAsync(obs_host, h->obs, (size_t)h->n * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (reward_host) CK(cudaMemcpyAsync(reward_host, h->reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (trunc_host) CK(cudaMemcpyAsync(trunc_host, h->trunc, (size_t)h->n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return DSIM_OK;
+    }
+    int rc = step_host_pipeline_init(h);
     if (rc) return rc;
-    if (obs_host) CK(cudaMemcpyAsync(obs_host, h->obs, (size_t)h->n * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (reward_host) CK(cudaMemcpyAsync(reward_host, h->reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (trunc_host) CK(cudaMemcpyAsync(trunc_host, h->trunc, (size_t)h->n, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(h->ev_a, st));                                       // everything queued on the caller's stream comes first
+    for (int i = 0; i < 3; i++) CK(cudaStreamWaitEvent(h->hs[i], h->ev_a, 0));
+    const int per = (h->npages + chunks - 1) / chunks;
+    const size_t D = (size_t)h->obs_dim;
+    float *act_dev = (float *)h->actions_stage, *obs_dev = (float *)h->obs;
+    for (int k = 0; k < chunks; k++) {
+        const int p0 = k * per, p1 = (p0 + per < h->npages) ? p0 + per : h->npages;
+        if (p0 >= p1) break;
+        const size_t e0 = (size_t)p0 * kTile, e1 = (size_t)p1 * kTile < (size_t)h->n ? (size_t)p1 * kTile : (size_t)h->n, cnt = e1 - e0;
+        CK(cudaMemcpyAsync(act_dev + e0 * 4, actions_host + e0 * 4, cnt * 4 * sizeof(float), cudaMemcpyHostToDevice, h->hs[0]));
+        CK(cudaEventRecord(h->ev_in[k], h->hs[0]));
+        CK(cudaStreamWaitEvent(h->hs[1], h->ev_in[k], 0));
+        auto kp = make_params<float>(h, act_dev);
+        kp.page0 = p0; kp.npages = p1; kp.ticket = h->ticket + k;           // its own work-stealing counter
+        CK(launch_step<float>(h, kp, h->hs[1]));
+        h->launches++;
+        CK(cudaEventRecord(h->ev_k[k], h->hs[1]));
+        if (obs_host) {
+            CK(cudaStreamWaitEvent(h->hs[2], h->ev_k[k], 0));
+            CK(cudaMemcpyAsync(obs_host + e0 * D, obs_dev + e0 * D, cnt * D * sizeof(float), cudaMemcpyDeviceToHost, h->hs[2]));
+        }
+    }
+    for (int k = 0; k < chunks && k * per < h->npages; k++) CK(cudaStreamWaitEvent(h->hs[2], h->ev_k[k], 0));
+    if (reward_host) CK(cudaMemcpyAsync(reward_host, h->reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[2]));
+    if (trunc_host) CK(cudaMemcpyAsync(trunc_host, h->trunc, (size_t)h->n, cudaMemcpyDeviceToHost, h->hs[2]));
+    CK(cudaEventRecord(h->ev_b, h->hs[2]));
+    CK(cudaStreamWaitEvent(st, h->ev_b, 0));                                // later work on the caller's stream sees the stepped state
+    CK(cudaStreamSynchronize(h->hs[2]));
     return DSIM_OK;
 }
 

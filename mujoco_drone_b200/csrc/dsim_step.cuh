@@ -69,7 +69,8 @@ DSIM_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;"
 
 // ------------------------------------------------------------------ kernel parameter block (constant bank)
 template <typename T> struct KParams {
-    int n, npages;
+    int n, npages;            // npages: one past the last page of this launch
+    int page0;                // first page of this launch (0 unless the host entry point steps the batch in chunks)
     T *rw;                    // [npages][RW_ROWS][32]
     const T *ro;              // [npages][RO_ROWS][32]
     T *refp;                  // [npages][REF_ROWS][32] (per-env setpoints) or nullptr
@@ -298,7 +299,8 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     if (p.timeline) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (wid >= p.npages) return;
+    const int my_pages = p.npages - p.page0;                       // pages of THIS launch
+    if (wid >= my_pages) return;
     int tl_k = 1;
     auto stamp = [&]() {
         if (p.timeline && lane == 0 && tl_k < 8) {
@@ -315,20 +317,20 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     if (lane == 0) {
         #pragma unroll
         for (int k = 0; k < kStages; k++) mbar_init(&s_bar[warp][k], 1);
-        issue_page_loads(p, wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0]);
+        issue_page_loads(p, p.page0 + wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0]);
     }
     __syncwarp();                                                  // barrier init visible to the waiting lanes
     unsigned parity = 0;                                           // bit b: phase of this warp's barrier b
     int buf = 0;
-    const unsigned last_ticket = (unsigned)(max(p.npages - nwarps, 0) + min(nwarps, p.npages) - 1);
-    int page = wid;
+    const unsigned last_ticket = (unsigned)(max(my_pages - nwarps, 0) + min(nwarps, my_pages) - 1);
+    int page = p.page0 + wid;
     #pragma unroll 1
     while (page < p.npages) {
         int next = 0;
         if (lane == 0) {                                           // grab the page after this one (result first needed after the physics)
             const unsigned tk = atomicAdd(p.ticket, 1u);
             if (tk == last_ticket) *p.ticket = 0u;
-            next = nwarps + (int)tk;
+            next = p.page0 + nwarps + (int)tk;
         }
         const int i = page * kTile + lane;
         const bool active = i < p.n;                               // pad lanes of the last page compute, but publish nothing
