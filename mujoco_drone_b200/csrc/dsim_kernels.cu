@@ -173,6 +173,7 @@ struct DsimHandle {
     double uconst[C_ROWS], uparams[6];
     double h;
     int first_reset_done, step_grid, step_cap;
+    int ro_dirty;                      // a kernel that rewrote the read-only pages was queued since the last step
     cudaStream_t hs[3];                // host entry point: copy-in, compute, copy-out streams (created on first use)
     cudaEvent_t ev_in[kHostChunks], ev_k[kHostChunks], ev_a, ev_b;
     int host_pipeline_ready;
@@ -242,6 +243,7 @@ template <typename T> static KParams<T> make_params(const DsimHandle *h, const v
     p.rc.random_start_pos = c.random_start_pos;
     p.seed = c.seed; p.env_base = (unsigned)c.env_id_offset;
     p.timeline = h->timeline; p.ticket = h->ticket;
+    p.early_ro = h->ro_dirty ? 0 : 1;
     return p;
 }
 
@@ -361,6 +363,7 @@ extern "C" void dsim_destroy(DsimHandle *h) {
 }
 
 static int compile_on_device(DsimHandle *h, cudaStream_t st) {
+    h->ro_dirty = 1;
     const int grid = (h->n + 127) / 128;
     if (h->rs == 4) compile_kernel<float><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (float *)h->ro, h->cfg.pendulum, h->cfg.round_precision);
     else compile_kernel<double><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (double *)h->ro, h->cfg.pendulum, h->cfg.round_precision);
@@ -533,6 +536,7 @@ static int step_impl(DsimHandle *h, const void *actions_dev, void *stream, int e
         CK(launch_step<double>(h, kp, (cudaStream_t)stream));
     }
     h->launches++;
+    h->ro_dirty = 0;
     CK(cudaGetLastError());
     return DSIM_OK;
 }

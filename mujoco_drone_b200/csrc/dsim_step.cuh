@@ -82,6 +82,7 @@ template <typename T> struct KParams {
     T uparams[6];
     int per_env_consts, auto_reset, obs_id, reward_id, obs_dim, frame_skip, max_steps;
     int eval_only;            // 1: termination / reward / obs of the CURRENT state, nothing advanced or stored
+    int early_ro;             // 1: the read-only rows may be fetched before the dependency wait (no kernel that writes them is in flight)
     unsigned smem_per_slot;   // bytes of one page slot (each warp owns kStages of them)
     T h, max_distance_t;
     T ref_off[3], ref_yaw, start_t[3];
@@ -267,14 +268,21 @@ template <typename T> DSIM_DEV void load_action(const T *row, T a[4]) {
 }
 
 // lane 0: arm the slot's mbarrier and start the page loads HBM -> slot
-template <typename T> DSIM_DEV void issue_page_loads(const KParams<T> &p, int page, T *slot, uint64_t *bar) {
+// `parts`: bit 0 = arm the barrier with the page's total byte count and load the READ-ONLY rows (compiled constants + raw
+// parameters: never written by a step kernel), bit 1 = load everything an earlier kernel of the stream may have written
+// (state rows, the policy's actions, the setpoint rows).  3 = the whole page.
+template <typename T> DSIM_DEV void issue_page_loads(const KParams<T> &p, int page, T *slot, uint64_t *bar, int parts = 3) {
     constexpr uint32_t rwb = RW_ROWS * kTile * sizeof(T), rob = RO_ROWS * kTile * sizeof(T), rfb = REF_ROWS * kTile * sizeof(T);
     const uint32_t acb = (uint32_t)min(kTile, p.n - page * kTile) * 4u * (uint32_t)sizeof(T);   // the policy's [n][4] action rows of this page
-    mbar_arrive_expect_tx(bar, rwb + acb + (p.per_env_consts ? rob : 0u) + (p.refp ? rfb : 0u));
-    bulk_g2s(slot, p.rw + (size_t)page * (RW_ROWS * kTile), rwb, bar);
-    bulk_g2s(slot + kSlotActOff, p.actions + (size_t)page * (kTile * 4), acb, bar);
-    if (p.per_env_consts) bulk_g2s(slot + RW_ROWS * kTile, p.ro + (size_t)page * (RO_ROWS * kTile), rob, bar);
-    if (p.refp) bulk_g2s(slot + (RW_ROWS + RO_ROWS) * kTile, p.refp + (size_t)page * (REF_ROWS * kTile), rfb, bar);
+    if (parts & 1) {
+        mbar_arrive_expect_tx(bar, rwb + acb + (p.per_env_consts ? rob : 0u) + (p.refp ? rfb : 0u));
+        if (p.per_env_consts) bulk_g2s(slot + RW_ROWS * kTile, p.ro + (size_t)page * (RO_ROWS * kTile), rob, bar);
+    }
+    if (parts & 2) {
+        bulk_g2s(slot, p.rw + (size_t)page * (RW_ROWS * kTile), rwb, bar);
+        bulk_g2s(slot + kSlotActOff, p.actions + (size_t)page * (kTile * 4), acb, bar);
+        if (p.refp) bulk_g2s(slot + (RW_ROWS + RO_ROWS) * kTile, p.refp + (size_t)page * (REF_ROWS * kTile), rfb, bar);
+    }
 }
 
 // OBS / REW >= 0 are compile-time specialisations of the wrapper class / reward function (smaller code, no dispatch
@@ -293,14 +301,23 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wid = blockIdx.x * kStepWarps + warp, nwarps = gridDim.x * kStepWarps;
     // Programmatic dependent launch: the NEXT kernel of the stream may be scheduled onto SMs as soon as this grid's CTAs
-    // retire (its launch latency and this grid's tail overlap); this grid in turn touches no global memory before every
-    // kernel ahead of it in the stream has completed and flushed.
+    // retire (its launch latency and this grid's tail overlap).  Before the dependency wait a warp only sets up its barriers
+    // and starts the bulk load of its first page's READ-ONLY rows (no step kernel writes them; the host clears `early_ro`
+    // for the first step after a kernel that does - regen / set_params); everything an earlier kernel may have written is
+    // touched after griddepcontrol.wait.
     unsigned long long t_entry = 0;
     if (p.timeline) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int my_pages = p.npages - p.page0;                       // pages of THIS launch
-    if (wid >= my_pages) return;
+    const bool has_work = wid < my_pages;
+    unsigned char *wslots = smem_raw + (size_t)warp * kStages * p.smem_per_slot;
+    if (has_work && lane == 0) {
+        #pragma unroll
+        for (int k = 0; k < kStages; k++) mbar_init(&s_bar[warp][k], 1);
+        if (p.early_ro) issue_page_loads(p, p.page0 + wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0], 1);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!has_work) return;                                         // warps are autonomous: no CTA-wide barrier below
     int tl_k = 1;
     auto stamp = [&]() {
         if (p.timeline && lane == 0 && tl_k < 8) {
@@ -313,12 +330,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     stamp();                                                       // [1] dependency wait passed                                   // warps are autonomous: no CTA-wide barrier below
     const int obs_id = OBS >= 0 ? OBS : p.obs_id, reward_id = REW >= 0 ? REW : p.reward_id;
     const int D = DC > 0 ? DC : p.obs_dim;
-    unsigned char *wslots = smem_raw + (size_t)warp * kStages * p.smem_per_slot;
-    if (lane == 0) {
-        #pragma unroll
-        for (int k = 0; k < kStages; k++) mbar_init(&s_bar[warp][k], 1);
-        issue_page_loads(p, p.page0 + wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0]);
-    }
+    if (lane == 0) issue_page_loads(p, p.page0 + wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0], p.early_ro ? 2 : 3);
     __syncwarp();                                                  // barrier init visible to the waiting lanes
     unsigned parity = 0;                                           // bit b: phase of this warp's barrier b
     int buf = 0;
