@@ -245,7 +245,8 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
     n = wl["envs_per_gpu"]
     env = make_env(wl, n, rank * n, local_rank)
     pol = M.policy.make_rma_full()
-    runner = M.rollout.RolloutRunner(env, pol, horizon=1, seed=42 + rank, policy_dtype=args.policy_dtype, use_graph=True)
+    runner = M.rollout.RolloutRunner(env, pol, horizon=1, seed=42 + rank, policy_dtype=args.policy_dtype, use_graph=True,
+                                    fuse_sampling=args.fuse_sampling)
 
     def barrier():
         if world > 1:
@@ -303,7 +304,8 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
                    "l2": "inputs larger than L2 (env state + activations of 524288 envs)", "parallelism": f"env-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * (4 * env.obs_dim + 5),
                 "api": "dsim_step_host (C ABI), host-side policy boundary"},
-        "gpu_launches": 3 * args.steps,      # per step: rma_full_forward_kernel (or torch GEMMs), beta_policy_kernel, step_kernel (graph replays)
+        # per step: rma_full_forward_kernel (forward + sampling; or torch GEMMs / + beta_policy_kernel when not fused), step_kernel
+        "gpu_launches": (2 if (args.policy_dtype == "fused" and args.fuse_sampling) else 3) * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "step_kernel<float,true> timed alone at this size", "algorithmic_bytes_per_env_step": wl["alg_bytes"], "peak_source": peak_src,
                      "env_step_kernel_ms": k_ms, "share_of_loop": k_ms / (ms / args.steps)},
@@ -326,6 +328,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every timed step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads / hot-L2 measurements")
+    ap.add_argument("--fuse-sampling", action="store_true", help="c5, fused policy: sample inside the policy kernel (dsim_policy_forward_sample; measured slower at 524288 envs)")
     ap.add_argument("--policy-dtype", default="fused", choices=["fp32", "tf32", "bf16", "fused"],
                     help="c5 policy: fused = hand-written tcgen05 kernel (bf16 operands, FP32 accumulate); others = torch / cuBLAS")
     ap.add_argument("--preroll", type=int, default=1500, help="untimed steps per replica before the warm-up (reach the steady-state reset rate)")

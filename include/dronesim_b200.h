@@ -160,6 +160,12 @@ void dsim_policy_destroy(DsimPolicy *h);
 int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev,
                         const uint8_t *reset_mask_dev /* NULL, or [n]: != 0 -> the row's previous action is zero (new episode) */,
                         int n, float *logits_dev, float *value_dev, void *stream);
+/* dsim_policy_forward + dsim_beta_policy in ONE launch (RMA_model.py:79-116 followed by distributions.py:6-38): the action row
+ * is sampled in the kernel's logits epilogue with the same Philox streams as dsim_beta_policy, so the logits need not be
+ * written at all (logits_dev / logp_dev may be NULL).  actions_dev [n][4] may alias prev_action_dev. */
+int dsim_policy_forward_sample(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev, const uint8_t *reset_mask_dev, int n,
+                               uint32_t seed, uint32_t env_id_offset, uint32_t step, const uint32_t *step_dev, int deterministic,
+                               float *logits_dev, float *value_dev, float *actions_dev, float *logp_dev, void *stream);
 int dsim_policy_error(DsimPolicy *h);            /* 1: a launch hit a tensor-core barrier timeout (device sync) */
 
 /* -- instrumentation */

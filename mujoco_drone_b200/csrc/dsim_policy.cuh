@@ -41,21 +41,16 @@ template <typename T> DSIM_DEV bool mt_accept(T d, T c, T z, T u, T &out) {
     out = d * v;
     return true;
 }
+// One env's action row: x[2A] head outputs -> out[A] actions in (0, 1) and their summed log-probability.  Called by the
+// stand-alone sampling kernel below and from the logits epilogue of the fused policy kernel (dsim_policy_mlp.cu); every
+// lane of the calling warp must enter (the retry loop is warp-wide).
 template <typename T, int A>
-__global__ void __launch_bounds__(128) beta_policy_kernel(int n, const T *logits, uint32_t seed, uint32_t env_base, uint32_t step,
-                                                          const uint32_t *step_dev, int deterministic, T *actions, T *logp) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (step_dev) step += *step_dev;                     // device-resident step counter: CUDA-graph replays draw fresh numbers
-    T x[2 * A];
-    #pragma unroll
-    for (int k = 0; k < 2 * A; k++) x[k] = logits[(size_t)i * (2 * A) + k];
+DSIM_DEV void beta_row(const T (&x)[2 * A], uint32_t seed, uint32_t env, uint32_t step, int deterministic, T (&out)[A], T &lp) {
     // alpha_k = al[k], beta_k = al[A + k]  (torch.chunk(inputs, 2, dim=-1): alpha first, beta second); variate index 2k / 2k+1
     T al[2 * A], g[2 * A];
     #pragma unroll
     for (int k = 0; k < 2 * A; k++) { al[k] = softplus1(x[k]); g[k] = T(0); }
     if (!deterministic) {
-        const uint32_t env = env_base + (uint32_t)i;
         // first attempt of all 2A variates: one Philox block per action (Box-Muller pair -> two normals, two more words -> two uniforms)
         unsigned pend = 0;
         #pragma unroll
@@ -90,7 +85,7 @@ __global__ void __launch_bounds__(128) beta_policy_kernel(int n, const T *logits
             }
         }
     }
-    T lp = T(0), out[A];
+    lp = T(0);
     #pragma unroll
     for (int k = 0; k < A; k++) {
         const T a = al[k], b = al[A + k];
@@ -99,6 +94,18 @@ __global__ void __launch_bounds__(128) beta_policy_kernel(int n, const T *logits
         const T xc = clamp_(s, T(1e-2), T(1 - 1e-2));              // logp clamps (distributions.py:19-22)
         lp += lgamma_ge1(a + b) - lgamma_ge1(a) - lgamma_ge1(b) + (a - T(1)) * flog_(xc) + (b - T(1)) * flog_(T(1) - xc);
     }
+}
+
+template <typename T, int A>
+__global__ void __launch_bounds__(128) beta_policy_kernel(int n, const T *logits, uint32_t seed, uint32_t env_base, uint32_t step,
+                                                          const uint32_t *step_dev, int deterministic, T *actions, T *logp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (step_dev) step += *step_dev;                     // device-resident step counter: CUDA-graph replays draw fresh numbers
+    T x[2 * A], out[A], lp;
+    #pragma unroll
+    for (int k = 0; k < 2 * A; k++) x[k] = logits[(size_t)i * (2 * A) + k];
+    beta_row<T, A>(x, seed, env_base + (uint32_t)i, step, deterministic, out, lp);
     #pragma unroll
     for (int k = 0; k < A; k++) actions[(size_t)i * A + k] = out[k];
     if (logp) logp[i] = lp;

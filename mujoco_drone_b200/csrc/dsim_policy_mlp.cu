@@ -24,6 +24,7 @@
 #include <new>
 
 #include "../../include/dronesim_b200.h"
+#include "dsim_policy.cuh"
 
 namespace {
 
@@ -131,8 +132,13 @@ struct MlpParams {
     const float *obs;         // [n][22]
     const float *prev_action; // [n][4]
     const unsigned char *reset_mask;   // [n] or nullptr: rows with mask != 0 see a zero previous action (episode start)
-    float *logits;            // [n][8]
+    float *logits;            // [n][8] or nullptr (fused sampling only)
     float *value;             // [n]
+    float *actions;           // [n][4] or nullptr: Beta-head sample drawn in the logits epilogue (dsim_policy.cuh::beta_row)
+    float *logp;              // [n] or nullptr
+    const uint32_t *step_dev; // optional device step counter added to `step`
+    uint32_t seed, env_base, step;
+    int deterministic;
     int *error;               // set to 1 on a barrier timeout
     long long *dbg;           // debug: clock64 stamps [2 warpgroups][32] of CTA 0's first tile, or nullptr
     int n, ntiles;
@@ -209,6 +215,7 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
         nxt_a[0] = v.x; nxt_a[1] = v.y; nxt_a[2] = v.z; nxt_a[3] = v.w;
     };
     load_row(2 * blockIdx.x + wg);
+    const uint32_t step_now = p.step + (p.step_dev ? __ldg(p.step_dev) : 0u);
     constexpr int kTurnsPerTile = 6;                                       // epilogues that take a turn (the 16-column logits read does not)
     if (wg == 1) turn_pass(1);                                             // warpgroup 0 holds the first turn
     int dbg_k = 0;
@@ -327,10 +334,21 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
         {
             float v[16];
             tmem_ld16(tD, v);
-            if (live) {
+            float x[8];
+            #pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = live ? v[k] + s_c[C_B4 + k] : 0.0f;
+            if (live && p.logits) {
                 float4 *out = reinterpret_cast<float4 *>(p.logits + (size_t)row * 8);
-                out[0] = make_float4(v[0] + s_c[C_B4 + 0], v[1] + s_c[C_B4 + 1], v[2] + s_c[C_B4 + 2], v[3] + s_c[C_B4 + 3]);
-                out[1] = make_float4(v[4] + s_c[C_B4 + 4], v[5] + s_c[C_B4 + 5], v[6] + s_c[C_B4 + 6], v[7] + s_c[C_B4 + 7]);
+                out[0] = make_float4(x[0], x[1], x[2], x[3]);
+                out[1] = make_float4(x[4], x[5], x[6], x[7]);
+            }
+            if (p.actions) {     // warp-uniform; every lane enters (rows past n sample from zero logits and store nothing)
+                float act[4], lp;
+                dsim::beta_row<float, 4>(x, p.seed, p.env_base + (uint32_t)row, step_now, p.deterministic, act, lp);
+                if (live) {
+                    *reinterpret_cast<float4 *>(p.actions + (size_t)row * 4) = make_float4(act[0], act[1], act[2], act[3]);
+                    if (p.logp) p.logp[row] = lp;
+                }
             }
         }
         fence_before_sync();
@@ -450,18 +468,36 @@ extern "C" void dsim_policy_destroy(DsimPolicy *h) {
     delete h;
 }
 
-extern "C" int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev, const uint8_t *reset_mask_dev, int n,
-                                   float *logits_dev, float *value_dev, void *stream) {
-    if (!h || !obs_dev || !prev_action_dev || !logits_dev || !value_dev || n <= 0) return DSIM_EINVAL;
-    if (((uintptr_t)obs_dev & 7) || ((uintptr_t)prev_action_dev & 15) || ((uintptr_t)logits_dev & 15)) return DSIM_EINVAL;
+static int launch_policy(DsimPolicy *h, MlpParams &p, const float *obs_dev, const float *prev_action_dev, const uint8_t *reset_mask_dev, int n,
+                         void *stream) {
+    if (((uintptr_t)obs_dev & 7) || ((uintptr_t)prev_action_dev & 15) || ((uintptr_t)p.logits & 15) || ((uintptr_t)p.actions & 15)) return DSIM_EINVAL;
     if (cudaSetDevice(h->device) != cudaSuccess) return DSIM_ECUDA;
-    MlpParams p;
-    p.w = h->w; p.c = h->c; p.obs = obs_dev; p.prev_action = prev_action_dev; p.reset_mask = reset_mask_dev; p.logits = logits_dev; p.value = value_dev; p.error = h->error;
+    p.w = h->w; p.c = h->c; p.obs = obs_dev; p.prev_action = prev_action_dev; p.reset_mask = reset_mask_dev; p.error = h->error;
     p.n = n; p.ntiles = (n + 127) / 128; p.dbg = h->dbg;
     const int pairs = (p.ntiles + 1) / 2;
     const int grid = pairs < h->sms ? pairs : h->sms;
     rma_full_forward_kernel<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
+}
+
+extern "C" int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev, const uint8_t *reset_mask_dev, int n,
+                                   float *logits_dev, float *value_dev, void *stream) {
+    if (!h || !obs_dev || !prev_action_dev || !logits_dev || !value_dev || n <= 0) return DSIM_EINVAL;
+    MlpParams p{};
+    p.logits = logits_dev; p.value = value_dev;
+    return launch_policy(h, p, obs_dev, prev_action_dev, reset_mask_dev, n, stream);
+}
+
+// forward + Beta-head sampling in one launch: the logits never leave the SM unless `logits_dev` is given.  `actions_dev` may
+// alias `prev_action_dev` (each row is read by the thread that later writes it).  Same Philox streams as dsim_beta_policy.
+extern "C" int dsim_policy_forward_sample(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev, const uint8_t *reset_mask_dev, int n,
+                                          uint32_t seed, uint32_t env_id_offset, uint32_t step, const uint32_t *step_dev, int deterministic,
+                                          float *logits_dev, float *value_dev, float *actions_dev, float *logp_dev, void *stream) {
+    if (!h || !obs_dev || !prev_action_dev || !value_dev || !actions_dev || n <= 0) return DSIM_EINVAL;
+    MlpParams p{};
+    p.logits = logits_dev; p.value = value_dev; p.actions = actions_dev; p.logp = logp_dev;
+    p.seed = seed; p.env_base = env_id_offset; p.step = step; p.step_dev = step_dev; p.deterministic = deterministic;
+    return launch_policy(h, p, obs_dev, prev_action_dev, reset_mask_dev, n, stream);
 }
 
 extern "C" int dsim_policy_debug(DsimPolicy *h, long long *out64) {

@@ -172,6 +172,32 @@ class FusedRMAFull:
             raise _lib.DsimError(rc, "dsim_policy_forward failed")
         return logits, value
 
+    def sample(self, obs, prev_action, seed, env_id_offset=0, step=0, deterministic=False, actions_out=None, logp_out=None,
+               value_out=None, logits_out=None, reset_mask=None, step_tensor=None, want_logits=False):
+        """forward + Beta-head sampling in one launch -> (actions [n, 4], logp [n], value [n], logits [n, 8] | None).
+        `actions_out` may be the `prev_action` tensor itself (in-place update).  Draws the numbers `beta_policy` draws."""
+        torch = self._torch
+        n = obs.shape[0]
+        if obs.shape != (n, 22) or prev_action.shape != (n, 4) or obs.dtype != torch.float32 or prev_action.dtype != torch.float32:
+            raise ValueError("FusedRMAFull expects float32 obs [n, 22] and prev_action [n, 4]")
+        if not (obs.is_contiguous() and prev_action.is_contiguous()):
+            raise ValueError("FusedRMAFull.sample expects contiguous inputs")
+        mk = lambda shape: torch.empty(shape, dtype=torch.float32, device=obs.device)
+        act = actions_out if actions_out is not None else mk((n, 4))
+        lp = logp_out if logp_out is not None else mk((n,))
+        value = value_out if value_out is not None else mk((n,))
+        logits = logits_out if logits_out is not None else (mk((n, 8)) if want_logits else None)
+        if reset_mask is not None and (reset_mask.dtype != torch.uint8 or reset_mask.numel() != n or not reset_mask.is_contiguous()):
+            raise ValueError("reset_mask must be a contiguous uint8 tensor [n]")
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        rc = self._L.dsim_policy_forward_sample(self._h, ptr(obs), ptr(prev_action), ptr(reset_mask), n, int(seed) & 0xFFFFFFFF,
+                                                int(env_id_offset) & 0xFFFFFFFF, int(step) & 0xFFFFFFFF, ptr(step_tensor),
+                                                int(bool(deterministic)), ptr(logits), ptr(value), ptr(act), ptr(lp),
+                                                C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream))
+        if rc != _lib.OK:
+            raise _lib.DsimError(rc, "dsim_policy_forward_sample failed")
+        return act, lp, value, logits
+
     def check(self):
         """raise if any launch hit a tensor-core barrier timeout (device sync)"""
         if self._L.dsim_policy_error(self._h) != 0:

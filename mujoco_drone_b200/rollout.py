@@ -4,7 +4,8 @@
     runner = RolloutRunner(env, policy, horizon=32)
     batch = runner.run()            # dict of [T, N, ...] device tensors, GAE-ready
 
-Per step: RMA_full forward (library GEMMs) -> `dsim_beta_policy` (one kernel) -> `dsim_step` (one kernel), with the env's
+Per step: RMA_full forward (library GEMMs) -> `dsim_beta_policy` (one kernel) -> `dsim_step` (one kernel) — or, with
+policy_dtype="fused", ONE tcgen05 kernel for forward + sampling (`dsim_policy_forward_sample`) -> `dsim_step` — with the env's
 in-kernel auto-reset; `prev_actions` is zeroed where an episode just ended, like RLlib's view requirement at an episode
 start.  With `use_graph=True` one step is captured in a CUDA graph and replayed (the sampling kernel reads its step
 counter from device memory, the step kernel's work-stealing counter re-arms itself)."""
@@ -13,7 +14,7 @@ import numpy as np
 
 class RolloutRunner:
     def __init__(self, env, policy, horizon, seed=0, policy_dtype="fp32", use_graph=True, deterministic=False, history_len=0,
-                 history_states=16):
+                 history_states=16, fuse_sampling=False):
         import torch
         if not env.auto_reset:
             raise ValueError("RolloutRunner needs an env created with auto_reset=True (the native loop)")
@@ -25,6 +26,10 @@ class RolloutRunner:
         if dt != torch.float32:
             raise ValueError("RolloutRunner drives the FP32 product path")
         self.policy_dtype = policy_dtype
+        # "fused" policy only: draw the action inside the policy kernel (2 launches per step instead of 3, no logits round trip).
+        # Off by default: at 524288 envs the sampling code runs at the policy kernel's 8 warps/SM and costs more there
+        # (+47 us) than the separate 64-warps/SM sampling launch (34 us); measured 276.6 vs 264.5 us per step on a B200.
+        self.fuse_sampling = bool(fuse_sampling)
         T, N, D = self.T, self.N, self.D
         z = dict(device=self.dev)
         self.obs = torch.zeros((T + 1, N, D), dtype=dt, **z)
@@ -79,11 +84,15 @@ class RolloutRunner:
 
     def _one_step(self):
         from .policy import beta_policy
-        logits, value = self._forward()
-        if value.data_ptr() != self._val.data_ptr():
-            self._val.copy_(value)
-        beta_policy(logits, self.seed, self.env.env_id_offset, 0, self.deterministic, actions_out=self._act, logp_out=self._logp,
-                    step_tensor=self._step_ctr)
+        if self._fused is not None and self.fuse_sampling:   # forward + sampling in one launch; actions updated in place
+            self._fused.sample(self._obs_cur, self._act, self.seed, self.env.env_id_offset, 0, self.deterministic, actions_out=self._act,
+                               logp_out=self._logp, value_out=self._val, reset_mask=self._mask, step_tensor=self._step_ctr)
+        else:
+            logits, value = self._forward()
+            if value.data_ptr() != self._val.data_ptr():
+                self._val.copy_(value)
+            beta_policy(logits, self.seed, self.env.env_id_offset, 0, self.deterministic, actions_out=self._act, logp_out=self._logp,
+                        step_tensor=self._step_ctr)
         self._step_ctr.add_(1)
         obs, rew, trunc = self.env.step_tensor(self._act)
         self._obs_next, self._rew, self._trunc = obs, rew, trunc

@@ -189,7 +189,43 @@ def test_fused_tcgen05_policy_matches_torch_fp32():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
-def test_rollout_runner_with_fused_policy_kernel():
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_fused_policy_sampling_equals_separate_sampling_kernel(deterministic):
+    """dsim_policy_forward_sample == dsim_policy_forward followed by dsim_beta_policy on its logits: same Philox streams
+    (seed, global env id, step, device step counter), same device function -> same actions and log-probabilities; also
+    in place (actions written over the previous-action rows) and with the reset mask."""
+    import torch
+    import mujoco_drone_b200 as M
+    torch.manual_seed(3)
+    model = M.policy.make_rma_full().cuda()
+    with torch.no_grad():
+        model.logits[2].bias.copy_(torch.randn(8, device="cuda"))
+        model.logits[2].weight.mul_(4.0)
+    fused = M.policy.FusedRMAFull(model, device=0)
+    ctr = torch.full((1,), 5, dtype=torch.int32, device="cuda")
+    for n in (1, 200, 128 * 301 + 5):
+        obs = torch.randn((n, 22), device="cuda")
+        prev = torch.rand((n, 4), device="cuda")
+        mask = (torch.rand((n,), device="cuda") < 0.3).to(torch.uint8)
+        lg, val = fused(obs, prev, reset_mask=mask)
+        act_ref, lp_ref = M.policy.beta_policy(lg, seed=11, env_id_offset=1000, step=7, deterministic=deterministic, step_tensor=ctr)
+        act, lp, val2, lg2 = fused.sample(obs, prev, seed=11, env_id_offset=1000, step=7, deterministic=deterministic, reset_mask=mask,
+                                          step_tensor=ctr, want_logits=True)
+        fused.check()
+        assert torch.equal(lg, lg2) and torch.equal(val, val2)
+        assert (act - act_ref).abs().max().item() < 1e-6 and (lp - lp_ref).abs().max().item() < 1e-4
+        inplace = prev.clone()
+        act3, lp3, _, none = fused.sample(obs, inplace, seed=11, env_id_offset=1000, step=7, deterministic=deterministic, reset_mask=mask,
+                                          step_tensor=ctr, actions_out=inplace)
+        assert none is None and act3.data_ptr() == inplace.data_ptr()
+        assert torch.equal(act3, act) and torch.equal(lp3, lp)
+    fused.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+@pytest.mark.parametrize("fuse_sampling", [False, True])
+def test_rollout_runner_with_fused_policy_kernel(fuse_sampling):
     """config-5 loop with the hand-written tcgen05 policy kernel, CUDA-graph replayed: finite, in-range, and its logits
     agree with the torch FP32 module evaluated on the recorded observations / previous actions"""
     import torch
@@ -198,7 +234,7 @@ def test_rollout_runner_with_fused_policy_kernel():
     cfg = dict(M.base_config, num_drones=n, auto_reset=True, max_steps=64, param_difficulty=1.0, reward_fcn=M.rewards.distance_energy_reward)
     env = M.observation_wrappers.LocalFrameRPYParamsEnv(cfg)
     pol = M.policy.make_rma_full()
-    r = M.rollout.RolloutRunner(env, pol, horizon=T, seed=1, policy_dtype="fused", use_graph=True)
+    r = M.rollout.RolloutRunner(env, pol, horizon=T, seed=1, policy_dtype="fused", use_graph=True, fuse_sampling=fuse_sampling)
     b = r.run()
     r._fused.check()
     assert ((b["actions"] > 0) & (b["actions"] < 1)).all() and torch.isfinite(b["values"]).all() and torch.isfinite(b["action_logp"]).all()
