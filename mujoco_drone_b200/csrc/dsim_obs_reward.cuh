@@ -73,7 +73,7 @@ DSIM_DEV T reward_fn(int id, const EnvState<T> &s, const PostState<T> &p, const 
                 - T(0.7) * he * he - T(0.3) * a2 - T(0.3) * dot(s.vel, s.vel) - T(0.5) * pav2) / T(10);
     }
     T sx, cx, sy, cy;
-    sincos_(s.hx, &sx, &cx); sincos_(s.hy, &sy, &cy);
+    sincos_hinge(s.hx, &sx, &cx); sincos_hinge(s.hy, &sy, &cy);
     if (id >= 6 && id <= 9) {
         // rewards.py:81-103: tip velocity w = Rd( w_b x Rp e + (Rx Ox Ry + Rx Ry Oy) e ), e = (0,0,-L), Rp = Rx Ry
         const T Lp = prm[4];

@@ -298,7 +298,10 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[kStepWarps][kStages];
     constexpr int DC = (OBS >= 0 && PEND) ? obs_dim_of(OBS) : 0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp-uniform values (warp index, page numbers) go through redux.sync: the compiler then knows they are uniform, keeps
+    // the page / slot address arithmetic in the uniform datapath and hands the bulk-copy instructions uniform registers
+    // directly instead of wrapping each one in a register-broadcast loop (~15 instructions per copy, 7 copies per page)
+    const int lane = threadIdx.x & 31, warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
     const int wid = blockIdx.x * kStepWarps + warp, nwarps = gridDim.x * kStepWarps;
     // Programmatic dependent launch: the NEXT kernel of the stream may be scheduled onto SMs as soon as this grid's CTAs
     // retire (its launch latency and this grid's tail overlap).  Before the dependency wait a warp only sets up its barriers
@@ -334,16 +337,24 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     __syncwarp();                                                  // barrier init visible to the waiting lanes
     unsigned parity = 0;                                           // bit b: phase of this warp's barrier b
     int buf = 0;
-    const unsigned last_ticket = (unsigned)(max(my_pages - nwarps, 0) + min(nwarps, my_pages) - 1);
+    // Work stealing: a warp draws one ticket at entry and one per processed page (W + my_pages draws per launch; the holder
+    // of the last one re-zeroes the counter: launches and graph replays need no host reset).  A ticket is drawn half an
+    // iteration before it is claimed (raw atom: the compiler's warp-aggregated atomicAdd consumes its result at once), so the
+    // ~700-cycle round trip to L2 hides behind the post-processing instead of stalling the warp at the top of the loop.
+    const unsigned last_ticket = (unsigned)(min(nwarps, my_pages) + my_pages - 1);
+    auto draw = [&]() {
+        unsigned tk = 0;
+        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(tk) : "l"(p.ticket));
+        return tk;
+    };
+    auto claim = [&](unsigned tk) {                                // tk: lane 0's draw
+        if (lane == 0 && tk == last_ticket) *p.ticket = 0u;
+        return __reduce_max_sync(0xffffffffu, lane == 0 ? p.page0 + nwarps + (int)tk : 0);
+    };
     int page = p.page0 + wid;
+    int next = claim(draw());                                      // latency overlaps the first page's load
     #pragma unroll 1
     while (page < p.npages) {
-        int next = 0;
-        if (lane == 0) {                                           // grab the page after this one (result first needed after the physics)
-            const unsigned tk = atomicAdd(p.ticket, 1u);
-            if (tk == last_ticket) *p.ticket = 0u;
-            next = p.page0 + nwarps + (int)tk;
-        }
         const int i = page * kTile + lane;
         const bool active = i < p.n;                               // pad lanes of the last page compute, but publish nothing
         T *slot = reinterpret_cast<T *>(wslots + (size_t)buf * p.smem_per_slot);
@@ -373,6 +384,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             #pragma unroll 1
             for (int f = 0; f < p.frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
         }
+        const unsigned drawn = draw();                             // for the page after `next`; claimed at the end of the iteration
         // ---- counters, termination, reward, observation
         int ns = slot_to_int(col[RW_NUM_STEPS * kTile]) + (p.eval_only ? 0 : 1);
         // MuJoCo's mj_checkPos/Vel/Acc warn and reset the whole MjData; here the one env is parked on a finite state for
@@ -449,7 +461,8 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         stamp();                                                   // [3], [5]: page published
         if (!obs_bulk)                                             // ragged last page whose byte count is not a multiple of 16
             for (int e = lane; e < nvalid * D; e += kTile) gobs[e] = s_obs[e];
-        page = __shfl_sync(0xffffffffu, next, 0);
+        page = next;
+        next = claim(drawn);
         buf ^= 1;
     }
     if (lane == 0) bulk_wait_read();                               // the slots must outlive the bulk reads
