@@ -518,7 +518,7 @@ def main():
                    "replicas": R,
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * (4 * env.obs_dim + 4 + 1),
-                "steps": e2e_steps, "api": "dsim_step_host (C ABI) with pinned host buffers"},
+                "steps": e2e_steps, "api": "dsim_step_host (C ABI) with pinned host buffers: one launch, the kernel's bulk loads / stores move actions and outputs over PCIe (zero-copy)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": wl.get("traffic"),
                      "traffic_source": wl.get("traffic_src"), "kernel": "step_kernel<float,true>", "algorithmic_bytes_per_launch": wl["alg_bytes"] * n,

@@ -117,7 +117,9 @@ int dsim_step(DsimHandle *h, const void *actions_dev /* real [N][4] */, void *st
 /* termination / reward / observation of the CURRENT state for the given raw actions; nothing is advanced, counted or
  * stored (what `terminated_fcn`, `reward_fcn`, `_get_obs` return when called on `self.states`, :275-284) */
 int dsim_evaluate(DsimHandle *h, const void *actions_dev /* real [N][4] */, void *stream);
-/* same with HOST buffers (pinned or pageable), copies inside: the end-to-end path */
+/* same with HOST buffers: the end-to-end path; returns after the outputs are in the host buffers.  Pinned buffers (all of
+ * them; actions / obs 16-byte aligned): ONE launch whose bulk loads / stores move actions and obs / reward / truncated over
+ * PCIe themselves (zero-copy).  Pageable buffers: staged H2D | kernel | D2H copies, pipelined over page ranges for N >= 65536. */
 int dsim_step_host(DsimHandle *h, const float *actions_host /*[N][4]*/, float *obs_host /*[N][obs_dim]*/,
                    float *reward_host /*[N]*/, uint8_t *truncated_host /*[N]*/, void *stream);
 

@@ -175,7 +175,7 @@ struct DsimHandle {
     int first_reset_done, step_grid, step_cap;
     int ro_dirty;                      // a kernel that rewrote the read-only pages was queued since the last step
     cudaStream_t hs[3];                // host entry point: copy-in, compute, copy-out streams (created on first use)
-    cudaEvent_t ev_in[kHostChunks], ev_k[kHostChunks], ev_a, ev_b;
+    cudaEvent_t ev_in[kHostChunks], ev_k[kHostChunks], ev_a, ev_b, ev_c;
     int host_pipeline_ready;
     int64_t launches;
     char err[512];
@@ -354,7 +354,7 @@ extern "C" void dsim_destroy(DsimHandle *h) {
     if (h->host_pipeline_ready) {
         for (int i = 0; i < 3; i++) cudaStreamDestroy(h->hs[i]);
         for (int i = 0; i < kHostChunks; i++) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
-        cudaEventDestroy(h->ev_a); cudaEventDestroy(h->ev_b);
+        cudaEventDestroy(h->ev_a); cudaEventDestroy(h->ev_b); cudaEventDestroy(h->ev_c);
     }
     void *ptrs[] = {h->rw, h->ro, h->refp, h->obs, h->reward, h->states33, h->actions_stage,
                     h->params64, h->stats, h->center_hw, h->trunc, h->timeline, h->ticket};
@@ -553,9 +553,10 @@ extern "C" int dsim_evaluate(DsimHandle *h, const void *actions_dev, void *strea
     return step_impl(h, actions_dev, stream, 1);
 }
 
-// vector_step with HOST buffers.  Large batches are stepped in kHostChunks page ranges on three internal streams so that
-// the PCIe legs overlap the kernel: H2D actions(k+1) | step kernel(k) | D2H observations(k-1).  The observation read-back
-// (88 B per env for the 22-float wrappers) is what bounds this path; reward / truncated go back in one copy each at the end.
+// vector_step with HOST buffers.  Pinned buffers take the zero-copy path in dsim_step_host.  Otherwise large batches are
+// stepped in page ranges on three internal streams so that the PCIe legs overlap the kernel: H2D actions(k+1) | step
+// kernel(k) | D2H observations(k-1).  Either way the observation read-back (88 B per env for the 22-float wrappers) is what
+// bounds this path.
 static int step_host_pipeline_init(DsimHandle *h) {
     if (h->host_pipeline_ready) return DSIM_OK;
     for (int i = 0; i < 3; i++) CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
@@ -565,7 +566,53 @@ static int step_host_pipeline_init(DsimHandle *h) {
     }
     CK(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_c, cudaEventDisableTiming));
     h->host_pipeline_ready = 1;
+    return DSIM_OK;
+}
+
+// page ranges of the host pipeline: two small leading chunks so the read-back starts early, then doubling sizes so that
+// few copy boundaries remain (1/16, 1/16, 1/8, 1/4, 1/2 of the pages).  Returns the chunk count; bounds[k] .. bounds[k+1].
+static int host_chunk_bounds(int npages, int *bounds) {
+    static const int sixteenths[] = {0, 1, 2, 4, 8, 16};
+    int nb = 0, last = -1;
+    for (int k = 0; k < 6; k++) {
+        const int b = (int)((long long)npages * sixteenths[k] / 16);
+        if (b == last) continue;
+        if (bounds) bounds[nb] = b;
+        nb++; last = b;
+    }
+    return nb - 1;
+}
+
+// fork from `root` onto the copy-in / copy-out streams, queue every chunk, join back into `root` (also valid under capture)
+static int enqueue_host_pipeline(DsimHandle *h, const KParams<float> &base, const float *actions_host, float *obs_host, float *reward_host,
+                                 uint8_t *trunc_host, cudaStream_t root) {
+    int bounds[kHostChunks + 1];
+    const int chunks = host_chunk_bounds(h->npages, bounds);
+    cudaStream_t s_in = h->hs[0], s_out = h->hs[2];
+    CK(cudaEventRecord(h->ev_c, root));
+    CK(cudaStreamWaitEvent(s_in, h->ev_c, 0));
+    CK(cudaStreamWaitEvent(s_out, h->ev_c, 0));
+    const size_t D = (size_t)h->obs_dim;
+    float *act_dev = (float *)h->actions_stage, *obs_dev = (float *)h->obs;
+    for (int k = 0; k < chunks; k++) {
+        const int p0 = bounds[k], p1 = bounds[k + 1];
+        const size_t e0 = (size_t)p0 * kTile, e1 = (size_t)p1 * kTile < (size_t)h->n ? (size_t)p1 * kTile : (size_t)h->n, cnt = e1 - e0;
+        CK(cudaMemcpyAsync(act_dev + e0 * 4, actions_host + e0 * 4, cnt * 4 * sizeof(float), cudaMemcpyHostToDevice, s_in));
+        CK(cudaEventRecord(h->ev_in[k], s_in));
+        CK(cudaStreamWaitEvent(root, h->ev_in[k], 0));
+        KParams<float> kp = base;
+        kp.page0 = p0; kp.npages = p1; kp.ticket = h->ticket + k;           // its own work-stealing counter
+        CK(launch_step<float>(h, kp, root));
+        CK(cudaEventRecord(h->ev_k[k], root));
+        CK(cudaStreamWaitEvent(s_out, h->ev_k[k], 0));
+        if (obs_host) CK(cudaMemcpyAsync(obs_host + e0 * D, obs_dev + e0 * D, cnt * D * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    }
+    if (reward_host) CK(cudaMemcpyAsync(reward_host, h->reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    if (trunc_host) CK(cudaMemcpyAsync(trunc_host, h->trunc, (size_t)h->n, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaEventRecord(h->ev_b, s_out));
+    CK(cudaStreamWaitEvent(root, h->ev_b, 0));                              // s_in joined through the per-chunk events already
     return DSIM_OK;
 }
 
@@ -574,6 +621,33 @@ extern "C" int dsim_step_host(DsimHandle *h, const float *actions_host, float *o
     if (h->cfg.precision != DSIM_FP32) return fail(h, DSIM_EUNSUPPORTED, "dsim_step_host moves float32 buffers; use dsim_step with precision=FP64%s", "");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    // Zero-copy path: every buffer the caller passed is pinned (cudaHostAlloc / cudaHostRegister / torch pin_memory), i.e.
+    // mapped into the device address space.  ONE launch on the caller's stream: the kernel's bulk loads fetch the action rows
+    // over PCIe and its bulk stores write observations / reward / truncated to the host buffers as posted PCIe writes, page
+    // by page while later pages are still being computed - no copy-engine pass, no chunk boundaries, no staging.  The
+    // device-resident outputs are written as well (dsim_buffer views stay current).
+    {
+        auto mapped = [](const void *q, size_t align, void **dp) {
+            *dp = nullptr;
+            if (!q) return true;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, q) != cudaSuccess) { cudaGetLastError(); return false; }
+            if (at.type != cudaMemoryTypeHost || !at.devicePointer || ((uintptr_t)at.devicePointer & (align - 1))) return false;
+            *dp = at.devicePointer;
+            return true;
+        };
+        void *d_act, *d_obs, *d_rew, *d_tr;
+        if (mapped(actions_host, 16, &d_act) && mapped(obs_host, 16, &d_obs) && mapped(reward_host, 4, &d_rew) && mapped(trunc_host, 1, &d_tr)) {
+            KParams<float> kp = make_params<float>(h, d_act);
+            kp.obs_host = (float *)d_obs; kp.reward_host = (float *)d_rew; kp.trunc_host = (unsigned char *)d_tr;
+            CK(launch_step<float>(h, kp, st));
+            h->launches++;
+            h->ro_dirty = 0;
+            CK(cudaStreamSynchronize(st));
+            return DSIM_OK;
+        }
+    }
+    // Pageable host memory: staged copies.
     const int chunks = h->npages >= 2048 ? kHostChunks : 1;                 // >= 65536 envs: worth pipelining
     if (chunks == 1) {
         CK(cudaMemcpyAsync(h->actions_stage, actions_host, (size_t)h->n * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -587,34 +661,15 @@ extern "C" int dsim_step_host(DsimHandle *h, const float *actions_host, float *o
     }
     int rc = step_host_pipeline_init(h);
     if (rc) return rc;
-    CK(cudaEventRecord(h->ev_a, st));                                       // everything queued on the caller's stream comes first
-    for (int i = 0; i < 3; i++) CK(cudaStreamWaitEvent(h->hs[i], h->ev_a, 0));
-    const int per = (h->npages + chunks - 1) / chunks;
-    const size_t D = (size_t)h->obs_dim;
-    float *act_dev = (float *)h->actions_stage, *obs_dev = (float *)h->obs;
-    for (int k = 0; k < chunks; k++) {
-        const int p0 = k * per, p1 = (p0 + per < h->npages) ? p0 + per : h->npages;
-        if (p0 >= p1) break;
-        const size_t e0 = (size_t)p0 * kTile, e1 = (size_t)p1 * kTile < (size_t)h->n ? (size_t)p1 * kTile : (size_t)h->n, cnt = e1 - e0;
-        CK(cudaMemcpyAsync(act_dev + e0 * 4, actions_host + e0 * 4, cnt * 4 * sizeof(float), cudaMemcpyHostToDevice, h->hs[0]));
-        CK(cudaEventRecord(h->ev_in[k], h->hs[0]));
-        CK(cudaStreamWaitEvent(h->hs[1], h->ev_in[k], 0));
-        auto kp = make_params<float>(h, act_dev);
-        kp.page0 = p0; kp.npages = p1; kp.ticket = h->ticket + k;           // its own work-stealing counter
-        CK(launch_step<float>(h, kp, h->hs[1]));
-        h->launches++;
-        CK(cudaEventRecord(h->ev_k[k], h->hs[1]));
-        if (obs_host) {
-            CK(cudaStreamWaitEvent(h->hs[2], h->ev_k[k], 0));
-            CK(cudaMemcpyAsync(obs_host + e0 * D, obs_dev + e0 * D, cnt * D * sizeof(float), cudaMemcpyDeviceToHost, h->hs[2]));
-        }
-    }
-    for (int k = 0; k < chunks && k * per < h->npages; k++) CK(cudaStreamWaitEvent(h->hs[2], h->ev_k[k], 0));
-    if (reward_host) CK(cudaMemcpyAsync(reward_host, h->reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, h->hs[2]));
-    if (trunc_host) CK(cudaMemcpyAsync(trunc_host, h->trunc, (size_t)h->n, cudaMemcpyDeviceToHost, h->hs[2]));
-    CK(cudaEventRecord(h->ev_b, h->hs[2]));
-    CK(cudaStreamWaitEvent(st, h->ev_b, 0));                                // later work on the caller's stream sees the stepped state
-    CK(cudaStreamSynchronize(h->hs[2]));
+    KParams<float> kp = make_params<float>(h, h->actions_stage);
+    CK(cudaEventRecord(h->ev_a, st));
+    CK(cudaStreamWaitEvent(h->hs[1], h->ev_a, 0));
+    rc = enqueue_host_pipeline(h, kp, actions_host, obs_host, reward_host, trunc_host, h->hs[1]);
+    if (rc) return rc;
+    h->launches += host_chunk_bounds(h->npages, nullptr);
+    CK(cudaEventRecord(h->ev_b, h->hs[1]));
+    CK(cudaStreamWaitEvent(st, h->ev_b, 0));
+    CK(cudaStreamSynchronize(h->hs[1]));
     return DSIM_OK;
 }
 

@@ -91,6 +91,10 @@ template <typename T> struct KParams {
     unsigned seed, env_base;
     unsigned *ticket;               // work-stealing page counter (0 between launches)
     unsigned long long *timeline;   // debug: [gridDim * warps][8] %globaltimer stamps of the last launch, or nullptr
+    // host entry point with pinned buffers: the mapped host copies of the outputs, written by the kernel itself next to the
+    // device-resident ones (posted PCIe writes from the same bulk stores; no copy-engine pass), or nullptr
+    T *obs_host, *reward_host;
+    unsigned char *trunc_host;
 };
 
 // integer rows of the read-write page are stored in a lane-sized slot (int32 for float pages, int64 for double)
@@ -427,6 +431,8 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         if (active) {
             p.reward[i] = rew;
             p.trunc[i] = trunc ? 1 : 0;
+            if (p.reward_host) p.reward_host[i] = rew;
+            if (p.trunc_host) p.trunc_host[i] = trunc ? 1 : 0;
         }
 
         if (!p.eval_only) {
@@ -456,11 +462,15 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         if (lane == 0) {
             if (!p.eval_only) bulk_s2g(p.rw + (size_t)page * (RW_ROWS * kTile), s_rw, RW_ROWS * kTile * sizeof(T));
             if (obs_bulk) bulk_s2g(gobs, s_obs, obs_bytes);
+            if (obs_bulk && p.obs_host) bulk_s2g(p.obs_host + (size_t)page * kTile * D, s_obs, obs_bytes);
             bulk_commit();
         }
         stamp();                                                   // [3], [5]: page published
         if (!obs_bulk)                                             // ragged last page whose byte count is not a multiple of 16
-            for (int e = lane; e < nvalid * D; e += kTile) gobs[e] = s_obs[e];
+            for (int e = lane; e < nvalid * D; e += kTile) {
+                gobs[e] = s_obs[e];
+                if (p.obs_host) p.obs_host[(size_t)page * kTile * D + e] = s_obs[e];
+            }
         page = next;
         next = claim(drawn);
         buf ^= 1;

@@ -291,15 +291,16 @@ class BaseDroneEnv(_VectorEnv):
         self._states_cache = None
 
     def step_host(self, actions, obs_out=None, reward_out=None, trunc_out=None):
-        """End-to-end path with HOST float32 arrays: H2D actions, one kernel, D2H obs/reward/truncated."""
+        """End-to-end path with HOST float32 arrays.  Pinned arrays (e.g. views of torch `pin_memory()` tensors): one kernel
+        that reads the actions and writes obs / reward / truncated over PCIe itself; pageable arrays: staged copies."""
         a = np.ascontiguousarray(actions, dtype=np.float32)
         if a.shape != (self.num_drones, 4):
             raise ValueError("Action dimension mismatch")
         obs_out = np.empty((self.num_drones, self.obs_dim), np.float32) if obs_out is None else obs_out
         reward_out = np.empty(self.num_drones, np.float32) if reward_out is None else reward_out
         trunc_out = np.empty(self.num_drones, np.uint8) if trunc_out is None else trunc_out
-        self._ck(self._L.dsim_step_host(self._h, a.ctypes.data, obs_out.ctypes.data, reward_out.ctypes.data,
-                                        trunc_out.ctypes.data, self._stream()))
+        ptr = lambda x: x.__array_interface__['data'][0]                     # (ndarray.ctypes builds a helper object per access)
+        self._ck(self._L.dsim_step_host(self._h, ptr(a), ptr(obs_out), ptr(reward_out), ptr(trunc_out), self._stream()))
         self.total_steps += 1
         self._states_cache = None
         return obs_out, reward_out, trunc_out

@@ -449,3 +449,36 @@ def test_host_entry_point_pipeline_equals_device_path():
     assert all(np.array_equal(x, y) for x, y in zip(s1, s2))
     assert e1.episode_stats()["n_episodes"] == e2.episode_stats()["n_episodes"] > 0
     e1.close(); e2.close()
+
+
+@pytest.mark.parametrize("n", [33, 65536 + 2048 + 31])
+def test_host_entry_point_zero_copy_with_pinned_buffers(n):
+    """pinned host buffers: one launch whose bulk loads / stores move actions and outputs over PCIe themselves; same results
+    bit-for-bit as the device path (ragged last page included), device-resident outputs still written, across a change of
+    buffers and of the setpoint"""
+    import torch
+    import mujoco_drone_b200 as M
+    kw = dict(num_drones=n, param_difficulty=1.0, state_difficulty=0.3, max_steps=5, max_distance=1.5, auto_reset=True,
+              reward_fcn=M.rewards.distance_energy_reward)
+    e1, e2 = _mk("LocalFrameRPYParamsEnv", **kw), _mk("LocalFrameRPYParamsEnv", **kw)
+    e1.reset_tensor(); e2.reset_tensor()
+    g = torch.Generator().manual_seed(1)
+    bufs = [(torch.empty((n, 4)).pin_memory(), torch.empty((n, e2.obs_dim)).pin_memory(), torch.empty((n,)).pin_memory(),
+             torch.empty((n,), dtype=torch.uint8).pin_memory()) for _ in range(2)]
+    l0 = e2.launch_count()
+    for t in range(12):
+        ha, ho, hr, ht = bufs[0] if t < 8 else bufs[1]
+        if t == 5:
+            e1.reference = [0.2, -0.1, 15.3, 0.4]; e2.reference = [0.2, -0.1, 15.3, 0.4]
+        ha.copy_(torch.rand((n, 4), generator=g))
+        o1, r1, t1 = e1.step_tensor(ha.cuda())
+        ho.fill_(-7.0)
+        e2.step_host(ha.numpy(), ho.numpy(), hr.numpy(), ht.numpy())
+        assert np.array_equal(o1.cpu().numpy(), ho.numpy()) and np.array_equal(r1.cpu().numpy(), hr.numpy()) and np.array_equal(t1.cpu().numpy(), ht.numpy()), t
+        assert torch.equal(e2.obs_tensor, o1) and torch.equal(e2.reward_tensor, r1) and torch.equal(e2.truncated_tensor, t1)
+    assert e2.launch_count() - l0 == 12                        # one kernel per step, no copies
+    s1, s2 = e1.get_state(), e2.get_state()
+    assert all(np.array_equal(x, y) for x, y in zip(s1, s2))
+    assert e1.episode_stats()["n_episodes"] == e2.episode_stats()["n_episodes"] > 0
+    e1.close(); e2.close()
+
