@@ -42,7 +42,7 @@ constexpr int C_B1 = 0, C_B2 = 256, C_B3 = 384, C_B4 = 640, C_C2 = 656, C_V3 = 7
               C_E2 = C_E1B + ENC_H, C_E2B = C_E2 + E_DIM * ENC_H, C_ELEMS = 1408;
 static_assert(C_E2B + E_DIM <= C_ELEMS, "constants blob too small");
 constexpr int X0_BYTES = 128 * K1 * 2;                   // per-warpgroup first-layer operand tile (canonical layout), 8 KB
-constexpr int SMEM_BYTES = W_ELEMS * 2 + C_ELEMS * 4 + 2 * X0_BYTES + 64;
+constexpr int SMEM_BYTES = W_ELEMS * 2 + C_ELEMS * 4 + 2 * X0_BYTES + 64 + 128;   // + b4 padded to 32 columns
 
 #define DEV __device__ __forceinline__
 DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,6 +108,23 @@ DEV void tmem_ld32(uint32_t taddr, float v[32]) {
     #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
 }
+// software-pipelined form: issue the load of the next 32 columns, compute on the current ones, wait only then.  The wait
+// "touches" the destination registers so that the compiler cannot schedule their consumers above it.
+DEV void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                 "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                   "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                   "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+DEV void tmem_ld32_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                      "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+    asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]),
+                      "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
+}
 DEV void tmem_ld16(uint32_t taddr, float v[16]) {
     uint32_t r[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -123,6 +140,25 @@ DEV void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
                    "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+DEV void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+                 "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+                   "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+                   "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+// The NEXT layer's bias goes into the accumulator columns as soon as this layer's values have left them (every MMA
+// accumulates): one tcgen05.st per 32 columns replaces 32 FADDs in the next epilogue, whose single warp per scheduler is
+// bound by its own issue rate.
+DEV void bias_to_tmem32(uint32_t taddr, const float *bias) {
+    uint32_t r[32];
+    #pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4 *>(bias + j);
+        r[j] = __float_as_uint(b.x); r[j + 1] = __float_as_uint(b.y); r[j + 2] = __float_as_uint(b.z); r[j + 3] = __float_as_uint(b.w);
+    }
+    tmem_st32(taddr, r);
 }
 DEV void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -151,15 +187,57 @@ DEV uint32_t tanh_pack(float lo, float hi) {
     asm("tanh.approx.bf16x2 %0, %0;" : "+r"(r));
     return r;
 }
-// epilogue: D[0..127] -> tanh(. + bias) -> bf16 -> A region at column `dst_col` (64 columns)
-DEV void epilogue_to_tmem(uint32_t tD, uint32_t tAdst, const float *bias) {
-    #pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {
-        float v[32];
-        tmem_ld32(tD + c, v);
+// The same activation on the FMA pipe, for a share of the columns: the SFU delivers 16 tanh/clk/SM and is the epilogue's
+// bound, while the FP32 pipe idles.  tanh(x) ~ x P(x^2) on |x| <= 3.5 (clamped beyond: 1 - tanh(3.5) = 1.8e-3), degree-13
+// odd polynomial fitted for minimax RELATIVE error (3.1e-3, the size of the bf16 rounding that follows), evaluated for two
+// columns at once with packed fma.rn.f32x2: 14 issue slots per column pair instead of 16 SFU cycles.
+#ifndef MLP_POLY
+#define MLP_POLY 3           // of every 8 column pairs, this many go to the FMA pipe
+#endif
+DEV uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+DEV void unpk2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+DEV uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+DEV uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+DEV void tanh_poly2(float &lo, float &hi) {
+    constexpr float R = 3.5f;
+    lo = fminf(fmaxf(lo, -R), R); hi = fminf(fmaxf(hi, -R), R);
+    const uint64_t x = pk2(lo, hi), s = mul2(x, x);
+    #define K2(c) pk2(c, c)
+    uint64_t q = fma2(s, K2(2.013471598e-06f), K2(-8.968956237e-05f));
+    q = fma2(q, s, K2(1.616502277e-03f)); q = fma2(q, s, K2(-1.532690791e-02f)); q = fma2(q, s, K2(8.490159052e-02f));
+    q = fma2(q, s, K2(-3.053695960e-01f)); q = fma2(q, s, K2(9.969368461e-01f));
+    #undef K2
+    unpk2(mul2(q, x), lo, hi);
+}
+DEV uint32_t tanh_poly_pack(float lo, float hi) { tanh_poly2(lo, hi); return pack_bf16(lo, hi); }
+// epilogue: D[0..127] (bias already inside) -> tanh -> bf16 -> A region at column `dst_col` (64 columns); the first
+// `next_cols` accumulator columns are re-armed with the next layer's bias.  The first accumulator load is issued BEFORE the
+// warpgroup waits for its turn (the turn rations the SFU, not tensor memory), and the load of columns c+32.. is in flight
+// while columns c.. are computed.  One copy (noinline): four unrolled 32-column stages, five call sites.
+__device__ __noinline__ void epilogue_to_tmem(uint32_t tD, uint32_t tAdst, const float *next_bias, int next_cols, int wg) {
+    uint32_t ra[32], rb[32];
+    tmem_ld32_issue(tD, ra);
+    turn_wait(wg);
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t (&cur)[32] = (k & 1) ? rb : ra;
+        uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
+        tmem_ld32_wait(cur);
+        if (k < 3) { tmem_ld32_issue(tD + 32 * (k + 1), nxt); __syncwarp(); }   // (the barrier keeps ptxas from sinking the load below the math)
+        const int c = 32 * k;
+        if (c < next_cols) bias_to_tmem32(tD + c, next_bias + c);
         uint32_t pk[16];
         #pragma unroll
-        for (int j = 0; j < 16; j++) pk[j] = tanh_pack(v[2 * j] + bias[c + 2 * j], v[2 * j + 1] + bias[c + 2 * j + 1]);
+        for (int j = 0; j < 16; j++) {
+            const float lo = __uint_as_float(cur[2 * j]), hi = __uint_as_float(cur[2 * j + 1]);
+#if defined(MLP_DBG_NOPACK)
+            pk[j] = __float_as_uint(lo) ^ __float_as_uint(hi);
+#elif defined(MLP_DBG_NOTANH)
+            pk[j] = pack_bf16(lo, hi);
+#else
+            pk[j] = (j & 7) < MLP_POLY ? tanh_poly_pack(lo, hi) : tanh_pack(lo, hi);
+#endif
+        }
         tmem_st16(tAdst + c / 2, pk);
     }
     tmem_st_wait();
@@ -172,6 +250,7 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
     unsigned char *s_x0 = smem + W_ELEMS * 2 + C_ELEMS * 4;                  // [2 warpgroups][8 KB]
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_x0 + 2 * X0_BYTES);      // [2]
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
+    float *s_b4 = reinterpret_cast<float *>(s_tmem + 12);                      // b4 (16 logits columns, 8 real) padded to 32
     const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, wq = (tid >> 5) & 3;
 
     // ---- one-time setup: weights + constants -> shared memory, TMEM allocation, barriers
@@ -180,6 +259,7 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
         uint4 *sw = reinterpret_cast<uint4 *>(s_w);
         for (int i = tid; i < W_ELEMS * 2 / 16; i += 256) sw[i] = __ldg(gw + i);
         for (int i = tid; i < C_ELEMS; i += 256) s_c[i] = __ldg(p.c + i);
+        if (tid < 32) s_b4[tid] = tid < 16 ? __ldg(p.c + C_B4 + tid) : 0.0f;
     }
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (tid < 32) {                                                          // warp 0 allocates all 512 columns
@@ -199,6 +279,9 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
     uint64_t *bar = &s_bar[wg];
     uint32_t parity = 0;
     bool ok = true;
+    #pragma unroll 1
+    for (int c = 0; c < 128; c += 32) bias_to_tmem32(tD + c, s_c + C_B1 + c);   // first layer's bias for the first tile
+    tmem_st_wait();
 
     // input rows are software-pipelined: nxt_* hold the obs / previous action of the tile this warpgroup will process next
     float nxt_o[OBS_DIM], nxt_a[A_DIM];
@@ -274,15 +357,14 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
                 const uint64_t da = umma_desc(x0_addr, 2048, 128), db = umma_desc(w_addr + (W1_OFF + half * 128 * 8) * 2, W1_N * 16, 128);
                 #pragma unroll
                 for (int s = 0; s < K1 / 16; s++)
-                    mma_ss(tD0, desc_advance(da, s * 2 * 2048), desc_advance(db, s * 2 * W1_N * 16), umma_idesc(128), s > 0);
+                    mma_ss(tD0, desc_advance(da, s * 2 * 2048), desc_advance(db, s * 2 * W1_N * 16), umma_idesc(128), true);
                 mma_commit(bar);
             }
             stamp();
             ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
             stamp();
             fence_after_sync();
-            turn_wait(wg);
-            epilogue_to_tmem(tD, tA + half * 64, s_c + C_B1 + half * 128);
+            epilogue_to_tmem(tD, tA + half * 64, half == 0 ? s_c + C_B1 + 128 : s_c + C_B2, 128, wg);
             turn_pass(wg);
             fence_before_sync();
             wg_sync(wg);
@@ -293,15 +375,14 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
             fence_after_sync();
             const uint64_t db = umma_desc(w_addr + W2_OFF * 2, W2_N * 16, 128);
             #pragma unroll 4
-            for (int s = 0; s < 256 / 16; s++) mma_ts(tD0, tA0 + s * 8, desc_advance(db, s * 2 * W2_N * 16), umma_idesc(128), s > 0);
+            for (int s = 0; s < 256 / 16; s++) mma_ts(tD0, tA0 + s * 8, desc_advance(db, s * 2 * W2_N * 16), umma_idesc(128), true);
             mma_commit(bar);
         }
         stamp();
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
         stamp();
         fence_after_sync();
-        turn_wait(wg);
-        epilogue_to_tmem(tD, tA, s_c + C_B2);                                // h2 -> columns 0..63
+        epilogue_to_tmem(tD, tA, s_c + C_B3, 128, wg);                       // h2 -> columns 0..63
         turn_pass(wg);
         fence_before_sync();
         wg_sync(wg);
@@ -311,13 +392,12 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
             fence_after_sync();
             const uint64_t db = umma_desc(w_addr + W3_OFF * 2, W3_N * 16, 128);
             #pragma unroll 4
-            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + s * 8, desc_advance(db, s * 2 * W3_N * 16), umma_idesc(128), s > 0);
+            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + s * 8, desc_advance(db, s * 2 * W3_N * 16), umma_idesc(128), true);
             mma_commit(bar);
         }
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
         fence_after_sync();
-        turn_wait(wg);
-        epilogue_to_tmem(tD, tA + 64, s_c + C_B3);
+        epilogue_to_tmem(tD, tA + 64, s_b4, 32, wg);
         turn_pass(wg);
         fence_before_sync();
         wg_sync(wg);
@@ -326,7 +406,7 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
             fence_after_sync();
             const uint64_t db = umma_desc(w_addr + W4_OFF * 2, W4_N * 16, 128);
             #pragma unroll 4
-            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + 64 + s * 8, desc_advance(db, s * 2 * W4_N * 16), umma_idesc(16), s > 0);
+            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + 64 + s * 8, desc_advance(db, s * 2 * W4_N * 16), umma_idesc(16), true);
             mma_commit(bar);
         }
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
@@ -336,7 +416,10 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
             tmem_ld16(tD, v);
             float x[8];
             #pragma unroll
-            for (int k = 0; k < 8; k++) x[k] = live ? v[k] + s_c[C_B4 + k] : 0.0f;
+            for (int k = 0; k < 8; k++) x[k] = live ? v[k] : 0.0f;          // (b4 was in the accumulator)
+            #pragma unroll 1
+            for (int c = 0; c < 128; c += 32) bias_to_tmem32(tD + c, s_c + C_B3 + 128 + c);   // value-branch hidden layer comes next
+            tmem_st_wait();
             if (live && p.logits) {
                 float4 *out = reinterpret_cast<float4 *>(p.logits + (size_t)row * 8);
                 out[0] = make_float4(x[0], x[1], x[2], x[3]);
@@ -358,13 +441,12 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
             fence_after_sync();
             const uint64_t db = umma_desc(w_addr + (W3_OFF + 128 * 8) * 2, W3_N * 16, 128);
             #pragma unroll 4
-            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + s * 8, desc_advance(db, s * 2 * W3_N * 16), umma_idesc(128), s > 0);
+            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + s * 8, desc_advance(db, s * 2 * W3_N * 16), umma_idesc(128), true);
             mma_commit(bar);
         }
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
         fence_after_sync();
-        turn_wait(wg);
-        epilogue_to_tmem(tD, tA + 64, s_c + C_B3 + 128);
+        epilogue_to_tmem(tD, tA + 64, s_c + C_C2, 128, wg);
         turn_pass(wg);
         fence_before_sync();
         wg_sync(wg);
@@ -373,7 +455,7 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
             fence_after_sync();
             const uint64_t db = umma_desc(w_addr + V2_OFF * 2, V2_N * 16, 128);
             #pragma unroll 4
-            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + 64 + s * 8, desc_advance(db, s * 2 * V2_N * 16), umma_idesc(128), s > 0);
+            for (int s = 0; s < 128 / 16; s++) mma_ts(tD0, tA0 + 64 + s * 8, desc_advance(db, s * 2 * V2_N * 16), umma_idesc(128), true);
             mma_commit(bar);
         }
         ok = mbar_wait_bounded(bar, parity) && ok; parity ^= 1;
@@ -385,14 +467,21 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
             for (int c = 0; c < 128; c += 32) {
                 float v[32];
                 tmem_ld32(tD + c, v);
+                bias_to_tmem32(tD + c, s_c + C_B1 + c);                      // the next tile's first layer
                 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const uint32_t t2 = tanh_pack(v[j] + s_c[C_C2 + c + j], v[j + 1] + s_c[C_C2 + c + j + 1]);
-                    val = fmaf(s_c[C_V3 + c + j], __uint_as_float(t2 << 16), val);
-                    val = fmaf(s_c[C_V3 + c + j + 1], __uint_as_float(t2 & 0xFFFF0000u), val);
+                    float lo = v[j], hi = v[j + 1];
+                    if (((j >> 1) & 7) < MLP_POLY) tanh_poly2(lo, hi);
+                    else {
+                        const uint32_t t2 = tanh_pack(lo, hi);
+                        lo = __uint_as_float(t2 << 16); hi = __uint_as_float(t2 & 0xFFFF0000u);
+                    }
+                    val = fmaf(s_c[C_V3 + c + j], lo, val);
+                    val = fmaf(s_c[C_V3 + c + j + 1], hi, val);
                 }
             }
             if (live) p.value[row] = val;
+            tmem_st_wait();
         }
         turn_pass(wg);
         fence_before_sync();

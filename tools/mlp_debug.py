@@ -5,7 +5,7 @@ import numpy as np, torch
 import mujoco_drone_b200 as M
 model = M.policy.make_rma_full().cuda()
 f = M.policy.FusedRMAFull(model)
-n = 524288
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 524288
 obs, prev = torch.randn((n, 22), device="cuda"), torch.rand((n, 4), device="cuda")
 for _ in range(3):
     f(obs, prev)
