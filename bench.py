@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[3]: RMA domain randomisation, 1M envs over 8 GPUs = 131072 per GPU (train_RMA.py:66-75)
     "c4": dict(cls="LocalFrameRPYParamsEnv", reward="distance_energy_reward", envs_per_gpu=131072, alg_bytes=104 + 94 + 88 + 24,
-               traffic=25.94e6 + 0.02e6, traffic_src="profiles/r01t_step_kernel_steady_state.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full; the 19.7 MB of algorithmic writes stay in the 126 MB L2 past the end of the kernel)",
+               traffic=26.25e6 + 0.01e6, traffic_src="profiles/r01z_step_kernel.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full; the 19.7 MB of algorithmic writes stay in the 126 MB L2 past the end of the kernel)",
                cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True),
                name="C4: LocalFrameRPYParamsEnv(22 obs)+distance_energy_reward, per-env randomised params, 131072 envs/GPU (1M over 8 GPUs)"),
     # configs[1]: BaseDroneEnv, 4096 envs, default (hover-at-reference) reward, raw 33-float obs
@@ -369,7 +369,7 @@ def main():
     env = envs[0]
     for e in envs:
         e.reset_tensor()
-    nbank = 8
+    nbank = 9            # coprime with the replica count: step i uses bank[i % nbank] on replica i % R, so every env sees a new action each step
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
     bank = torch.rand((nbank, n, 4), device=dev, generator=g)   # synthetic random actions ~U[0,1]^4, resident in HBM

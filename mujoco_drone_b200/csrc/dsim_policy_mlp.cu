@@ -192,7 +192,7 @@ DEV uint32_t tanh_pack(float lo, float hi) {
 // odd polynomial fitted for minimax RELATIVE error (3.1e-3, the size of the bf16 rounding that follows), evaluated for two
 // columns at once with packed fma.rn.f32x2: 14 issue slots per column pair instead of 16 SFU cycles.
 #ifndef MLP_POLY
-#define MLP_POLY 3           // of every 8 column pairs, this many go to the FMA pipe
+#define MLP_POLY 2           // of every 8 column pairs, this many go to the FMA pipe (sweep 0/2/3/4/5: 187/180/181/190/198 us)
 #endif
 DEV uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 DEV void unpk2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
