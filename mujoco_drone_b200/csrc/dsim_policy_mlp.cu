@@ -503,10 +503,269 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+
+// =====================================================================================================================
+// v2 schedule (DSIM_MLP_V2=1): every epilogue is shared by ALL eight compute warps (two per scheduler: warp w and w + 4 read
+// the same tensor-memory lane quarter and split the 128 columns in halves), and a ninth warp issues every MMA.
+// Why: within one warp the accumulator read (tcgen05.ld occupies the warp, 190 cycles per 32 columns) and the SFU work
+// (256 cycles per 32 columns) ADD; with two warps per scheduler one reads while the other computes.  The epilogue of tile A
+// runs while the tensor core works on tile B's layer and vice versa (the MMA warp is released by an mbarrier that all 256
+// compute threads arrive on), so no turn-taking is needed.
+constexpr int V2_THREADS = 288;
+constexpr int SMEM_BYTES_V2 = SMEM_BYTES + 64 + 2 * 2 * 128 * 4;            // + 4 mbarriers + value partial sums [2 tiles][2 halves][128]
+
+DEV void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+
+// first-layer operand row [s(16), a_prev(4), z(8), 0(4)] -> bf16, canonical smem tile (the parameter encoder runs on the CUDA cores)
+DEV void build_x0_row(const float *s_c, const float (&o)[OBS_DIM], const float (&a)[A_DIM], unsigned char *x0_tile, int r) {
+    float hdn[ENC_H];
+    #pragma unroll
+    for (int j = 0; j < ENC_H; j++) {
+        float acc = s_c[C_E1B + j];
+        #pragma unroll
+        for (int k = 0; k < P_DIM; k++) acc = fmaf(s_c[C_E1 + j * P_DIM + k], o[S_DIM + k], acc);
+        hdn[j] = tanh_fast(acc);
+    }
+    float x[K1];
+    #pragma unroll
+    for (int k = 0; k < S_DIM; k++) x[k] = o[k];
+    #pragma unroll
+    for (int k = 0; k < A_DIM; k++) x[S_DIM + k] = a[k];
+    #pragma unroll
+    for (int e = 0; e < E_DIM; e++) {
+        float acc = s_c[C_E2B + e];
+        #pragma unroll
+        for (int j = 0; j < ENC_H; j++) acc = fmaf(s_c[C_E2 + e * ENC_H + j], hdn[j], acc);
+        x[S_DIM + A_DIM + e] = acc;
+    }
+    #pragma unroll
+    for (int k = S_DIM + A_DIM + E_DIM; k < K1; k++) x[k] = 0.f;
+    #pragma unroll
+    for (int kc = 0; kc < K1 / 8; kc++) {                                    // element (row, k) at (k/8) * 2048 + row * 16 + (k%8) * 2
+        uint4 q;
+        q.x = pack_bf16(x[8 * kc + 0], x[8 * kc + 1]); q.y = pack_bf16(x[8 * kc + 2], x[8 * kc + 3]);
+        q.z = pack_bf16(x[8 * kc + 4], x[8 * kc + 5]); q.w = pack_bf16(x[8 * kc + 6], x[8 * kc + 7]);
+        *reinterpret_cast<uint4 *>(x0_tile + kc * 2048 + r * 16) = q;
+    }
+}
+
+// this thread's 64 accumulator columns [d, d + 64) -> tanh -> bf16 -> 32 operand columns at dst; nb0 / nb1: the next layer's
+// bias for the two 32-column chunks (nullptr: leave the columns alone)
+__device__ __noinline__ void epi_half(uint32_t d, uint32_t dst, const float *nb0, const float *nb1) {
+    uint32_t ra[32], rb[32];
+    tmem_ld32_issue(d, ra);
+    tmem_ld32_wait(ra);
+    tmem_ld32_issue(d + 32, rb);
+    __syncwarp();
+    if (nb0) bias_to_tmem32(d, nb0);
+    uint32_t pk[16];
+    #pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const float lo = __uint_as_float(ra[2 * j]), hi = __uint_as_float(ra[2 * j + 1]);
+        pk[j] = (j & 7) < MLP_POLY ? tanh_poly_pack(lo, hi) : tanh_pack(lo, hi);
+    }
+    tmem_st16(dst, pk);
+    tmem_ld32_wait(rb);
+    if (nb1) bias_to_tmem32(d + 32, nb1);
+    #pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const float lo = __uint_as_float(rb[2 * j]), hi = __uint_as_float(rb[2 * j + 1]);
+        pk[j] = (j & 7) < MLP_POLY ? tanh_poly_pack(lo, hi) : tanh_pack(lo, hi);
+    }
+    tmem_st16(dst + 16, pk);
+    tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(V2_THREADS, 1) rma_full_forward_kernel_v2(const MlpParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint16_t *s_w = reinterpret_cast<uint16_t *>(smem);
+    float *s_c = reinterpret_cast<float *>(smem + W_ELEMS * 2);
+    unsigned char *s_x0 = smem + W_ELEMS * 2 + C_ELEMS * 4;                  // [2 tiles][8 KB]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_x0 + 2 * X0_BYTES);      // [0..1] MMA done (tile), [2..3] epilogue done (tile)
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 4);
+    float *s_b4 = reinterpret_cast<float *>(s_tmem + 8);                      // 32 floats
+    float *s_val = s_b4 + 32;                                                 // [2][2][128]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_mma = warp == 8;
+    const int half = (warp >> 2) & 1, wq = warp & 3, r128 = tid & 127, my_tile = (tid >> 7) & 1;
+
+    {
+        const uint4 *gw = reinterpret_cast<const uint4 *>(p.w);
+        uint4 *sw = reinterpret_cast<uint4 *>(s_w);
+        for (int i = tid; i < W_ELEMS * 2 / 16; i += V2_THREADS) sw[i] = __ldg(gw + i);
+        for (int i = tid; i < C_ELEMS; i += V2_THREADS) s_c[i] = __ldg(p.c + i);
+        if (tid < 32) s_b4[tid] = tid < 16 ? __ldg(p.c + C_B4 + tid) : 0.0f;
+    }
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init(&s_bar[2], 256); mbar_init(&s_bar[3], 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t w_addr = smem_u32(s_w);
+    const int npairs = (p.ntiles + 1) / 2;
+    bool ok = true;
+
+    if (is_mma) {
+        if (lane == 0) {
+            uint32_t dpar[2] = {0u, 0u};
+            #pragma unroll 1
+            for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+                #pragma unroll 1
+                for (int st = 0; st < 7; st++) {
+                    #pragma unroll 1
+                    for (int T = 0; T < 2; T++) {
+                        ok = mbar_wait_bounded(&s_bar[2 + T], dpar[T]) && ok; dpar[T] ^= 1u;
+                        fence_after_sync();
+                        const uint32_t d0 = tmem_base + T * 256, a0 = d0 + 128;
+                        if (st < 2) {
+                            const uint64_t da = umma_desc(smem_u32(s_x0 + T * X0_BYTES), 2048, 128);
+                            const uint64_t db = umma_desc(w_addr + (W1_OFF + st * 128 * 8) * 2, W1_N * 16, 128);
+                            #pragma unroll
+                            for (int k = 0; k < K1 / 16; k++) mma_ss(d0, desc_advance(da, k * 2 * 2048), desc_advance(db, k * 2 * W1_N * 16), umma_idesc(128), true);
+                        } else if (st == 2) {
+                            const uint64_t db = umma_desc(w_addr + W2_OFF * 2, W2_N * 16, 128);
+                            #pragma unroll 4
+                            for (int k = 0; k < 256 / 16; k++) mma_ts(d0, a0 + k * 8, desc_advance(db, k * 2 * W2_N * 16), umma_idesc(128), true);
+                        } else if (st == 3 || st == 5) {
+                            const uint64_t db = umma_desc(w_addr + (W3_OFF + (st == 5 ? 128 * 8 : 0)) * 2, W3_N * 16, 128);
+                            #pragma unroll 4
+                            for (int k = 0; k < 128 / 16; k++) mma_ts(d0, a0 + k * 8, desc_advance(db, k * 2 * W3_N * 16), umma_idesc(128), true);
+                        } else if (st == 4) {
+                            const uint64_t db = umma_desc(w_addr + W4_OFF * 2, W4_N * 16, 128);
+                            #pragma unroll 4
+                            for (int k = 0; k < 128 / 16; k++) mma_ts(d0, a0 + 64 + k * 8, desc_advance(db, k * 2 * W4_N * 16), umma_idesc(16), true);
+                        } else {
+                            const uint64_t db = umma_desc(w_addr + V2_OFF * 2, V2_N * 16, 128);
+                            #pragma unroll 4
+                            for (int k = 0; k < 128 / 16; k++) mma_ts(d0, a0 + 64 + k * 8, desc_advance(db, k * 2 * V2_N * 16), umma_idesc(128), true);
+                        }
+                        mma_commit(&s_bar[T]);
+                    }
+                }
+            }
+        }
+    } else {
+        const uint32_t lane_off = (uint32_t)(32 * wq) << 16;
+        const uint32_t step_now = p.step + (p.step_dev ? __ldg(p.step_dev) : 0u);
+        float nxt_o[OBS_DIM], nxt_a[A_DIM];
+        auto load_row = [&](int pair_) {
+            const int tile_ = 2 * pair_ + my_tile, r_ = tile_ * 128 + r128;
+            const bool live_ = pair_ < npairs && tile_ < p.ntiles && r_ < p.n;
+            #pragma unroll
+            for (int k = 0; k < OBS_DIM; k += 2) {
+                const float2 v = live_ ? __ldg(reinterpret_cast<const float2 *>(p.obs + (size_t)r_ * OBS_DIM + k)) : make_float2(0.f, 0.f);
+                nxt_o[k] = v.x; nxt_o[k + 1] = v.y;
+            }
+            const bool fresh = live_ && p.reset_mask && p.reset_mask[r_];
+            const float4 v = (live_ && !fresh) ? __ldg(reinterpret_cast<const float4 *>(p.prev_action) + r_) : make_float4(0.f, 0.f, 0.f, 0.f);
+            nxt_a[0] = v.x; nxt_a[1] = v.y; nxt_a[2] = v.z; nxt_a[3] = v.w;
+        };
+        auto finish = [&](int T) { fence_before_sync(); mbar_arrive(&s_bar[2 + T]); };
+        // prologue: first layer's bias into both accumulators (my 64 columns), first pair's operand rows
+        #pragma unroll 1
+        for (int T = 0; T < 2; T++) {
+            const uint32_t d = tmem_base + T * 256 + lane_off + 64 * half;
+            bias_to_tmem32(d, s_c + C_B1 + 64 * half); bias_to_tmem32(d + 32, s_c + C_B1 + 64 * half + 32);
+        }
+        tmem_st_wait();
+        load_row(blockIdx.x);
+        build_x0_row(s_c, nxt_o, nxt_a, s_x0 + my_tile * X0_BYTES, r128);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        finish(0); finish(1);
+        uint32_t bpar[2] = {0u, 0u};
+        #pragma unroll 1
+        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+            load_row(pair + (int)gridDim.x);                                 // next pair's rows: in flight during the first two stages
+            #pragma unroll 1
+            for (int st = 0; st < 7; st++) {
+                #pragma unroll 1
+                for (int T = 0; T < 2; T++) {
+                    ok = mbar_wait_bounded(&s_bar[T], bpar[T]) && ok; bpar[T] ^= 1u;
+                    fence_after_sync();
+                    const uint32_t tD = tmem_base + T * 256 + lane_off, tA = tD + 128;
+                    const uint32_t d = tD + 64 * half;
+                    const int row = (2 * pair + T) * 128 + r128;
+                    const bool live = row < p.n;
+                    if (st == 4) {                                           // logits: 16 FP32 columns, rows handled by the half-0 warps
+                        if (half == 0) {
+                            float v[16];
+                            tmem_ld16(tD, v);
+                            float x[8];
+                            #pragma unroll
+                            for (int k = 0; k < 8; k++) x[k] = live ? v[k] : 0.0f;
+                            if (live && p.logits) {
+                                float4 *out = reinterpret_cast<float4 *>(p.logits + (size_t)row * 8);
+                                out[0] = make_float4(x[0], x[1], x[2], x[3]);
+                                out[1] = make_float4(x[4], x[5], x[6], x[7]);
+                            }
+                            if (p.actions) {
+                                float act[4], lp;
+                                dsim::beta_row<float, 4>(x, p.seed, p.env_base + (uint32_t)row, step_now, p.deterministic, act, lp);
+                                if (live) {
+                                    *reinterpret_cast<float4 *>(p.actions + (size_t)row * 4) = make_float4(act[0], act[1], act[2], act[3]);
+                                    if (p.logp) p.logp[row] = lp;
+                                }
+                            }
+                        }
+                        bias_to_tmem32(d, s_c + C_B3 + 128 + 64 * half); bias_to_tmem32(d + 32, s_c + C_B3 + 128 + 64 * half + 32);
+                        tmem_st_wait();
+                    } else if (st == 6) {                                    // value head: partial dot product over my 64 columns
+                        float val = 0.f;
+                        #pragma unroll 1
+                        for (int c = 0; c < 64; c += 32) {
+                            float v[32];
+                            tmem_ld32(d + c, v);
+                            bias_to_tmem32(d + c, s_c + C_B1 + 64 * half + c);   // the next pair's first layer
+                            #pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                float lo = v[j], hi = v[j + 1];
+                                if (((j >> 1) & 7) < MLP_POLY) tanh_poly2(lo, hi);
+                                else {
+                                    const uint32_t t2 = tanh_pack(lo, hi);
+                                    lo = __uint_as_float(t2 << 16); hi = __uint_as_float(t2 & 0xFFFF0000u);
+                                }
+                                val = fmaf(s_c[C_V3 + 64 * half + c + j], lo, val);
+                                val = fmaf(s_c[C_V3 + 64 * half + c + j + 1], hi, val);
+                            }
+                        }
+                        tmem_st_wait();
+                        s_val[(T * 2 + half) * 128 + r128] = val;
+                        asm volatile("bar.sync 5, 256;" ::: "memory");
+                        if (half == 0 && live) p.value[row] = s_c[C_C3] + s_val[(T * 2) * 128 + r128] + s_val[(T * 2 + 1) * 128 + r128];
+                    } else {
+                        const float *nb = st == 0 ? s_c + C_B1 + 128 : st == 1 ? s_c + C_B2 : st == 2 ? s_c + C_B3 : st == 5 ? s_c + C_C2 : nullptr;
+                        const float *nb0 = nb ? nb + 64 * half : (half == 0 ? s_b4 : nullptr);     // st == 3: FP32 b4 into columns 0..31
+                        const float *nb1 = nb ? nb + 64 * half + 32 : nullptr;
+                        const uint32_t dst = tA + ((st == 1 || st == 3 || st == 5) ? 64 : 0) + 32 * half;
+                        epi_half(d, dst, nb0, nb1);
+                    }
+                    finish(T);
+                    if (st == 1 && T == 1) {                                 // both first-layer MMAs of this pair are done: the operand tiles are free
+                        build_x0_row(s_c, nxt_o, nxt_a, s_x0 + my_tile * X0_BYTES, r128);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
+                }
+            }
+        }
+    }
+    if (!ok) atomicExch(p.error, 1);
+    fence_before_sync();
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
 }  // namespace
 
 struct DsimPolicy {
-    int device, sms;
+    int device, sms, v2;
     uint16_t *w;
     float *c;
     int *error;
@@ -539,6 +798,8 @@ extern "C" int dsim_policy_create(int device, const uint16_t *weights_host, cons
     if (e == cudaSuccess) e = cudaMemcpy(h->w, weights_host, (size_t)W_ELEMS * 2, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->c, consts_host, (size_t)C_ELEMS * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rma_full_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rma_full_forward_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_V2);
+    h->v2 = getenv("DSIM_MLP_V2") && atoi(getenv("DSIM_MLP_V2")) != 0;
     if (e != cudaSuccess) {
         if (h->w) cudaFree(h->w);
         if (h->c) cudaFree(h->c);
@@ -565,7 +826,8 @@ static int launch_policy(DsimPolicy *h, MlpParams &p, const float *obs_dev, cons
     p.n = n; p.ntiles = (n + 127) / 128; p.dbg = h->dbg;
     const int pairs = (p.ntiles + 1) / 2;
     const int grid = pairs < h->sms ? pairs : h->sms;
-    rma_full_forward_kernel<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    if (h->v2) rma_full_forward_kernel_v2<<<grid, V2_THREADS, SMEM_BYTES_V2, (cudaStream_t)stream>>>(p);
+    else rma_full_forward_kernel<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
 }
 

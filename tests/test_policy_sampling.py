@@ -157,11 +157,14 @@ def test_umma_weight_packing_layout():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
-def test_fused_tcgen05_policy_matches_torch_fp32():
+@pytest.mark.parametrize("schedule", ["pingpong", "shared_epilogue"])
+def test_fused_tcgen05_policy_matches_torch_fp32(schedule, monkeypatch):
     """the fused tcgen05 RMA_full kernel vs the plain PyTorch FP32 module (same weights, BatchNorm with non-trivial running
-    statistics).  Tolerance: bf16 operands with FP32 accumulation through 5 layers -> 3e-2 absolute on O(1) logits."""
+    statistics).  Tolerance: bf16 operands with FP32 accumulation through 5 layers -> 3e-2 absolute on O(1) logits.
+    Both schedules of the kernel (default ping-pong; DSIM_MLP_V2=1: epilogues shared by all warps + a dedicated MMA warp)."""
     import torch
     import mujoco_drone_b200 as M
+    monkeypatch.setenv("DSIM_MLP_V2", "1" if schedule == "shared_epilogue" else "0")
     torch.manual_seed(0)
     model = M.policy.make_rma_full().cuda()
     bn = model.hidden[4]
