@@ -166,6 +166,14 @@ def make_env(wl, n, rank_offset, device, auto_reset=True):
     return cls(cfg)
 
 
+def host_threads():
+    """host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: the OpenMP default is not it)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(wl, threads, target_seconds=12.0, n=8192):
     """FP64 C oracle (oracle/dsim_oracle.c, OpenMP over envs) on a bounded sample of the same workload."""
     from oracle import oracle as O
@@ -201,7 +209,7 @@ def run_reference_arm(args, wl, rank, world):
     if rank != 0:
         return
     from oracle import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     n = 8192
     # each "step" = one vector_step over a bounded sample of n envs
     from oracle import oracle as O2  # noqa: F401
@@ -530,7 +538,7 @@ def main():
         line["extras"] = extras
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
-        line["cpu_baseline"] = cpu_baseline(wl, O.max_threads())
+        line["cpu_baseline"] = cpu_baseline(wl, host_threads())
     if rank == 0:
         print(json.dumps(line))
     for e in envs:
