@@ -341,22 +341,28 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     __syncwarp();                                                  // barrier init visible to the waiting lanes
     unsigned parity = 0;                                           // bit b: phase of this warp's barrier b
     int buf = 0;
-    // Work stealing: a warp draws one ticket at entry and one per processed page (W + my_pages draws per launch; the holder
-    // of the last one re-zeroes the counter: launches and graph replays need no host reset).  A ticket is drawn half an
-    // iteration before it is claimed (raw atom: the compiler's warp-aggregated atomicAdd consumes its result at once), so the
-    // ~700-cycle round trip to L2 hides behind the post-processing instead of stalling the warp at the top of the loop.
-    const unsigned last_ticket = (unsigned)(min(nwarps, my_pages) + my_pages - 1);
+    // Page assignment.  The first two pages of a warp are static: page `wid`, then one of the next `nwarps` pages dealt
+    // round-robin over the CTAs (so that every SM gets the same number of second pages).  No atomic sits in front of the
+    // first page: 2368 warps drawing from one counter at kernel entry cost each of them ~2 us (same-address atomics
+    // serialise in L2), more than the page load they were meant to overlap.  From the third page on, work stealing: a warp
+    // draws one ticket per processed page, half an iteration before it claims it (raw atom: the compiler's warp-aggregated
+    // atomicAdd consumes its result at once), so the round trip to L2 hides behind the post-processing; the holder of the
+    // last ticket re-zeroes the counter (launches and graph replays need no host reset).  Launches with at most two pages
+    // per warp (C4: 1.73) draw nothing.
+    const bool stealing = my_pages > 2 * nwarps;
+    const unsigned last_ticket = (unsigned)(my_pages - 1);
     auto draw = [&]() {
         unsigned tk = 0;
-        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(tk) : "l"(p.ticket));
+        if (stealing && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(tk) : "l"(p.ticket));
         return tk;
     };
     auto claim = [&](unsigned tk) {                                // tk: lane 0's draw
+        if (!stealing) return p.npages;
         if (lane == 0 && tk == last_ticket) *p.ticket = 0u;
-        return __reduce_max_sync(0xffffffffu, lane == 0 ? p.page0 + nwarps + (int)tk : 0);
+        return __reduce_max_sync(0xffffffffu, lane == 0 ? p.page0 + 2 * nwarps + (int)tk : 0);
     };
     int page = p.page0 + wid;
-    int next = claim(draw());                                      // latency overlaps the first page's load
+    int next = p.page0 + nwarps + warp * (int)gridDim.x + (int)blockIdx.x;
     #pragma unroll 1
     while (page < p.npages) {
         const int i = page * kTile + lane;
