@@ -332,6 +332,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--envs", type=int, default=0, help="override the workload's envs per GPU (size sweep)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every timed step from Python instead of replaying a CUDA graph")
@@ -341,7 +342,11 @@ def main():
                     help="c5 policy: fused = hand-written tcgen05 kernel (bf16 operands, FP32 accumulate); others = torch / cuBLAS")
     ap.add_argument("--preroll", type=int, default=1500, help="untimed steps per replica before the warm-up (reach the steady-state reset rate)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.envs:                                              # size sweeps (not a BASELINE config: the line says so in config.workload)
+        wl["envs_per_gpu"] = int(args.envs)
+        wl["name"] += f" [envs_per_gpu overridden: {int(args.envs)}]"
+        wl.pop("traffic", None); wl.pop("traffic_src", None)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
