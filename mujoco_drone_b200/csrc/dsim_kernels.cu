@@ -516,7 +516,7 @@ template <typename T> static cudaError_t launch_step(DsimHandle *h, const KParam
     const unsigned smem = kp.smem_per_slot * kStages * kStepWarps;
     const int pages = kp.npages - kp.page0;
     if (!h->cfg.pendulum) return launch_one(h, step_kernel<T, false, -1, -1>, smem, st, &kp, pages);
-    if constexpr (std::is_same<T, float>::value) {
+    if (std::is_same<T, float>::value && !kp.eval_only && !kp.timeline) {   // specialised instantiations: plain steps only
         const int o = kp.obs_id, r = kp.reward_id;
         if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2>, smem, st, &kp, pages);   // C4 / C5
         if (o == DSIM_OBS_LOCAL_RPY && r == 1) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1>, smem, st, &kp, pages);                 // C3

@@ -302,6 +302,11 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[kStepWarps][kStages];
     constexpr int DC = (OBS >= 0 && PEND) ? obs_dim_of(OBS) : 0;
+    // the specialised instantiations (BASELINE configs) are only launched for plain steps: no debug timeline, not the
+    // evaluate-only mode (dsim_evaluate / DSIM_TIMELINE take the generic instantiation), so those branches fold away
+    constexpr bool kPlain = OBS >= 0;
+    unsigned long long *const timeline = kPlain ? nullptr : p.timeline;
+    const bool eval_only = kPlain ? false : (p.eval_only != 0);
     // warp-uniform values (warp index, page numbers) go through redux.sync: the compiler then knows they are uniform, keeps
     // the page / slot address arithmetic in the uniform datapath and hands the bulk-copy instructions uniform registers
     // directly instead of wrapping each one in a register-broadcast loop (~15 instructions per copy, 7 copies per page)
@@ -313,7 +318,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     // for the first step after a kernel that does - regen / set_params); everything an earlier kernel may have written is
     // touched after griddepcontrol.wait.
     unsigned long long t_entry = 0;
-    if (p.timeline) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
+    if (timeline) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int my_pages = p.npages - p.page0;                       // pages of THIS launch
     const bool has_work = wid < my_pages;
@@ -327,13 +332,13 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     if (!has_work) return;                                         // warps are autonomous: no CTA-wide barrier below
     int tl_k = 1;
     auto stamp = [&]() {
-        if (p.timeline && lane == 0 && tl_k < 8) {
+        if (timeline && lane == 0 && tl_k < 8) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            p.timeline[(size_t)wid * 8 + tl_k++] = t;
+            timeline[(size_t)wid * 8 + tl_k++] = t;
         }
     };
-    if (p.timeline && lane == 0) p.timeline[(size_t)wid * 8] = t_entry;
+    if (timeline && lane == 0) timeline[(size_t)wid * 8] = t_entry;
     stamp();                                                       // [1] dependency wait passed                                   // warps are autonomous: no CTA-wide barrier below
     const int obs_id = OBS >= 0 ? OBS : p.obs_id, reward_id = REW >= 0 ? REW : p.reward_id;
     const int D = DC > 0 ? DC : p.obs_dim;
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         }
         const unsigned drawn = draw();                             // for the page after `next`; claimed at the end of the iteration
         // ---- counters, termination, reward, observation
-        int ns = slot_to_int(col[RW_NUM_STEPS * kTile]) + (p.eval_only ? 0 : 1);
+        int ns = slot_to_int(col[RW_NUM_STEPS * kTile]) + (eval_only ? 0 : 1);
         // MuJoCo's mj_checkPos/Vel/Acc warn and reset the whole MjData; here the one env is parked on a finite state for
         // the outputs of this step, flagged truncated, counted, and re-sampled below.  Never silent.
         const bool bad = !state_finite(s);
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             if (p.trunc_host) p.trunc_host[i] = trunc ? 1 : 0;
         }
 
-        if (!p.eval_only) {
+        if (!eval_only) {
             // would-be ground contact (the floor plane is out of reach in the BASELINE configs; detected, never ignored)
             if (active && p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(p.stats + 4, 1.0);
             T ret = col[RW_EP_RETURN * kTile] + rew;
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             store_state(col, s);
         }
         {
-            const unsigned need = __ballot_sync(0xffffffffu, !p.eval_only && active && trunc && (p.auto_reset || bad));
+            const unsigned need = __ballot_sync(0xffffffffu, !eval_only && active && trunc && (p.auto_reset || bad));
             if (need) resample_page<T, PEND>(need, s_rw, p.rc, p.seed, p.env_base + (unsigned)(page * kTile));
         }
 
@@ -466,7 +471,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         T *gobs = p.obs + (size_t)page * kTile * D;
         const bool obs_bulk = (obs_bytes & 15u) == 0;              // always true for full pages
         if (lane == 0) {
-            if (!p.eval_only) bulk_s2g(p.rw + (size_t)page * (RW_ROWS * kTile), s_rw, RW_ROWS * kTile * sizeof(T));
+            if (!eval_only) bulk_s2g(p.rw + (size_t)page * (RW_ROWS * kTile), s_rw, RW_ROWS * kTile * sizeof(T));
             if (obs_bulk) bulk_s2g(gobs, s_obs, obs_bytes);
             if (obs_bulk && p.obs_host) bulk_s2g(p.obs_host + (size_t)page * kTile * D, s_obs, obs_bytes);
             bulk_commit();
@@ -482,9 +487,9 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         buf ^= 1;
     }
     if (lane == 0) bulk_wait_read();                               // the slots must outlive the bulk reads
-    if (p.timeline && lane == 0) {
+    if (timeline && lane == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.timeline[(size_t)wid * 8 + 7] = t;                        // [7] exit
+        timeline[(size_t)wid * 8 + 7] = t;                        // [7] exit
     }
 }
