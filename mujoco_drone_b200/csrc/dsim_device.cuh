@@ -397,7 +397,7 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
             } else {
                 const float iw = rsqrt_(w2), wn = w2 * iw;
                 float sh;
-                sincosf(0.5f * h * wn, &sh, &rw);
+                sincos_hinge(0.5f * h * wn, &sh, &rw);                      // branch-free polynomial (7e-8): no libm slow path in the kernel image
                 kq = sh * iw;
             }
         } else if (w2 >= T(1e-30)) {

@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         }
         stamp();                                                   // [3], [5]: page published
         if (!obs_bulk)                                             // ragged last page whose byte count is not a multiple of 16
+            #pragma unroll 1
             for (int e = lane; e < nvalid * D; e += kTile) {
                 gobs[e] = s_obs[e];
                 if (p.obs_host) p.obs_host[(size_t)page * kTile * D + e] = s_obs[e];
