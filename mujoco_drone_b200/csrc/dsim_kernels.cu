@@ -33,15 +33,15 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const KParams<T> p, int
     T *col = p.rw + page_elem(RW_ROWS, 0, i);
     const T *ro_col = p.ro + page_elem(RO_ROWS, 0, i);
     EnvState<T> s = load_state(col);
-    const EnvConsts<T> c = load_consts(p, ro_col);
+    const EnvConsts<T> c = load_consts(p, ro_col, p.per_env_consts != 0);
     const T ctrl[4] = {T(0), T(0), T(0), T(0)};
     substep<T, PEND, false>(s, c, ctrl, p.h);
     col[21 * kTile] = s.acc.x; col[22 * kTile] = s.acc.y; col[23 * kTile] = s.acc.z;
     if (refresh_obs) {
         V3<T> ref_off; T ref_yaw; double ref64[3];
-        load_ref(p, p.refp ? p.refp + page_elem(REF_ROWS, 0, i) : nullptr, ref_off, ref_yaw, ref64);
+        load_ref(p, p.refp ? p.refp + page_elem(REF_ROWS, 0, i) : nullptr, ref_off, ref_yaw, ref64, p.refp != nullptr);
         T prm[6];
-        load_params(p, ro_col, prm);
+        load_params(p, ro_col, prm, p.per_env_consts != 0);
         const PostState<T> ps = post_state(s, ref_off, ref_yaw);
         ObsWriter<T, 1> w; w.base = p.obs + (size_t)i * p.obs_dim; w.stride = 1;
         emit_obs<T, PEND>(p.obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(kBlock) states_kernel(const KParams<T> p, T *o
     if (i >= p.n) return;
     const EnvState<T> s = load_state(p.rw + page_elem(RW_ROWS, 0, i));
     V3<T> ref_off; T ref_yaw; double ref64[3];
-    load_ref(p, p.refp ? p.refp + page_elem(REF_ROWS, 0, i) : nullptr, ref_off, ref_yaw, ref64);
+    load_ref(p, p.refp ? p.refp + page_elem(REF_ROWS, 0, i) : nullptr, ref_off, ref_yaw, ref64, p.refp != nullptr);
     T prm[6];
-    load_params(p, p.ro + page_elem(RO_ROWS, 0, i), prm);
+    load_params(p, p.ro + page_elem(RO_ROWS, 0, i), prm, p.per_env_consts != 0);
     const PostState<T> ps = post_state(s, ref_off, ref_yaw);
     ObsWriter<T> w; w.base = out + (size_t)i * width; w.stride = 1;
     emit_state_row<T, PEND>(s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
@@ -518,9 +518,11 @@ template <typename T> static cudaError_t launch_step(DsimHandle *h, const KParam
     if (!h->cfg.pendulum) return launch_one(h, step_kernel<T, false, -1, -1>, smem, st, &kp, pages);
     if (std::is_same<T, float>::value && !kp.eval_only && !kp.timeline) {   // specialised instantiations: plain steps only
         const int o = kp.obs_id, r = kp.reward_id;
-        if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2>, smem, st, &kp, pages);   // C4 / C5
-        if (o == DSIM_OBS_LOCAL_RPY && r == 1) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1>, smem, st, &kp, pages);                 // C3
-        if (o == DSIM_OBS_BASE && r == 0) return launch_one(h, step_kernel<float, true, DSIM_OBS_BASE, 0>, smem, st, &kp, pages);                           // C2
+        const int cfg = (kp.per_env_consts ? 1 : 0) | (kp.refp ? 2 : 0) | (kp.frame_skip == 1 ? 4 : 0);
+        // BASELINE configs 4 / 5 (per-env randomised parameters), 3 (moving per-env setpoints), 2 (one parameter set)
+        if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2 && cfg == 5) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2, 5>, smem, st, &kp, pages);
+        if (o == DSIM_OBS_LOCAL_RPY && r == 1 && cfg == 6) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1, 6>, smem, st, &kp, pages);
+        if (o == DSIM_OBS_BASE && r == 0 && cfg == 4) return launch_one(h, step_kernel<float, true, DSIM_OBS_BASE, 0, 4>, smem, st, &kp, pages);
     }
     return launch_one(h, step_kernel<T, true, -1, -1>, smem, st, &kp, pages);
 }
@@ -884,7 +886,7 @@ extern "C" int64_t dsim_launch_count(const DsimHandle *h) { return h ? h->launch
 
 extern "C" int dsim_kernel_info(int which, int32_t *regs, int32_t *local_bytes, int32_t *max_threads) {
     cudaFuncAttributes a;
-    cudaError_t e = which == 0 ? cudaFuncGetAttributes(&a, step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2>) : cudaFuncGetAttributes(&a, step_kernel<double, true, -1, -1>);
+    cudaError_t e = which == 0 ? cudaFuncGetAttributes(&a, step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2, 5>) : cudaFuncGetAttributes(&a, step_kernel<double, true, -1, -1>);
     if (e != cudaSuccess) return DSIM_ECUDA;
     if (regs) *regs = a.numRegs;
     if (local_bytes) *local_bytes = (int32_t)a.localSizeBytes;

@@ -138,19 +138,19 @@ template <typename T> DSIM_DEV EnvConsts<T> consts_from(const T v[C_ROWS]) {
     return c;
 }
 // `ro_col`: (row 0, this env) of the read-only page, shared or global
-template <typename T> DSIM_DEV EnvConsts<T> load_consts(const KParams<T> &p, const T *ro_col) {
+template <typename T> DSIM_DEV EnvConsts<T> load_consts(const KParams<T> &p, const T *ro_col, bool per_env) {
     T v[C_ROWS];
     #pragma unroll
-    for (int k = 0; k < C_ROWS; k++) v[k] = p.per_env_consts ? ro_col[(RO_CONSTS + k) * kTile] : p.uconst[k];
+    for (int k = 0; k < C_ROWS; k++) v[k] = per_env ? ro_col[(RO_CONSTS + k) * kTile] : p.uconst[k];
     return consts_from(v);
 }
-template <typename T> DSIM_DEV void load_params(const KParams<T> &p, const T *ro_col, T prm[6]) {
+template <typename T> DSIM_DEV void load_params(const KParams<T> &p, const T *ro_col, T prm[6], bool per_env) {
     #pragma unroll
-    for (int k = 0; k < 6; k++) prm[k] = p.per_env_consts ? ro_col[(RO_PARAMS + k) * kTile] : p.uparams[k];
+    for (int k = 0; k < 6; k++) prm[k] = per_env ? ro_col[(RO_PARAMS + k) * kTile] : p.uparams[k];
 }
 // `ref_col`: (row 0, this env) of the setpoint page (ignored when the reference is shared)
-template <typename T> DSIM_DEV void load_ref(const KParams<T> &p, const T *ref_col, V3<T> &ref_off, T &ref_yaw, double ref64[3]) {
-    if (p.refp) {
+template <typename T> DSIM_DEV void load_ref(const KParams<T> &p, const T *ref_col, V3<T> &ref_off, T &ref_yaw, double ref64[3], bool per_env) {
+    if (per_env) {
         ref_off = mk(ref_col[0], ref_col[kTile], ref_col[2 * kTile]);
         ref_yaw = ref_col[3 * kTile];
         ref64[0] = p.start[0] + (double)ref_off.x; ref64[1] = p.start[1] + (double)ref_off.y; ref64[2] = p.start[2] + (double)ref_off.z;
@@ -275,17 +275,17 @@ template <typename T> DSIM_DEV void load_action(const T *row, T a[4]) {
 // `parts`: bit 0 = arm the barrier with the page's total byte count and load the READ-ONLY rows (compiled constants + raw
 // parameters: never written by a step kernel), bit 1 = load everything an earlier kernel of the stream may have written
 // (state rows, the policy's actions, the setpoint rows).  3 = the whole page.
-template <typename T> DSIM_DEV void issue_page_loads(const KParams<T> &p, int page, T *slot, uint64_t *bar, int parts = 3) {
+template <typename T> DSIM_DEV void issue_page_loads(const KParams<T> &p, int page, T *slot, uint64_t *bar, int parts, bool pec, bool pref) {
     constexpr uint32_t rwb = RW_ROWS * kTile * sizeof(T), rob = RO_ROWS * kTile * sizeof(T), rfb = REF_ROWS * kTile * sizeof(T);
     const uint32_t acb = (uint32_t)min(kTile, p.n - page * kTile) * 4u * (uint32_t)sizeof(T);   // the policy's [n][4] action rows of this page
     if (parts & 1) {
-        mbar_arrive_expect_tx(bar, rwb + acb + (p.per_env_consts ? rob : 0u) + (p.refp ? rfb : 0u));
-        if (p.per_env_consts) bulk_g2s(slot + RW_ROWS * kTile, p.ro + (size_t)page * (RO_ROWS * kTile), rob, bar);
+        mbar_arrive_expect_tx(bar, rwb + acb + (pec ? rob : 0u) + (pref ? rfb : 0u));
+        if (pec) bulk_g2s(slot + RW_ROWS * kTile, p.ro + (size_t)page * (RO_ROWS * kTile), rob, bar);
     }
     if (parts & 2) {
         bulk_g2s(slot, p.rw + (size_t)page * (RW_ROWS * kTile), rwb, bar);
         bulk_g2s(slot + kSlotActOff, p.actions + (size_t)page * (kTile * 4), acb, bar);
-        if (p.refp) bulk_g2s(slot + (RW_ROWS + RO_ROWS) * kTile, p.refp + (size_t)page * (REF_ROWS * kTile), rfb, bar);
+        if (pref) bulk_g2s(slot + (RW_ROWS + RO_ROWS) * kTile, p.refp + (size_t)page * (REF_ROWS * kTile), rfb, bar);
     }
 }
 
@@ -297,7 +297,9 @@ template <typename T> DSIM_DEV void issue_page_loads(const KParams<T> &p, int pa
 // expensive (in-kernel resets) and W rarely divides the page count, so static striding leaves a long tail.  Every active
 // warp's last grab fails; the warp that draws the last ticket of the launch re-zeroes the counter (nobody grabs after it,
 // and the next launch only starts grabbing once this grid has completed), so launches and CUDA-graph replays need no host reset.
-template <typename T, bool PEND, int OBS, int REW>
+// CFG >= 0 (specialised instantiations): bit 0 per-env constants, bit 1 per-env setpoints, bit 2 frame_skip == 1 - the host
+// launches such an instantiation only when the handle's configuration matches; -1: everything is a run-time option
+template <typename T, bool PEND, int OBS, int REW, int CFG = -1>
 __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[kStepWarps][kStages];
@@ -305,6 +307,9 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     // the specialised instantiations (BASELINE configs) are only launched for plain steps: no debug timeline, not the
     // evaluate-only mode (dsim_evaluate / DSIM_TIMELINE take the generic instantiation), so those branches fold away
     constexpr bool kPlain = OBS >= 0;
+    const bool pec = CFG >= 0 ? (CFG & 1) != 0 : (p.per_env_consts != 0);
+    const bool pref = CFG >= 0 ? (CFG & 2) != 0 : (p.refp != nullptr);
+    const int frame_skip = (CFG >= 0 && (CFG & 4)) ? 1 : p.frame_skip;
     unsigned long long *const timeline = kPlain ? nullptr : p.timeline;
     const bool eval_only = kPlain ? false : (p.eval_only != 0);
     // warp-uniform values (warp index, page numbers) go through redux.sync: the compiler then knows they are uniform, keeps
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     if (has_work && lane == 0) {
         #pragma unroll
         for (int k = 0; k < kStages; k++) mbar_init(&s_bar[warp][k], 1);
-        if (p.early_ro) issue_page_loads(p, p.page0 + wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0], 1);
+        if (p.early_ro) issue_page_loads(p, p.page0 + wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0], 1, pec, pref);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (!has_work) return;                                         // warps are autonomous: no CTA-wide barrier below
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     stamp();                                                       // [1] dependency wait passed                                   // warps are autonomous: no CTA-wide barrier below
     const int obs_id = OBS >= 0 ? OBS : p.obs_id, reward_id = REW >= 0 ? REW : p.reward_id;
     const int D = DC > 0 ? DC : p.obs_dim;
-    if (lane == 0) issue_page_loads(p, p.page0 + wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0], p.early_ro ? 2 : 3);
+    if (lane == 0) issue_page_loads(p, p.page0 + wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0], p.early_ro ? 2 : 3, pec, pref);
     __syncwarp();                                                  // barrier init visible to the waiting lanes
     unsigned parity = 0;                                           // bit b: phase of this warp's barrier b
     int buf = 0;
@@ -387,17 +392,17 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         // end of the previous iteration; their shared-memory reads complete within a few hundred cycles.
         if (lane == 0 && next < p.npages) {
             bulk_wait_read();
-            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + (size_t)(buf ^ 1) * p.smem_per_slot), &s_bar[warp][buf ^ 1]);
+            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + (size_t)(buf ^ 1) * p.smem_per_slot), &s_bar[warp][buf ^ 1], 3, pec, pref);
         }
 
         {
-            const EnvConsts<T> c = load_consts(p, ro_col);
+            const EnvConsts<T> c = load_consts(p, ro_col, pec);
             T a[4], ctrl[4];
             load_action(s_act, a);
             #pragma unroll
             for (int k = 0; k < 4; k++) ctrl[k] = clamp_(T(0.1) + T(0.9) * a[k], T(0), T(1));   // :269 + ctrlrange (0,1) clamp of mj_fwdActuation
             #pragma unroll 1
-            for (int f = 0; f < p.frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
+            for (int f = 0; f < frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
         }
         const unsigned drawn = draw();                             // for the page after `next`; claimed at the end of the iteration
         // ---- counters, termination, reward, observation
@@ -412,9 +417,9 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             for (int k = 0; k < 4; k++) s.act[k] = T(0);
         }
         V3<T> ref_off; T ref_yaw; double ref64[3];
-        load_ref(p, s_ref + lane, ref_off, ref_yaw, ref64);
+        load_ref(p, s_ref + lane, ref_off, ref_yaw, ref64, pref);
         T prm[6];
-        load_params(p, ro_col, prm);
+        load_params(p, ro_col, prm, pec);
         const PostState<T> ps = post_state(s, ref_off, ref_yaw);
         const bool trunc = terminated(s.pos, p.start, ref64, p.max_d2, ns, p.max_steps) || bad;
         T a[4];
