@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Debug: per-warp %globaltimer timeline of one step launch (DSIM_TIMELINE=1).  usage: timeline.py [workload] [cold|hot]"""
+"""Debug: per-warp %globaltimer timeline of one step launch (DSIM_TIMELINE=1).  usage: timeline.py [workload] [cold|hot]
+Note: with the timeline enabled the library launches the GENERIC instantiation of the step kernel (the specialised ones
+have the stamps compiled out), which executes ~10 % more instructions per page than the kernel the bench times."""
 import ctypes as C
 import os
 import sys
