@@ -17,7 +17,8 @@ constexpr int kBetaMaxBlocks = 8;     // 16 attempts; acceptance >= 95 % per att
 
 template <typename T> DSIM_DEV T softplus1(T x) {     // torch.log(torch.exp(clamp(x, -50, 50)) + 1.0) + 1.0
     x = clamp_(x, T(-50), T(50));
-    if constexpr (std::is_same<T, float>::value) return logf(expf(x) + 1.0f) + 1.0f; else return log(exp(x) + 1.0) + 1.0;
+    if constexpr (std::is_same<T, float>::value) return __logf(__expf(x) + 1.0f) + 1.0f;     // MUFU ex2 / lg2: ~1e-6 relative, 6 instructions instead of libm's ~30
+    else return log(exp(x) + 1.0) + 1.0;
 }
 template <typename T> DSIM_DEV T log1p_(T x) { if constexpr (std::is_same<T, float>::value) return log1pf(x); else return log1p(x); }
 // log Gamma(x) for x >= 1 (alpha, beta = softplus + 1 >= 1, their sum >= 2).  FP32: shift the argument up by 4 and use the
