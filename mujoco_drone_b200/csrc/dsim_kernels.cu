@@ -875,10 +875,17 @@ extern "C" int dsim_beta_policy(const void *logits_dev, int n, int precision, ui
     if (precision != DSIM_FP32 && precision != DSIM_FP64) return DSIM_EINVAL;
     const int grid = (n + 127) / 128;
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == DSIM_FP32)
-        beta_policy_kernel<float, 4><<<grid, 128, 0, st>>>(n, (const float *)logits_dev, seed, (uint32_t)env_id_offset, step, step_dev, deterministic, (float *)actions_dev, (float *)logp_dev);
-    else
-        beta_policy_kernel<double, 4><<<grid, 128, 0, st>>>(n, (const double *)logits_dev, seed, (uint32_t)env_id_offset, step, step_dev, deterministic, (double *)actions_dev, (double *)logp_dev);
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(128); lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // pairs with griddepcontrol.* at the top of the kernel
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    uint32_t env0 = (uint32_t)env_id_offset;
+    void *args[] = {&n, &logits_dev, &seed, &env0, &step, &step_dev, &deterministic, &actions_dev, &logp_dev};
+    const void *fn = precision == DSIM_FP32 ? (const void *)beta_policy_kernel<float, 4> : (const void *)beta_policy_kernel<double, 4>;
+    if (cudaLaunchKernelExC(&lc, fn, args) != cudaSuccess) return DSIM_ECUDA;
     return cudaGetLastError() == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
 }
 

@@ -100,6 +100,10 @@ DSIM_DEV void beta_row(const T (&x)[2 * A], uint32_t seed, uint32_t env, uint32_
 template <typename T, int A>
 __global__ void __launch_bounds__(128) beta_policy_kernel(int n, const T *logits, uint32_t seed, uint32_t env_base, uint32_t step,
                                                           const uint32_t *step_dev, int deterministic, T *actions, T *logp) {
+    // programmatic dependent launch: the next kernel of the stream (the env step) may be scheduled while this grid drains;
+    // nothing an earlier kernel wrote (the logits) is read before the dependency wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (step_dev) step += *step_dev;                     // device-resident step counter: CUDA-graph replays draw fresh numbers

@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
     float *s_b4 = reinterpret_cast<float *>(s_tmem + 12);                      // b4 (16 logits columns, 8 real) padded to 32
     const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, wq = (tid >> 5) & 3;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // ---- one-time setup: weights + constants -> shared memory, TMEM allocation, barriers
     {
@@ -297,6 +298,9 @@ __global__ void __launch_bounds__(256, 1) rma_full_forward_kernel(const MlpParam
         const float4 v = (live_ && !fresh) ? __ldg(reinterpret_cast<const float4 *>(p.prev_action) + r_) : make_float4(0.f, 0.f, 0.f, 0.f);
         nxt_a[0] = v.x; nxt_a[1] = v.y; nxt_a[2] = v.z; nxt_a[3] = v.w;
     };
+    // programmatic dependent launch: everything above (weights into shared memory, tensor-memory allocation) reads nothing an
+    // earlier kernel of the stream writes and may overlap its tail; the observation rows come after the dependency wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     load_row(2 * blockIdx.x + wg);
     const uint32_t step_now = p.step + (p.step_dev ? __ldg(p.step_dev) : 0u);
     constexpr int kTurnsPerTile = 6;                                       // epilogues that take a turn (the 16-column logits read does not)
@@ -826,9 +830,19 @@ static int launch_policy(DsimPolicy *h, MlpParams &p, const float *obs_dev, cons
     p.n = n; p.ntiles = (n + 127) / 128; p.dbg = h->dbg;
     const int pairs = (p.ntiles + 1) / 2;
     const int grid = pairs < h->sms ? pairs : h->sms;
-    if (h->v2) rma_full_forward_kernel_v2<<<grid, V2_THREADS, SMEM_BYTES_V2, (cudaStream_t)stream>>>(p);
-    else rma_full_forward_kernel<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(p);
-    return cudaGetLastError() == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
+    if (h->v2) {
+        rma_full_forward_kernel_v2<<<grid, V2_THREADS, SMEM_BYTES_V2, (cudaStream_t)stream>>>(p);
+        return cudaGetLastError() == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
+    }
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(256); lc.dynamicSmemBytes = SMEM_BYTES; lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // pairs with griddepcontrol.* in the kernel
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    void *args[] = {&p};
+    return cudaLaunchKernelExC(&lc, (const void *)rma_full_forward_kernel, args) == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
 }
 
 extern "C" int dsim_policy_forward(DsimPolicy *h, const float *obs_dev, const float *prev_action_dev, const uint8_t *reset_mask_dev, int n,
