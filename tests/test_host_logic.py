@@ -146,3 +146,21 @@ def test_single_process_allreduce_is_identity():
     st = {"sum_return": 6.0, "sum_length": 30.0, "n_episodes": 3.0, "n_nonfinite": 0.0, "n_near_ground": 2.0}
     out = dist.allreduce_episode_stats(st)
     assert out["mean_return"] == 2.0 and out["mean_length"] == 10.0 and out["n_near_ground"] == 2.0
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port timed on the host cores) prints ONE JSON line with the contract's keys"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env-steps/sec" and d["unit"] == "env-steps/s" and d["higher_is_better"] is True
+    assert d["steps"] == 2 and d["value"] > 0 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
