@@ -514,6 +514,19 @@ def main():
         extras["flushed_per_step"] = {"value": n / (msf * 1e-3), "ms_per_step": msf,
                                       "note": "L2 flushed (256 MiB write + 256 MiB read) before each step; one CUDA-event pair per step"}
         del flush, flush_rd
+        # (c) the other single-GPU BASELINE configs (configs[1]: 4096 envs, configs[2]: 65536 envs with moving setpoints), each as
+        # its own short run of this script, for the record next to the headline workload
+        if world == 1 and args.workload == "c4" and not args.envs:
+            for name in ("c2", "c3"):
+                try:
+                    # (c3 steps 16 replicas round-robin in graphs of 32 steps: a multiple of 32 leaves no eagerly launched remainder)
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", "200" if name == "c2" else "192", "--warmup", "5",
+                                        "--no-cpu-baseline", "--no-extras"], capture_output=True, text=True, timeout=300)
+                    sub = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")][-1]
+                    extras["baseline_config_" + name] = {"workload": sub["config"]["workload"], "value": sub["value"], "ms_per_step": sub["ms_per_step"],
+                                                         "roofline_frac": sub["roofline"]["frac"], "e2e": sub["e2e"]["value"]}
+                except Exception as ex:                      # secondary information only: never fail the headline line
+                    extras["baseline_config_" + name] = {"error": repr(ex)[:200]}
     if world > 1:
         dist.barrier()
 
