@@ -33,6 +33,14 @@ WORKLOADS = {
                traffic=26.25e6 + 0.01e6, traffic_src="profiles/r01z_step_kernel.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full; the 19.7 MB of algorithmic writes stay in the 126 MB L2 past the end of the kernel)",
                cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True),
                name="C4: LocalFrameRPYParamsEnv(22 obs)+distance_energy_reward, per-env randomised params, 131072 envs/GPU (1M over 8 GPUs)"),
+    # configs[0]: SimpleDrone single env (SimpleDrone.py:41-46: no pendulum, env_gen defaults mass 1.35 / arm 0.15 / force 7.5 / tau 0.015,
+    # timestep 0.001 (make_sim default frequency=1000), frame_skip 2, actions in [0.5, 1]); CPU-runnable reference case
+    "c1": dict(cls="BaseDroneEnv", reward="default_reward_fcn", envs_per_gpu=1, alg_bytes=(16 + 28 + 24 + 16 + 4) + (28 + 24 + 16 + 4 + 4 + 2) + 116,
+               cfg=dict(pendulum=False, frequency=1000, skip_steps=2, random_params=False, random_start_pos=False, reference=[0, 0, 1, 0], start_pos=[0, 0, 1, 0],
+                        mass_interval=[1.35, 0], arm_len_interval=[0.15, 0], motor_force_interval=[7.5, 0], motor_tau_interval=[0.015, 0],
+                        pendulum_length_interval=[0, 0], weight_mass_interval=[0, 0], max_distance=0.5, max_steps=10 ** 9),
+               action_range=(0.5, 1.0),
+               name="C1: SimpleDrone-equivalent single drone, no pendulum, timestep 0.001, frame_skip 2, actions U[0.5,1] (SimpleDrone.py:41-58)"),
     # configs[1]: BaseDroneEnv, 4096 envs, default (hover-at-reference) reward, raw 33-float obs
     "c2": dict(cls="BaseDroneEnv", reward="default_reward_fcn", envs_per_gpu=4096, alg_bytes=104 + 94 + 132,
                cfg=dict(), name="C2: BaseDroneEnv(33 obs)+default_reward_fcn, base_config, 4096 envs"),
@@ -155,6 +163,63 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pcie_probe(torch, dist, dev, world, d2h_bytes, h2d_bytes, barrier, reps=10):
+    """Bare pinned-memory copies of the end-to-end step's byte counts, every rank at once: the PCIe roof of `e2e`.
+    Returns the aggregate GB/s over all ranks (sum of bytes / slowest rank's time)."""
+    h = torch.empty(max(d2h_bytes, h2d_bytes), dtype=torch.uint8).pin_memory()
+    d = torch.empty(max(d2h_bytes, h2d_bytes), dtype=torch.uint8, device=dev)
+    out = {}
+    for name, nbytes, fn in (("d2h_gbs", d2h_bytes, lambda nb: h[:nb].copy_(d[:nb], non_blocking=True)),
+                             ("h2d_gbs", h2d_bytes, lambda nb: d[:nb].copy_(h[:nb], non_blocking=True))):
+        for _ in range(3):
+            fn(nbytes)
+        barrier()
+        t = time.perf_counter()
+        for _ in range(reps):
+            fn(nbytes)
+            torch.cuda.synchronize(dev)              # one copy per step and a sync, like the step it bounds
+        dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out[name] = world * nbytes * reps / float(dt.item()) / 1e9
+    out["how"] = (f"measured in this run: {reps} cudaMemcpyAsync copies (torch copy_, pinned host memory) of the step's D2H byte count + synchronize each, "
+                  f"{world} rank(s) concurrently, aggregate over ranks")
+    return out
+
+
+def pin_rank_to_cores(local_rank, world):
+    """Give every rank its own slice of the host cores the job may use (and allocate pinned memory afterwards, so first
+    touch happens there).  The pool's boxes report ONE NUMA node / the same affinity mask for all 8 GPUs, so the slice is
+    by rank order; on a multi-socket host NVML's per-GPU CPU affinity is intersected first."""
+    info = {"pinned": False}
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        near = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+            hdl = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (max(allowed) // 64) + 1)
+            near = [c for c in allowed if (words[c // 64] >> (c % 64)) & 1]
+            info["numa_node"] = None
+        except Exception:
+            near = None
+        pool = near if near and len(near) >= 1 else allowed
+        info["gpu_cpu_affinity_cores"] = len(pool)
+        if world > 1 and len(pool) >= world:
+            per = len(pool) // world
+            mine = pool[local_rank * per:(local_rank + 1) * per]
+            os.sched_setaffinity(0, mine)
+            info.update(pinned=True, cores=[mine[0], mine[-1]])
+        else:
+            info["cores"] = [pool[0], pool[-1]]
+    except Exception as ex:                         # placement is an optimisation, never a failure
+        info["error"] = repr(ex)[:100]
+    return info
+
+
 def make_env(wl, n, rank_offset, device, auto_reset=True):
     import mujoco_drone_b200 as M
     cls = M.BaseDroneEnv if wl["cls"] == "BaseDroneEnv" else getattr(M.observation_wrappers, wl["cls"])
@@ -174,71 +239,97 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+class CpuArm:
+    """The CPU side of every number: the FP64 C restatement of the path (oracle/dsim_oracle.c, OpenMP over envs) on a bounded
+    sample of the SAME workload - per-env randomised parameters, states drawn by sample_state, random actions from a bank,
+    the config's own max_distance / max_steps, and RLlib's reset_at() round trip for every truncated env after each step
+    (orc_reset_truncated), so episodes end and restart at the same rate as on the GPU.
+    What it is NOT: the reference's Python (BaseDroneEnv.vector_step costs >= 174 us per drone-step of interpreter time on top
+    of mj_step, SURVEY F8 / BASELINE.md §2) - `kind: "port"` is the best case a CPU could do for this path."""
+
+    def __init__(self, wl, n=8192):
+        from oracle import oracle as O
+        import mujoco_drone_b200 as M
+        self.O, self.n, self.wl = O, n, wl
+        rng = np.random.default_rng(0)
+        cfgd = dict(M.base_config)
+        cfgd.update(wl["cfg"])
+        self.cfgd = cfgd
+        pend = bool(cfgd.get("pendulum", True))
+        iv = [cfgd[k] for k in ("mass_interval", "arm_len_interval", "motor_force_interval", "motor_tau_interval",
+                                "pendulum_length_interval", "weight_mass_interval")]
+        c, hw = np.array([x[0] for x in iv], dtype=float), np.array([x[1] for x in iv], dtype=float)
+        pd = cfgd["param_difficulty"] if cfgd.get("random_params", True) else 0.0
+        params = c + rng.uniform(-1, 1, size=(n, 6)) * hw * pd
+        if not pend:
+            params[:, 4:] = 0
+        self.env = O.CpuVecEnv(params, pend, float(cfgd["frequency"]), int(cfgd["skip_steps"]), True)
+        sd = cfgd["state_difficulty"]
+        start = list(cfgd.get("start_pos", cfgd["reference"]))
+        self.rc = O.make_reset_cfg(start, sd * cfgd.get("max_random_offset", 0), [0, 0], sd * np.array(cfgd["vel_variance"]),
+                                   sd * np.array(cfgd["ang_vel_variance"]), sd * np.array(cfgd["pendulum_rp_variance"]),
+                                   sd * np.array(cfgd["pendulum_ang_vel_variance"]), cfgd["random_start_pos"], pend)
+        for i in range(n):
+            self.env.qpos[i], self.env.qvel[i] = O.sample_state(self.rc, 42, i, 0)
+        self.rid, self.oid = O.REWARD_IDS[wl["reward"]], O.OBS_IDS[wl["cls"]]
+        ref = np.array(cfgd["reference"], dtype=float)
+        self.ref = np.tile(ref, (n, 1)) if cfgd.get("per_env_reference") else ref
+        self.bank = rng.uniform(*wl.get("action_range", (0, 1)), size=(9, n, 4))
+        self.k = 0
+        self.truncations = 0
+
+    def step(self, threads, reps=1):
+        """`reps` vector_steps (+ reset_at round trips) in one call into the C library"""
+        e, c = self.env, self.cfgd
+        self.truncations += e.step_repeat(reps, self.bank, self.ref, self.rid, self.oid, float(c["max_distance"]), int(c["max_steps"]),
+                                          self.rc, 42, 0, nthreads=threads)
+        self.k += reps
+
+    def describe(self, steps, dt, threads):
+        return (f"{steps} vector_steps x {self.n} envs of the same workload in {dt:.1f} s: FP64 C restatement of mj_step x frame_skip + states + "
+                f"termination + reward + obs (oracle port), {threads} OpenMP threads, random actions, episodes end and are re-sampled "
+                f"({self.truncations / max(1, steps * self.n):.4f} resets per env-step); the reference's Python interpreter overhead is NOT included")
+
+
 def cpu_baseline(wl, threads, target_seconds=12.0, n=8192):
     """FP64 C oracle (oracle/dsim_oracle.c, OpenMP over envs) on a bounded sample of the same workload."""
-    from oracle import oracle as O
-    import mujoco_drone_b200 as M
-    rng = np.random.default_rng(0)
-    cfgd = dict(M.base_config)
-    cfgd.update(wl["cfg"])
-    pd = cfgd["param_difficulty"] if cfgd.get("random_params", True) else 0.0
-    c = np.array([1, 0.17, 7, 0.01, 1.2, 0.3])
-    hw = np.array([0.1, 0.02, 1, 0.0025, 0.2, 0.05])
-    params = c + rng.uniform(-1, 1, size=(n, 6)) * hw * pd
-    env = O.CpuVecEnv(params, True, 100.0, 1, True)
-    sd = cfgd["state_difficulty"]
-    rc = O.make_reset_cfg([0, 0, 15, 0], sd * 2, [0, 0], [sd] * 3, [sd] * 3, [0.5 * sd] * 2, [0.5 * sd] * 2, True, True)
-    for i in range(n):
-        env.qpos[i], env.qvel[i] = O.sample_state(rc, 42, i, 0)
-    rid, oid = O.REWARD_IDS[wl["reward"]], O.OBS_IDS[wl["cls"]]
-    ref = np.array([0, 0, 15.0, 0])
-    if cfgd.get("per_env_reference"):
-        ref = np.tile(ref, (n, 1))
-    acts = rng.uniform(0, 1, size=(n, 4))
-    env.step(acts, ref, rid, oid, 4.0, 10 ** 9, nthreads=threads)       # warm-up
+    arm = CpuArm(wl, n)
+    arm.step(threads, 20)                                             # OpenMP team start-up, caches, a first round of episode ends
     steps, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < target_seconds:
-        env.step(acts, ref, rid, oid, 4.0, 10 ** 9, nthreads=threads)
-        steps += 1
+        arm.step(threads, 10)
+        steps += 10
     dt = time.perf_counter() - t0
-    return dict(value=n * steps / dt, unit="env-steps/s", cores=threads, kind="port",
-                sample=f"{steps} vector_steps x {n} envs of the same workload in {dt:.1f} s (FP64 C restatement of mj_step + obs/reward, OpenMP)")
+    return dict(value=n * steps / dt, unit="env-steps/s", cores=threads, kind="port", sample=arm.describe(steps, dt, threads))
 
 
 def run_reference_arm(args, wl, rank, world):
+    """--impl reference: the CPU implementation of the path alone, all host threads.  --steps K is a lower bound: blocks of
+    K steps are repeated until at least `min_seconds` have been timed (a 20-step run of 1.8 ms steps measures the OpenMP
+    warm-up, not the code)."""
     if rank != 0:
         return
-    from oracle import oracle as O
-    threads = host_threads()
-    n = 8192
-    # each "step" = one vector_step over a bounded sample of n envs
-    from oracle import oracle as O2  # noqa: F401
-    import mujoco_drone_b200 as M
-    rng = np.random.default_rng(0)
-    cfgd = dict(M.base_config)
-    cfgd.update(wl["cfg"])
-    pd = cfgd["param_difficulty"] if cfgd.get("random_params", True) else 0.0
-    params = np.array([1, 0.17, 7, 0.01, 1.2, 0.3]) + rng.uniform(-1, 1, size=(n, 6)) * np.array([0.1, 0.02, 1, 0.0025, 0.2, 0.05]) * pd
-    env = O.CpuVecEnv(params, True, 100.0, 1, True)
-    env.qpos[:, 2] = 15.0
-    rid, oid = O.REWARD_IDS[wl["reward"]], O.OBS_IDS[wl["cls"]]
-    ref = np.tile(np.array([0, 0, 15.0, 0]), (n, 1)) if cfgd.get("per_env_reference") else np.array([0, 0, 15.0, 0])
-    acts = rng.uniform(0, 1, size=(n, 4))
-    for _ in range(args.warmup):
-        env.step(acts, ref, rid, oid, 4.0, 10 ** 9, nthreads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        env.step(acts, ref, rid, oid, 4.0, 10 ** 9, nthreads=threads)
+    n = int(args.envs) if args.envs else min(8192, wl["envs_per_gpu"])
+    threads = min(host_threads(), n)
+    arm = CpuArm(wl, n)
+    arm.step(threads, max(args.warmup, 20))
+    min_seconds = 3.0
+    block = max(1, args.steps) if n > 64 else 2000                    # tiny batches: many steps per call into the C library
+    steps, t0 = 0, time.perf_counter()
+    while steps < args.steps or time.perf_counter() - t0 < min_seconds:
+        arm.step(threads, block)
+        steps += block
     dt = time.perf_counter() - t0
-    v = n * args.steps / dt
-    sample = f"each step = one vector_step over a {n}-env sample of the workload; FP64 C restatement (oracle port), {threads} OpenMP threads"
+    v = n * steps / dt
+    sample = arm.describe(steps, dt, threads)
     print(json.dumps({
         "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": {"workload": wl["name"], "cpu_sample_envs": n},
+        "warmup": max(args.warmup, 20), "ms_per_step": 1e3 * dt / steps, "timed_steps": steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": wl["name"], "cpu_sample_envs": n, "same_config": True},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference Python + mujoco wheel are not installable/present on the GPU box; this is the oracle port of the same path",
+        "note": ("reference Python + mujoco wheel are not installable/present on the GPU box; this is the oracle port of the same path "
+                 "(best-case CPU: no interpreter overhead; BASELINE.md holds the 'reference Python + restated mj_step' row measured in the build container)"),
     }))
 
 
@@ -264,12 +355,24 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
     for _ in range(min(args.preroll, 300) + max(args.warmup, 3)):
         runner._graph.replay()
     barrier()
-    l0 = env.launch_count()
+    # --steps K is a lower bound: the per-step graph is replayed until the event window is >= min_window_ms as well
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    for _ in range(20):
+        runner._graph.replay()
+    w1.record()
+    torch.cuda.synchronize(dev)
+    timed_steps = max(args.steps, int(np.ceil(args.min_window_ms / max(w0.elapsed_time(w1) / 20, 1e-3))))
+    if world > 1:
+        mt = torch.tensor([timed_steps], dtype=torch.int64, device=dev)
+        dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        timed_steps = int(mt.item())
+    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()
-    for i in range(args.steps):
+    for i in range(timed_steps):
         runner._graph.replay()
     e1.record()
     barrier()
@@ -304,19 +407,20 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     achieved = wl["alg_bytes"] * n / (k_ms * 1e-3) / 1e9
     line = {
-        "metric": "env-steps/sec", "value": world * n * args.steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": "env-steps/sec", "value": world * n * timed_steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / timed_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 env step; policy " + ("bf16 operands / f32 accumulate, fused tcgen05 kernel" if args.policy_dtype == "fused" else args.policy_dtype + " torch GEMMs"), "data": "synthetic",
         "config": {"workload": wl["name"], "envs_per_gpu": n, "total_envs": n * world, "policy": "RMA_full random init (6->32->8 | 28->256->128+BN | 128->128->8 | 128->128->128->1), " + args.policy_dtype,
                    "sampling": "MyBetaDist, Philox Marsaglia-Tsang", "graph": "one CUDA graph replay per step",
+                   "timed_steps": timed_steps, "timed_window_ms": ms,
                    "l2": "inputs larger than L2 (env state + activations of 524288 envs)", "parallelism": f"env-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * (4 * env.obs_dim + 5),
                 "api": "dsim_step_host (C ABI), host-side policy boundary"},
         # per step: rma_full_forward_kernel (forward + sampling; or torch GEMMs / + beta_policy_kernel when not fused), step_kernel
-        "gpu_launches": (2 if (args.policy_dtype == "fused" and args.fuse_sampling) else 3) * args.steps,
+        "gpu_launches": (2 if (args.policy_dtype == "fused" and args.fuse_sampling) else 3) * timed_steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "step_kernel<float,true> timed alone at this size", "algorithmic_bytes_per_env_step": wl["alg_bytes"], "peak_source": peak_src,
-                     "env_step_kernel_ms": k_ms, "share_of_loop": k_ms / (ms / args.steps)},
+                     "env_step_kernel_ms": k_ms, "share_of_loop": k_ms / (ms / timed_steps)},
         "clocks": clocks,
         "episode_stats": {k: stats[k] for k in ("n_episodes", "mean_return", "mean_length", "n_nonfinite", "n_near_ground")},
     }
@@ -340,6 +444,7 @@ def main():
     ap.add_argument("--fuse-sampling", action="store_true", help="c5, fused policy: sample inside the policy kernel (dsim_policy_forward_sample; measured slower at 524288 envs)")
     ap.add_argument("--policy-dtype", default="fused", choices=["fp32", "tf32", "bf16", "fused"],
                     help="c5 policy: fused = hand-written tcgen05 kernel (bf16 operands, FP32 accumulate); others = torch / cuBLAS")
+    ap.add_argument("--min-window-ms", type=float, default=30.0, help="the graph of timed steps is replayed until the event window is at least this long")
     ap.add_argument("--preroll", type=int, default=1500, help="untimed steps per replica before the warm-up (reach the steady-state reset rate)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -364,6 +469,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_placement = pin_rank_to_cores(local_rank, world)      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if wl.get("rollout"):
@@ -410,12 +516,15 @@ def main():
     run_steps(args.preroll * R, envs)
     run_steps(max(args.warmup, 3) * R, envs)                  # every replica warmed up
     barrier()
-    # The timed region replays a CUDA graph of G consecutive steps (round-robin over the replicas): at ~15 us per step the
-    # Python / ctypes launch path (~10 us per call, worse with N processes sharing a host) would otherwise be what is
-    # measured.  Setpoint updates (C3) stay outside the graph, every 50 steps per replica as before.
+    # The timed region replays a CUDA graph of G consecutive steps (round-robin over the replicas, G a multiple of R so
+    # every replay continues the rotation): at ~10 us per step the Python / ctypes launch path (~10 us per call, worse
+    # with N processes sharing a host) would otherwise be what is measured.  The driver's --steps K only sets a LOWER
+    # bound: the same graph is replayed M times so that at least K steps are timed AND the event window is >= 30 ms
+    # (>= 10 NVML clock samples inside it); ms_per_step divides by the true count M * G (`timed_steps` in the line).
+    # Setpoint updates (C3) stay outside the graph, every 50 steps per replica as before.
     G = R * max(1, 40 // R) if not args.no_graph else 0
-    graph = None
-    if G and args.steps >= G:
+    graph, M, timed_steps = None, 0, args.steps
+    if G:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -428,12 +537,24 @@ def main():
             run_steps(G, envs)
         axes = saved_axes
         # capture / instantiation left the GPU idle for tens of ms (its clocks drop to the idle state): replay untimed until
-        # it has been busy for ~50 ms again, so the timed region does not include the clock ramp
+        # it has been busy for ~50 ms again, so the timed region does not include the clock ramp; the last block of
+        # replays is timed to size the window
         tw = time.perf_counter()
-        while time.perf_counter() - tw < 0.05:
+        est_ms = None
+        while time.perf_counter() - tw < 0.05 or est_ms is None:
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
             for _ in range(8):
                 graph.replay()
+            w1.record()
             torch.cuda.synchronize(dev)
+            est_ms = w0.elapsed_time(w1) / 8
+        M = max(-(-args.steps // G), int(np.ceil(args.min_window_ms / max(est_ms, 1e-3))))
+        if world > 1:                                          # same replay count on every rank
+            mt = torch.tensor([M], dtype=torch.int64, device=dev)
+            dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+            M = int(mt.item())
+        timed_steps = M * G
     barrier()
     l0 = sum(e.launch_count() for e in envs)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -441,15 +562,12 @@ def main():
     t0 = time.time()
     e0.record()
     if graph is not None:
-        done = 0
-        while done + G <= args.steps:
-            if axes is not None and (done // R) % 50 < G // R:
+        for m in range(M):
+            if axes is not None and ((m * G) // R) % 50 < G // R:
                 for e in envs:
                     e.control_reference_tensor(axes)
             graph.replay()
-            done += G
-        graph_launches = done
-        run_steps(args.steps - done, envs, sampler)            # remainder, eager
+        graph_launches = M * G
     else:
         graph_launches = 0
         run_steps(args.steps, envs, sampler)
@@ -467,14 +585,14 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
-    value = world * n * args.steps / (ms * 1e-3)
+    value = world * n * timed_steps / (ms * 1e-3)
 
     # ---- end-to-end through the C-ABI host-buffer entry point (pinned host memory, copies inside the timed region)
     h_act = torch.rand((nbank, n, 4)).pin_memory()
     h_obs = torch.empty((n, env.obs_dim)).pin_memory()
     h_rew = torch.empty((n,)).pin_memory()
     h_tr = torch.empty((n,), dtype=torch.uint8).pin_memory()
-    e2e_steps = max(10, min(args.steps, 50))
+    e2e_steps = max(20, min(args.steps, 100))
     for i in range(3):
         env.step_host(h_act[i % nbank].numpy(), h_obs.numpy(), h_rew.numpy(), h_tr.numpy())
     barrier()
@@ -486,6 +604,8 @@ def main():
     if world > 1:
         dist.all_reduce(dte, op=dist.ReduceOp.MAX)
     e2e = world * n * e2e_steps / float(dte.item())
+    d2h_bytes, h2d_bytes = n * (4 * env.obs_dim + 4 + 1), n * 16
+    pcie = pcie_probe(torch, dist, dev, world, d2h_bytes, h2d_bytes, barrier)
 
     extras = {}
     if not args.no_extras and rank == 0:
@@ -514,37 +634,58 @@ def main():
         extras["flushed_per_step"] = {"value": n / (msf * 1e-3), "ms_per_step": msf,
                                       "note": "L2 flushed (256 MiB write + 256 MiB read) before each step; one CUDA-event pair per step"}
         del flush, flush_rd
-        # (c) the other single-GPU BASELINE configs (configs[1]: 4096 envs, configs[2]: 65536 envs with moving setpoints), each as
-        # its own short run of this script, for the record next to the headline workload
+        # (c) the other BASELINE configs that fit one GPU (configs[1]: 4096 envs, configs[2]: 65536 envs with moving setpoints,
+        # configs[4]: the policy-in-the-loop rollout at its per-GPU size of 524288 envs), each as its own short run of this
+        # script, for the record next to the headline workload; configs[0] (single SimpleDrone env) is the CPU-runnable case
         if world == 1 and args.workload == "c4" and not args.envs:
-            for name in ("c2", "c3"):
+            for name in ("c2", "c3", "c5"):
                 try:
-                    # (c3 steps 16 replicas round-robin in graphs of 32 steps: a multiple of 32 leaves no eagerly launched remainder)
-                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", "200" if name == "c2" else "192", "--warmup", "5",
-                                        "--no-cpu-baseline", "--no-extras"], capture_output=True, text=True, timeout=300)
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", str(args.steps), "--warmup", "5",
+                                        "--no-cpu-baseline", "--no-extras"], capture_output=True, text=True, timeout=600)
                     sub = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")][-1]
                     extras["baseline_config_" + name] = {"workload": sub["config"]["workload"], "value": sub["value"], "ms_per_step": sub["ms_per_step"],
+                                                         "timed_steps": sub["config"].get("timed_steps"), "dtype": sub["dtype"],
                                                          "roofline_frac": sub["roofline"]["frac"], "e2e": sub["e2e"]["value"]}
                 except Exception as ex:                      # secondary information only: never fail the headline line
                     extras["baseline_config_" + name] = {"error": repr(ex)[:200]}
+            try:
+                arm1 = CpuArm(WORKLOADS["c1"], 1)
+                arm1.step(1, 2000)
+                t1c, k1c = time.perf_counter(), 0
+                while time.perf_counter() - t1c < 1.5:
+                    arm1.step(1, 5000)
+                    k1c += 5000
+                extras["baseline_config_c1_cpu"] = {"workload": WORKLOADS["c1"]["name"], "value": k1c / (time.perf_counter() - t1c), "cores": 1,
+                                                    "note": "CPU only (one drone cannot occupy a GPU): the FP64 oracle port, one thread"}
+            except Exception as ex:
+                extras["baseline_config_c1_cpu"] = {"error": repr(ex)[:200]}
     if world > 1:
         dist.barrier()
 
     peak, peak_src = measured_peaks()
-    k_ms = ms / args.steps
+    k_ms = ms / timed_steps
     achieved = wl["alg_bytes"] * n / (k_ms * 1e-3) / 1e9
     line = {
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "envs_per_gpu": n, "total_envs": n * world, "frame_skip": 1, "timestep": 0.01,
                    "actions": "random U[0,1]^4 from an HBM-resident bank", "auto_reset": "in-kernel Philox", "preroll_steps_per_replica": args.preroll,
-                   "launch": (f"CUDA graph of {G} consecutive steps replayed" if graph is not None else "one Python/ctypes launch per step"),
+                   "launch": (f"CUDA graph of {G} consecutive steps replayed {M} times inside ONE event pair: {timed_steps} timed steps (>= --steps {args.steps}, window >= {args.min_window_ms:.0f} ms)"
+                              if graph is not None else "one Python/ctypes launch per step"),
+                   "timed_steps": timed_steps, "timed_window_ms": ms,
                    "l2": (f"inputs larger than L2: {R} independent replicas of the batch stepped round-robin, {R * per_replica / 1e6:.0f} MB working set vs 126 MB L2"
                           if R > 1 else "not flushed (single replica)"),
                    "replicas": R,
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
-        "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * (4 * env.obs_dim + 4 + 1),
-                "steps": e2e_steps, "api": "dsim_step_host (C ABI) with pinned host buffers: one launch, the kernel's bulk loads / stores move actions and outputs over PCIe (zero-copy)"},
+        "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "steps": e2e_steps, "api": "dsim_step_host (C ABI) with pinned host buffers: one launch, the kernel's bulk loads / stores move actions and outputs over PCIe (zero-copy)",
+                # the end-to-end step is bound by the device->host leg (93 of its 109 bytes per env-step; PCIe is full duplex, the
+                # 16-byte action reads travel the other way): achieved = D2H bytes of all ranks / wall time, peak = what bare
+                # cudaMemcpyAsync copies of the same sizes reach on this box, all ranks copying at once
+                "roofline": {"bound": "pcie", "achieved": world * d2h_bytes * e2e_steps / float(dte.item()) / 1e9, "peak": pcie["d2h_gbs"],
+                             "unit": "GB/s", "frac": world * d2h_bytes * e2e_steps / float(dte.item()) / 1e9 / pcie["d2h_gbs"] if pcie["d2h_gbs"] else None,
+                             "peak_source": pcie["how"], "h2d_peak": pcie["h2d_gbs"]},
+                "host": host_placement},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": wl.get("traffic"),
                      "traffic_source": wl.get("traffic_src"), "kernel": "step_kernel<float,true>", "algorithmic_bytes_per_launch": wl["alg_bytes"] * n,

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -107,25 +108,36 @@ __global__ void compile_kernel(int n, int ld, const double *params64, T *ro, int
     for (int k = 0; k < C_ROWS; k++) col[(RO_CONSTS + k) * kTile] = (T)c[k];
     for (int k = 0; k < 6; k++) col[(RO_PARAMS + k) * kTile] = (T)p[k];
 }
-// control_reference (:151-172) per env: axes [4][ld] are the already sign-flipped joystick values (x, -y, -z, -yaw)
+// control_reference (:151-172) per env: axes [4][ld] are the already sign-flipped joystick values (x, -y, -z, -yaw).
+// The dead-zone DECISIONS (:160-161) are index logic and are taken in FP64 whatever the page precision: an axis value that is
+// a 2-decimal number which went through FP32 (joystick.py:36 rounds to 2 decimals; 0.12f != 0.12) is restored to the double
+// the reference sees, products and sums are not contracted, so the active / inactive bits equal the reference's; the
+// setpoint itself is accumulated in FP64 and stored in the page's precision.
 template <typename T>
 __global__ void control_reference_kernel(int n, int ld, const T *axes, T *refp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     T *col = refp + page_elem(REF_ROWS, 0, i);
-    T pert[4], r[4];
-    for (int k = 0; k < 4; k++) { pert[k] = axes[(size_t)k * ld + i]; r[k] = col[k * kTile]; }
-    const bool xy = sqrt_(pert[0] * pert[0] + pert[1] * pert[1]) > T(0.2), zy = sqrt_(pert[2] * pert[2] + pert[3] * pert[3]) > T(0.2);
-    const T lim[3] = {T(5), T(5), T(6)};
+    double pert[4], r[4];
     for (int k = 0; k < 4; k++) {
-        const T mag = max_(abs_(pert[k]) - T(0.1), T(0));
-        const T sg = pert[k] > T(0) ? T(1) : (pert[k] < T(0) ? T(-1) : T(0));
-        const bool active = k < 2 ? xy : zy;
-        r[k] += active ? T(0.1) * mag * sg : T(0);
+        const double a = (double)axes[(size_t)k * ld + i], c = rint(a * 100.0);
+        pert[k] = fabs(a * 100.0 - c) < 1e-3 ? c / 100.0 : a;
+        r[k] = (double)col[k * kTile];
     }
-    r[3] = wrap_pi(r[3]);
-    for (int k = 0; k < 3; k++) r[k] = clamp_(r[k], -lim[k], lim[k]);      // clip to start_pos +- (5,5,6); ref rows are offsets
-    for (int k = 0; k < 4; k++) col[k * kTile] = r[k];
+    const bool xy = sqrt(__dadd_rn(__dmul_rn(pert[0], pert[0]), __dmul_rn(pert[1], pert[1]))) > 0.2;
+    const bool zy = sqrt(__dadd_rn(__dmul_rn(pert[2], pert[2]), __dmul_rn(pert[3], pert[3]))) > 0.2;
+    const double lim[3] = {5.0, 5.0, 6.0};
+    for (int k = 0; k < 4; k++) {
+        const double mag = fmax(fabs(pert[k]) - 0.1, 0.0);
+        const double sg = pert[k] > 0.0 ? 1.0 : (pert[k] < 0.0 ? -1.0 : 0.0);
+        const bool active = k < 2 ? xy : zy;
+        r[k] = __dadd_rn(r[k], __dmul_rn(__dmul_rn(__dmul_rn(0.1, mag), sg), active ? 1.0 : 0.0));
+    }
+    double y = fmod(__dadd_rn(r[3], kPi), 2 * kPi);                         // Python's float %: sign of the divisor
+    if (y < 0.0) y += 2 * kPi;
+    r[3] = __dsub_rn(y, kPi);                                               // (yaw + pi) % (2 pi) - pi  (:168)
+    for (int k = 0; k < 3; k++) r[k] = fmin(fmax(r[k], -lim[k]), lim[k]);   // clip to start_pos +- (5,5,6); ref rows are offsets
+    for (int k = 0; k < 4; k++) col[k * kTile] = (T)r[k];
 }
 // setpoint streams on the device (evaluation.py:135-152 gen_circle / gen_step / gen_ramp_trajectory): env i follows the
 // trajectory at time t + i * phase_step, so a batch covers every phase of it; the setpoint page holds offsets from start_pos
@@ -172,7 +184,7 @@ struct DsimHandle {
     int per_env_consts;
     double uconst[C_ROWS], uparams[6];
     double h;
-    int first_reset_done, step_grid, step_cap;
+    int first_reset_done;
     int ro_dirty;                      // a kernel that rewrote the read-only pages was queued since the last step
     cudaStream_t hs[3];                // host entry point: copy-in, compute, copy-out streams (created on first use)
     cudaEvent_t ev_in[kHostChunks], ev_k[kHostChunks], ev_a, ev_b, ev_c;
@@ -486,22 +498,35 @@ extern "C" int dsim_zero_act(DsimHandle *h, void *stream) {
 }
 
 // step-kernel dispatch: compile-time specialisations for the BASELINE configs, generic kernel otherwise.  The kernel is
-// persistent: grid = min(CTAs needed, CTAs the GPU can hold at once), queried once per handle.
+// persistent: grid = min(CTAs needed, CTAs the GPU can hold at once).  The > 48 KB dynamic shared-memory opt-in and the
+// occupancy are properties of ONE kernel instantiation on ONE device (and of the slot size), and one handle launches
+// several instantiations (specialised plain steps, the generic kernel for dsim_evaluate / after a set_params that flips
+// per_env_consts): both are looked up per (function, device, smem) in a small process-wide table.
+struct StepFnInfo { const void *fn; int device; unsigned smem; int cap; };
+static StepFnInfo g_step_fn[128];
+static int g_step_fn_count = 0;
+static std::mutex g_step_fn_mutex;
+static cudaError_t step_fn_capacity(const void *fn, int device, unsigned smem, int *cap) {
+    std::lock_guard<std::mutex> lock(g_step_fn_mutex);
+    for (int k = 0; k < g_step_fn_count; k++)
+        if (g_step_fn[k].fn == fn && g_step_fn[k].device == device && g_step_fn[k].smem == smem) { *cap = g_step_fn[k].cap; return cudaSuccess; }
+    // opt in to the largest slot any handle can ask for
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(slot_bytes(DSIM_MAX_OBS, 8) * kStages * kStepWarps));
+    if (e != cudaSuccess) return e;
+    int sms = 0, per_sm = 0;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kStepBlock, smem)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    *cap = sms * per_sm;
+    if (g_step_fn_count < 128) g_step_fn[g_step_fn_count++] = StepFnInfo{fn, device, smem, *cap};
+    return cudaSuccess;
+}
 template <typename K> static cudaError_t launch_one(DsimHandle *h, K kernel, unsigned smem, cudaStream_t st, const void *kp_ptr, int pages) {
-    if (!h->step_grid) {
-        // opt in once to the largest slot any handle can ask for (the attribute is per function, not per handle)
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(slot_bytes(DSIM_MAX_OBS, 8) * kStages * kStepWarps));
-        if (e != cudaSuccess) return e;
-        int sms = 0, per_sm = 0;
-        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kStepBlock, smem)) != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        const int need = (h->npages + kStepWarps - 1) / kStepWarps, cap = sms * per_sm;
-        h->step_grid = need < cap ? need : cap;
-        h->step_cap = cap;
-    }
-    int grid = h->step_grid;
-    if (pages != h->npages) { const int need = (pages + kStepWarps - 1) / kStepWarps; grid = need < h->step_cap ? need : h->step_cap; }
+    int cap = 0;
+    cudaError_t e = step_fn_capacity((const void *)kernel, h->device, smem, &cap);
+    if (e != cudaSuccess) return e;
+    const int need = (pages + kStepWarps - 1) / kStepWarps;
+    const int grid = need < cap ? need : cap;
     void *args[] = {const_cast<void *>(kp_ptr)};
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof lc);

@@ -274,12 +274,15 @@ class BaseDroneEnv(_VectorEnv):
     def evaluate_tensor(self, actions):
         """termination / reward / observation of the CURRENT state (no physics, no counters): what the reference's
         terminated_fcn / reward_fcn / _get_obs return on `self.states`."""
+        if tuple(actions.shape) != (self.num_drones, 4):
+            raise ValueError("Action dimension mismatch")
         actions = actions.to(device=self._device, dtype=self._d_actions.dtype).contiguous()
         self._ck(self._L.dsim_evaluate(self._h, C.c_void_p(actions.data_ptr()), self._stream()))
         return self.obs_tensor, self.reward_tensor, self.truncated_tensor
 
     def reset_tensor(self):
         self._ck(self._L.dsim_reset_all(self._h, self._stream()))
+        self._sensor_stale = False                                          # dsim_reset_all ends with mj_forward
         self._states_cache = None
         return self.obs_tensor
 
@@ -299,9 +302,17 @@ class BaseDroneEnv(_VectorEnv):
         obs_out = np.empty((self.num_drones, self.obs_dim), np.float32) if obs_out is None else obs_out
         reward_out = np.empty(self.num_drones, np.float32) if reward_out is None else reward_out
         trunc_out = np.empty(self.num_drones, np.uint8) if trunc_out is None else trunc_out
+        # the library writes through raw pointers (from the GPU, over PCIe, on the pinned path): anything but the exact
+        # C-contiguous layout would be a silent out-of-bounds / garbled write
+        for name, arr, shape, dt in (("obs_out", obs_out, (self.num_drones, self.obs_dim), np.float32),
+                                     ("reward_out", reward_out, (self.num_drones,), np.float32),
+                                     ("trunc_out", trunc_out, (self.num_drones,), np.uint8)):
+            if not (isinstance(arr, np.ndarray) and arr.dtype == dt and arr.shape == shape and arr.flags['C_CONTIGUOUS'] and arr.flags['WRITEABLE']):
+                raise ValueError(f"{name} must be a writable C-contiguous {np.dtype(dt).name} array of shape {shape}")
         ptr = lambda x: x.__array_interface__['data'][0]                     # (ndarray.ctypes builds a helper object per access)
         self._ck(self._L.dsim_step_host(self._h, ptr(a), ptr(obs_out), ptr(reward_out), ptr(trunc_out), self._stream()))
         self.total_steps += 1
+        self._sensor_stale = False
         self._states_cache = None
         return obs_out, reward_out, trunc_out
 

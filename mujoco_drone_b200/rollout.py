@@ -99,18 +99,28 @@ class RolloutRunner:
         if self._fused is None:   # first action of a new episode sees zeros as its previous action
             self.prev_actions.copy_(self._act * (trunc == 0).to(self._act.dtype).unsqueeze(1))
 
+    WARMUP_STEPS = 3
+
+    def warm_up(self, steps=None):
+        """`steps` UNRECORDED policy + sample + env steps (default WARMUP_STEPS = what the CUDA-graph capture runs first:
+        lazy init, cuBLAS workspaces, shared-memory opt-in).  They advance the env, the sampling step counter and
+        env.total_steps like recorded steps do; an eager runner that calls warm_up() once is bit-identical to a graph runner."""
+        for _ in range(self.WARMUP_STEPS if steps is None else steps):
+            self._one_step()
+
     def _capture(self):
         torch = self.torch
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
-            for _ in range(3):                 # warm-up outside capture: lazy init, cuBLAS workspaces, smem attribute opt-in
-                self._one_step()
+            self.warm_up()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
+        ts = self.env.total_steps
         with torch.cuda.graph(g):
             self._one_step()
+        self.env.total_steps = ts                # the captured pass queued nothing: only replays advance the env
         self._graph = g
 
     def step(self, t):
@@ -122,6 +132,8 @@ class RolloutRunner:
             self._record_history()
         if self._graph is not None:
             self._graph.replay()
+            self.env.total_steps += 1            # what step_tensor does on the eager path
+            self.env._states_cache = None
         else:
             self._one_step()
         self.values[t].copy_(self._val)
@@ -166,6 +178,8 @@ class RolloutRunner:
         self.obs[self.T].copy_(self._obs_cur)
         _, v = self._forward()
         self.values[self.T].copy_(v)
+        if self._fused is not None:
+            self._fused.check()                  # a tensor-core barrier timeout invalidates the whole batch: raise, never return it
         return dict(obs=self.obs, actions=self.actions, rewards=self.rewards, truncated=self.truncated, values=self.values,
                     action_logp=self.logp)
 

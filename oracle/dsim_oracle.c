@@ -808,6 +808,46 @@ void orc_sample_params(const OrcResetCfg *c, uint32_t seed, uint32_t env, uint32
     if (!c->pendulum) { p[4] = 0; p[5] = 0; }
 }
 
+/* BaseDroneEnv.control_reference (BaseDroneEnv.py:151-172) without the joystick polling / mocap side effects.
+ * axes = (x, y, z, yaw) AFTER the sign flips of :154-157, i.e. the `pert` vector of :159 (joystick.py:36 has already
+ * rounded every axis to 2 decimals; that is the caller's business, not this function's).
+ * ref[4] is self.reference (absolute position + yaw), start_pos[3] the clip centre (:168-169). */
+void orc_control_reference(double ref[4], const double axes[4], const double start_pos[3]) {
+    double pert[4], mag[4], sg[4];
+    for (int k = 0; k < 4; k++) pert[k] = axes[k];
+    /* np.linalg.norm of a 2-vector: sqrt(dot(x, x)) */
+    const int xy_active = sqrt(pert[0] * pert[0] + pert[1] * pert[1]) > 0.2;          /* :160 */
+    const int zyaw_active = sqrt(pert[2] * pert[2] + pert[3] * pert[3]) > 0.2;        /* :161 */
+    for (int k = 0; k < 4; k++) {
+        mag[k] = fmax(fabs(pert[k]) - 0.1, 0.0);                                      /* :162 */
+        sg[k] = (pert[k] > 0) - (pert[k] < 0);                                        /* :163 */
+        const int on = k < 2 ? xy_active : zyaw_active;
+        ref[k] = ref[k] + 0.1 * mag[k] * sg[k] * (double)on;                          /* :164, :167 */
+    }
+    /* Python's float % : result takes the sign of the divisor */
+    double y = fmod(ref[3] + PI, 2 * PI);
+    if (y < 0) y += 2 * PI;
+    ref[3] = y - PI;                                                                  /* :168 */
+    const double lim[3] = {5, 5, 6};
+    for (int k = 0; k < 3; k++) ref[k] = fmin(fmax(ref[k], start_pos[k] - lim[k]), start_pos[k] + lim[k]);   /* :170 */
+}
+
+/* RLlib's reset_at() round trip after vector_step (BaseDroneEnv.py:334-351), batched: every env whose
+ * `truncated` flag is set gets the next draw of its own reset stream (reset_count += 1, the same bookkeeping as the
+ * in-kernel reset of the CUDA path) and num_steps = 0; act / sensordata persist (Q3). */
+void orc_reset_truncated(int n, int nq, int nv, const OrcResetCfg *c, uint32_t seed, uint32_t env0, uint32_t *reset_count,
+                         const uint8_t *truncated, double *qpos, double *qvel, int64_t *num_steps) {
+    for (int i = 0; i < n; i++) {
+        if (!truncated[i]) continue;
+        double qp[ORC_MAXNQ], qv[ORC_MAXNV];
+        reset_count[i] += 1;
+        orc_sample_state(c, seed, env0 + (uint32_t)i, reset_count[i], qp, qv);
+        for (int k = 0; k < nq; k++) qpos[(size_t)nq * i + k] = qp[k];
+        for (int k = 0; k < nv; k++) qvel[(size_t)nv * i + k] = qv[k];
+        num_steps[i] = 0;
+    }
+}
+
 /* ------------------------------------------------------------------ batched CPU vec-env step */
 /* ------------------------------------------------------------------ MyBetaDist (distributions.py:6-38) on policy logits
  * alpha / beta = log(exp(clamp(x, -50, 50)) + 1) + 1 (:12-13), chunked alpha-first (:16); sample = Beta(alpha, beta) as
@@ -893,5 +933,20 @@ void orc_vector_step(int n, const OrcModel *models, int frame_skip, double *qpos
         truncated[i] = (uint8_t)orc_termination(st, ref, max_distance, num_steps[i], max_steps);
         rewards[i] = orc_reward(reward_id, st, ns, ac, num_steps[i], ref, max_distance);
         if (obs) orc_obs(obs_id, st, ns, ref, obs + (size_t)obs_stride * i);
+    }
+}
+
+/* `reps` consecutive vector_steps + reset_at round trips in one call (single-env configs: a Python call per step would
+ * time the interpreter, not the path).  Actions cycle through `actions` [nact][n][4]. */
+void orc_vector_step_repeat(int reps, int n, const OrcModel *models, int frame_skip, double *qpos, double *qvel, double *act,
+                            double *sens, int64_t *num_steps, const double *actions, int nact, const double *reference,
+                            int per_env_ref, int reward_id, int obs_id, double max_distance, int64_t max_steps, double *obs,
+                            int obs_stride, double *rewards, uint8_t *truncated, int nthreads, const OrcResetCfg *c,
+                            uint32_t seed, uint32_t env0, uint32_t *reset_count, int64_t *n_truncations) {
+    for (int r = 0; r < reps; r++) {
+        orc_vector_step(n, models, frame_skip, qpos, qvel, act, sens, num_steps, actions + (size_t)(r % nact) * n * 4, reference,
+                        per_env_ref, reward_id, obs_id, max_distance, max_steps, obs, obs_stride, rewards, truncated, nthreads);
+        for (int i = 0; i < n; i++) *n_truncations += truncated[i];
+        orc_reset_truncated(n, models[0].nq, models[0].nv, c, seed, env0, reset_count, truncated, qpos, qvel, num_steps);
     }
 }

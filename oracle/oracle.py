@@ -123,6 +123,15 @@ def lib():
                                       C.POINTER(C.c_int64), dp, dp, C.c_int, C.c_int, C.c_int,
                                       C.c_double, C.c_int64, dp, C.c_int, dp, C.POINTER(C.c_uint8), C.c_int]
         L.orc_max_threads.restype = C.c_int
+        L.orc_vector_step_repeat.argtypes = [C.c_int, C.c_int, C.POINTER(OrcModel), C.c_int, dp, dp, dp, dp, C.POINTER(C.c_int64), dp, C.c_int, dp,
+                                             C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, dp, C.c_int, dp, C.POINTER(C.c_uint8), C.c_int,
+                                             C.POINTER(OrcResetCfg), C.c_uint32, C.c_uint32, u32p, C.POINTER(C.c_int64)]
+        L.orc_vector_step_repeat.restype = None
+        L.orc_control_reference.argtypes = [dp, dp, dp]
+        L.orc_control_reference.restype = None
+        L.orc_reset_truncated.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(OrcResetCfg), C.c_uint32, C.c_uint32, u32p,
+                                          C.POINTER(C.c_uint8), dp, dp, C.POINTER(C.c_int64)]
+        L.orc_reset_truncated.restype = None
         _lib = L
     return _lib
 
@@ -301,6 +310,38 @@ class CpuVecEnv:
                               int(max_steps), _dp(obs), od, _dp(rew), trunc.ctypes.data_as(C.POINTER(C.c_uint8)),
                               int(nthreads))
         return obs, rew, trunc.astype(bool)
+
+    def step_repeat(self, reps, action_bank, reference, reward_id, obs_id, max_distance, max_steps, cfg, seed, env0, nthreads=0):
+        """`reps` x (vector_step + reset_at of the truncated envs) inside ONE C call; returns the number of truncations"""
+        if not hasattr(self, "reset_count"):
+            self.reset_count = np.zeros(self.n, dtype=np.uint32)
+        bank = np.ascontiguousarray(np.asarray(action_bank, dtype=np.float64).reshape(-1, self.n, 4))
+        reference = np.ascontiguousarray(np.asarray(reference, dtype=np.float64))
+        od = OBS_DIMS[obs_id] if (obs_id != 0 or self.nq == 9) else 29
+        obs, rew, trunc, cnt = np.zeros((self.n, od)), np.zeros(self.n), np.zeros(self.n, dtype=np.uint8), np.zeros(1, dtype=np.int64)
+        lib().orc_vector_step_repeat(int(reps), self.n, self.models, self.frame_skip, _dp(self.qpos), _dp(self.qvel), _dp(self.act), _dp(self.sens),
+                                     self.num_steps.ctypes.data_as(C.POINTER(C.c_int64)), _dp(bank), bank.shape[0], _dp(reference),
+                                     int(reference.ndim == 2), int(reward_id), int(obs_id), float(max_distance), int(max_steps), _dp(obs), od,
+                                     _dp(rew), trunc.ctypes.data_as(C.POINTER(C.c_uint8)), int(nthreads), C.byref(cfg), int(seed) & 0xFFFFFFFF,
+                                     int(env0) & 0xFFFFFFFF, self.reset_count.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                     cnt.ctypes.data_as(C.POINTER(C.c_int64)))
+        return int(cnt[0])
+
+    def reset_truncated(self, cfg, seed, env0, truncated):
+        """RLlib's reset_at() for every truncated env (BaseDroneEnv.py:334-351), reset stream per env like the CUDA path."""
+        if not hasattr(self, "reset_count"):
+            self.reset_count = np.zeros(self.n, dtype=np.uint32)
+        t = np.ascontiguousarray(truncated, dtype=np.uint8)
+        lib().orc_reset_truncated(self.n, self.nq, self.nv, C.byref(cfg), int(seed) & 0xFFFFFFFF, int(env0) & 0xFFFFFFFF,
+                                  self.reset_count.ctypes.data_as(C.POINTER(C.c_uint32)), t.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                  _dp(self.qpos), _dp(self.qvel), self.num_steps.ctypes.data_as(C.POINTER(C.c_int64)))
+
+
+def control_reference(reference, axes, start_pos):
+    """BaseDroneEnv.control_reference (:151-172) for one joystick sample `axes` = (x, y, z, yaw) after the sign flips."""
+    r = np.array(reference, dtype=np.float64)
+    lib().orc_control_reference(_dp(r), _dp(np.ascontiguousarray(axes, dtype=np.float64)), _dp(np.ascontiguousarray(start_pos, dtype=np.float64)))
+    return r
 
 
 def max_threads():

@@ -107,3 +107,19 @@ def test_protocol_replay(oracle):
         np.testing.assert_allclose(g["reset_obs"][t][idx], g["obs"][t][idx], atol=0)
     assert g["truncated"].any()
     assert (g["total_steps"] == 0).any()
+
+
+def test_control_reference_matches_reference(oracle):
+    """orc_control_reference vs BaseDroneEnv.control_reference (:151-172) run under stubs with a fake joystick
+    (tools/make_golden_r2.py): dead-zone edges, yaw wrap, clip - bit for bit"""
+    g = golden("control_reference.npz")
+    start, ref, last = g["start"], None, -1
+    moved = 0
+    for a, want, k in zip(g["axes"], g["reference"], g["seq_id"]):
+        if k != last:
+            ref, last = start.copy(), k
+        new = oracle.control_reference(ref, a, start[:3])
+        assert np.array_equal(new, want), (k, a, new, want)
+        moved += int(np.any(new[:3] != ref[:3]))
+        ref = new
+    assert 100 < moved < len(g["axes"])              # both branches of the dead zones are exercised

@@ -117,10 +117,10 @@ def test_rollout_runner_graph_equals_eager_and_replays_through_the_env():
     for mode in (False, True):
         env = mk()
         r = M.rollout.RolloutRunner(env, pol, horizon=T, seed=9, use_graph=mode)
-        if mode:
-            # the graph warm-up advanced the env by 3 steps; do the same in eager mode for comparability
-            pass
+        if not mode:
+            r.warm_up()                   # the graph capture runs the same 3 unrecorded steps first
         b = r.run()
+        assert env.total_steps == T + r.WARMUP_STEPS
         out[mode] = {k: v.clone() for k, v in b.items()}
         assert b["obs"].shape == (T + 1, n, 22) and b["actions"].shape == (T, n, 4) and b["truncated"].dtype == torch.uint8
         assert ((b["actions"] > 0) & (b["actions"] < 1)).all() and torch.isfinite(b["values"]).all() and torch.isfinite(b["action_logp"]).all()
@@ -130,16 +130,18 @@ def test_rollout_runner_graph_equals_eager_and_replays_through_the_env():
         # (ii) replay the recorded actions through a fresh env from the same reset
         env2 = mk()
         if mode:
-            continue                      # graph mode starts 3 warm-up steps later; the replay check runs on the eager rollout
-        obs0 = env2.reset_tensor().clone()
-        assert torch.equal(obs0, b["obs"][0])
+            continue                      # the replay check runs on the eager rollout
+        r2 = M.rollout.RolloutRunner(env2, pol, horizon=T, seed=9, use_graph=False)
+        r2.warm_up()                      # same start as the recorded rollout
+        assert torch.equal(r2._obs_cur, b["obs"][0])
         for t in range(T):
             o, rew, tr = env2.step_tensor(b["actions"][t])
             assert torch.equal(o, b["obs"][t + 1]) and torch.equal(rew, b["rewards"][t]) and torch.equal(tr, b["truncated"][t])
         env2.close()
         env.close()
-    # (i) graph vs eager: same policy, same seeds; the graph run is offset by its 3 warm-up steps, so compare distributions
-    assert abs(out[True]["actions"].mean().item() - out[False]["actions"].mean().item()) < 0.05
+    # (i) graph replay == eager stepping, bit for bit (same policy, seeds and warm-up steps)
+    for k in out[False]:
+        assert torch.equal(out[True][k], out[False][k]), k
 
 
 def test_umma_weight_packing_layout():
