@@ -440,6 +440,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every timed step from Python instead of replaying a CUDA graph")
+    ap.add_argument("--strict-deps", action="store_true", help="do not declare the replicas' inputs ready: every step touches its inputs only after the previous kernel has completed")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads / hot-L2 measurements")
     ap.add_argument("--fuse-sampling", action="store_true", help="c5, fused policy: sample inside the policy kernel (dsim_policy_forward_sample; measured slower at 524288 envs)")
     ap.add_argument("--policy-dtype", default="fused", choices=["fp32", "tf32", "bf16", "fused"],
@@ -486,7 +487,12 @@ def main():
     R = 1 if args.no_flush else min(32, max(2, -(-2 * 132_000_000 // per_replica) + 1))
     envs = [make_env(wl, n, (rank * R + r) * n, local_rank) for r in range(R)]
     env = envs[0]
+    # The replicas are independent env shards interleaved on one stream: the kernel queued right before a shard's step
+    # belongs to ANOTHER shard, so every shard may declare its inputs ready (dsim_set_inputs_ready) and the step kernel
+    # starts fetching its first pages while its predecessor drains.  --strict-deps measures without that promise.
+    overlap = R > 1 and not args.strict_deps
     for e in envs:
+        e.inputs_ready = overlap
         e.reset_tensor()
     nbank = 9            # coprime with the replica count: step i uses bank[i % nbank] on replica i % R, so every env sees a new action each step
     g = torch.Generator(device=dev)
@@ -609,6 +615,29 @@ def main():
 
     extras = {}
     if not args.no_extras and rank == 0:
+        # (0) the same graph of steps without the inputs-ready promise (what a single-shard policy -> step loop pays per step)
+        if graph is not None and overlap:
+            for e in envs:
+                e.inputs_ready = False
+            g2 = torch.cuda.CUDAGraph()
+            saved_axes2, axes = axes, None
+            with torch.cuda.graph(g2):
+                run_steps(G, envs)
+            axes = saved_axes2
+            for _ in range(20):
+                g2.replay()
+            torch.cuda.synchronize(dev)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(M):
+                g2.replay()
+            s1.record()
+            torch.cuda.synchronize(dev)
+            mss = s0.elapsed_time(s1) / (M * G)
+            extras["strict_deps"] = {"value": n / (mss * 1e-3), "ms_per_step": mss, "roofline_frac": wl["alg_bytes"] * n / (mss * 1e-3) / 1e9 / measured_peaks()[0],
+                                     "note": "same CUDA graph of steps, inputs_ready off: each step fetches its pages only after the previous kernel has completed"}
+            for e in envs:
+                e.inputs_ready = True
         # (a) one replica only: its ~40 MB working set stays L2-resident between steps, as in a tight rollout loop
         run_steps(5, envs[:1])
         torch.cuda.synchronize(dev)
@@ -676,6 +705,9 @@ def main():
                    "l2": (f"inputs larger than L2: {R} independent replicas of the batch stepped round-robin, {R * per_replica / 1e6:.0f} MB working set vs 126 MB L2"
                           if R > 1 else "not flushed (single replica)"),
                    "replicas": R,
+                   "inputs_ready": (("dsim_set_inputs_ready(1) on every replica: the kernel queued before a replica's step belongs to another replica, so the step "
+                                     "prefetches its first state / action pages before the programmatic-dependency wait (PDL); extras.strict_deps is the same run without it")
+                                    if overlap else "off: inputs are touched only after the previous kernel has completed"),
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps, "api": "dsim_step_host (C ABI) with pinned host buffers: one launch, the kernel's bulk loads / stores move actions and outputs over PCIe (zero-copy)",

@@ -14,11 +14,13 @@
  * precision == DSIM_FP64.  Per-env data lives in PAGES of 32 envs (one warp of the step kernel); a page of a buffer
  * with R rows is the contiguous block real[R][32], so ONE 1D bulk copy (TMA) moves a warp's whole working set:
  *     element (row r, env i)  =  base[(i / 32) * R * 32 + r * 32 + (i % 32)]          ("PAGED", R = page_rows)
- *   read-write page (R = 27):  rows 0-23 state = MuJoCo's qpos[9], qvel[8], act[4], sensordata[3] per drone
+ *   read-write page (R = 27):  rows 0-20 state = MuJoCo's qpos[9], qvel[8], act[4] per drone
  *           (BaseDroneEnv.py:367-375): 0-2 position OFFSET from start_pos[0:3] | 3-6 quat (w,x,y,z) | 7-8 hinge angles
- *           | 9-11 world linear velocity | 12-14 body angular velocity | 15-16 hinge rates | 17-20 `act` | 21-23 accelerometer;
- *           row 24 BaseDroneEnv.num_steps (integer of the width of `real`), row 25 running episode return,
- *           row 26 reset count (integer; Philox epoch of the env's reset stream)
+ *           | 9-11 world linear velocity | 12-14 body angular velocity | 15-16 hinge rates | 17-20 `act`;
+ *           row 21 BaseDroneEnv.num_steps (integer of the width of `real`), row 22 running episode return,
+ *           row 23 reset count (integer; Philox epoch of the env's reset stream);
+ *           rows 24-26 sensordata (accelerometer): written by every step, never read by one - the step kernel fetches
+ *           rows 0-23 only and stores all 27
  *   read-only page  (R = 19):  rows 0-12 compiled rigid-body constants, rows 13-18 raw drone_params
  *   setpoint page   (R = 4):   x, y, z offsets from start_pos and yaw (only read when per_env_reference)
  *   ld = num_envs rounded up to a multiple of 32.
@@ -31,15 +33,15 @@
 extern "C" {
 #endif
 
-#define DSIM_ABI_VERSION 2
+#define DSIM_ABI_VERSION 3
 
 enum { DSIM_OK = 0, DSIM_EINVAL = -1, DSIM_ECUDA = -2, DSIM_ENOMEM = -3, DSIM_EUNSUPPORTED = -4, DSIM_ESHAPE = -5 };
 enum { DSIM_FP32 = 0, DSIM_FP64 = 1 };
-enum { DSIM_NSTATE_ROWS = 24, DSIM_NCONST = 13, DSIM_NPARAM = 6, DSIM_MAX_OBS = 33 };
+enum { DSIM_NSTATE_ROWS = 21, DSIM_NCONST = 13, DSIM_NPARAM = 6, DSIM_MAX_OBS = 33 };
 
 /* buffer ids for dsim_buffer() */
 enum {
-    DSIM_BUF_STATE = 0,      /* real  PAGED 24 rows of the read-write page       data.qpos/qvel/act/sensordata */
+    DSIM_BUF_STATE = 0,      /* real  PAGED 21 rows of the read-write page       data.qpos/qvel/act */
     DSIM_BUF_NUM_STEPS = 1,  /* int   PAGED 1 row (int32 | int64 as `real`)      BaseDroneEnv.num_steps (:110) */
     DSIM_BUF_OBS = 2,        /* real  [N][obs_dim] policy-ready rows             vector_step()[0] */
     DSIM_BUF_REWARD = 3,     /* real  [N]                                        vector_step()[1] */
@@ -50,7 +52,8 @@ enum {
     DSIM_BUF_RESET_COUNT = 8,/* int   PAGED 1 row: Philox epoch of each env's reset stream */
     DSIM_BUF_STATES33 = 9,   /* real  [N][33|29] get_drone_states() rows, filled by dsim_compute_states */
     DSIM_BUF_EP_RETURN = 10, /* real  PAGED 1 row: running return of the current episode */
-    DSIM_BUF_STATS = 11      /* double[8]: sum_return, sum_length, n_episodes, n_nonfinite, n_near_ground, 0,0,0 */
+    DSIM_BUF_STATS = 11,     /* double[8]: sum_return, sum_length, n_episodes, n_nonfinite, n_near_ground, 0,0,0 */
+    DSIM_BUF_SENSORDATA = 12 /* real  PAGED 3 rows of the read-write page        data.sensordata (accelerometer) */
 };
 enum { DSIM_DT_F32 = 0, DSIM_DT_F64 = 1, DSIM_DT_I32 = 2, DSIM_DT_U8 = 3, DSIM_DT_U32 = 4, DSIM_DT_I64 = 5 };
 
@@ -122,6 +125,18 @@ int dsim_evaluate(DsimHandle *h, const void *actions_dev /* real [N][4] */, void
  * PCIe themselves (zero-copy).  Pageable buffers: staged H2D | kernel | D2H copies, pipelined over page ranges for N >= 65536. */
 int dsim_step_host(DsimHandle *h, const float *actions_host /*[N][4]*/, float *obs_host /*[N][obs_dim]*/,
                    float *reward_host /*[N]*/, uint8_t *truncated_host /*[N]*/, void *stream);
+
+/* Scheduling contract for callers that interleave several independent shards (handles) on one stream, e.g. double-buffered
+ * rollouts or this repo's bench (R replicas stepped round-robin).  ready != 0 promises, for every later dsim_step(h, actions,
+ * stream): the kernel queued just before it in `stream` (a) does not write `actions`, this handle's state or its setpoints,
+ * and (b) is either a step kernel of a handle that has inputs_ready set too, or a kernel launched without programmatic
+ * stream serialisation.  The step kernel then fetches its first state / action pages and runs the physics of its first page
+ * while that predecessor is still draining, and performs the programmatic-dependency wait just before its first store; it
+ * releases ITS dependents only after that wait, so an early-starting kernel knows that everything older than its
+ * predecessor has completed - the state this handle wrote R launches ago included.  Default 0 (strict): nothing an earlier
+ * kernel may have written is touched before the wait - what a single-shard policy -> step -> policy loop needs.
+ * Results are bit-identical either way. */
+int dsim_set_inputs_ready(DsimHandle *h, int ready);
 
 /* -- reference / setpoints: self.reference (:80), control_reference (:151-172) */
 int dsim_set_reference(DsimHandle *h, const double ref[4]);

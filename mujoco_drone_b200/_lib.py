@@ -11,17 +11,17 @@ LIB_PATH = os.environ.get("DSIM_LIB") or os.path.join(_HERE, "libdronesim_b200.s
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ESHAPE = 0, -1, -2, -3, -4, -5
 FP32, FP64 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 TRAJ_CIRCLE, TRAJ_STEP, TRAJ_RAMP = 0, 1, 2
 TILE = 32                     # envs per page (include/dronesim_b200.h: PAGED buffers)
 (BUF_STATE, BUF_NUM_STEPS, BUF_OBS, BUF_REWARD, BUF_TRUNCATED, BUF_PARAMS, BUF_CONSTS, BUF_REFERENCE,
- BUF_RESET_COUNT, BUF_STATES33, BUF_EP_RETURN, BUF_STATS) = range(12)
+ BUF_RESET_COUNT, BUF_STATES33, BUF_EP_RETURN, BUF_STATS, BUF_SENSORDATA) = range(13)
 DT_F32, DT_F64, DT_I32, DT_U8, DT_U32, DT_I64 = range(6)
 
 EXPORTS = [
     "dsim_abi_version", "dsim_create", "dsim_destroy", "dsim_last_error", "dsim_obs_dim", "dsim_regen_params",
     "dsim_set_params", "dsim_get_params", "dsim_get_consts", "dsim_reset_all", "dsim_reset_masked", "dsim_reset_at",
-    "dsim_forward", "dsim_zero_act", "dsim_step", "dsim_evaluate", "dsim_step_host", "dsim_set_reference", "dsim_control_reference",
+    "dsim_forward", "dsim_zero_act", "dsim_step", "dsim_evaluate", "dsim_step_host", "dsim_set_inputs_ready", "dsim_set_reference", "dsim_control_reference",
     "dsim_set_state", "dsim_get_state", "dsim_compute_states", "dsim_buffer", "dsim_stats", "dsim_sync",
     "dsim_launch_count", "dsim_kernel_info", "dsim_debug_timeline", "dsim_beta_policy", "dsim_trajectory_reference", "dsim_policy_blob_sizes", "dsim_policy_create", "dsim_policy_destroy", "dsim_policy_forward", "dsim_policy_forward_sample", "dsim_policy_error",
 ]
@@ -82,6 +82,7 @@ def load():
     L.dsim_evaluate.argtypes = [vp, vp, vp]
     L.dsim_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.dsim_set_reference.argtypes = [vp, dp]
+    L.dsim_set_inputs_ready.argtypes = [vp, C.c_int]
     L.dsim_control_reference.argtypes = [vp, vp, vp]
     L.dsim_set_state.argtypes = [vp, dp, dp, dp, C.POINTER(i32), vp]
     L.dsim_get_state.argtypes = [vp, dp, dp, dp, dp, C.POINTER(i32)]

@@ -45,5 +45,24 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_variant(name, defines, verbose=False):
+    """kernel-variant experiments (tools/sweep_variants.sh): mujoco_drone_b200/variants/<name>.so compiled with extra -D flags;
+    loaded through DSIM_LIB, never by default"""
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, name + ".so")
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building variant " + name)
+    return out
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:                       # python -m mujoco_drone_b200.build --variant name DEF1 DEF2=3 ...
+        k = sys.argv.index("--variant")
+        print(build_variant(sys.argv[k + 1], [a for a in sys.argv[k + 2:] if not a.startswith("--")], verbose="--verbose" in sys.argv))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -33,8 +33,8 @@ constexpr double kInertiaC = 0.4 * 0.01 * 0.02 * 0.02;   // solid sphere r = 0.0
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kMinVal = 1e-15;        // mjMINVAL
 
-// rows of the per-env state (include/dronesim_b200.h)
-enum { S_POS = 0, S_QUAT = 3, S_HINGE = 7, S_VEL = 9, S_OMEGA = 12, S_HVEL = 15, S_ACT = 17, S_ACC = 21, S_ROWS = 24 };
+// rows of the per-env state (include/dronesim_b200.h): qpos, qvel, act = 21 rows the step both reads and writes
+enum { S_POS = 0, S_QUAT = 3, S_HINGE = 7, S_VEL = 9, S_OMEGA = 12, S_HVEL = 15, S_ACT = 17, S_ROWS = 21 };
 // rows of the compiled constants
 enum { C_MB = 0, C_CZ, C_IBX, C_IBY, C_IBZ, C_MD, C_ZD, C_IDX, C_IDZ, C_FS, C_F, C_KQ, C_INVTAU, C_ROWS };
 
@@ -44,9 +44,11 @@ enum { C_MB = 0, C_CZ, C_IBX, C_IBY, C_IBZ, C_MD, C_ZD, C_IDX, C_IDZ, C_FS, C_F,
 // contiguous 1D bulk-copy (TMA, cp.async.bulk) between HBM and a warp's shared-memory slot; inside the slot every
 // row is a conflict-free 128-byte (FP32) line and each row is reached with an immediate offset from one base.
 constexpr int kTile = 32;
-// read-write page: MuJoCo state (qpos, qvel, act, sensordata) + BaseDroneEnv.num_steps + running episode return + the
-// env's reset count (Philox epoch of its reset stream: rides with the page so the reset path has no global round trip)
-enum { RW_NUM_STEPS = S_ROWS, RW_EP_RETURN = S_ROWS + 1, RW_RESET_COUNT = S_ROWS + 2, RW_ROWS = S_ROWS + 3 };
+// read-write page: MuJoCo state (qpos, qvel, act) + BaseDroneEnv.num_steps + running episode return + the env's reset
+// count (Philox epoch of its reset stream: rides with the page so the reset path has no global round trip) = the
+// RW_IN_ROWS rows a step LOADS; the sensordata rows (accelerometer) come last: a step overwrites them (mj_sensorAcc runs
+// in every substep) and never reads them, so they are stored with the page but not fetched (12 of 108 bytes per env)
+enum { RW_NUM_STEPS = S_ROWS, RW_EP_RETURN = S_ROWS + 1, RW_RESET_COUNT = S_ROWS + 2, RW_IN_ROWS = S_ROWS + 3, S_ACC = RW_IN_ROWS, RW_ROWS = RW_IN_ROWS + 3 };
 // read-only page: compiled rigid-body constants + raw drone_params (rewritten only by regen / set_params)
 enum { RO_CONSTS = 0, RO_PARAMS = C_ROWS, RO_ROWS = C_ROWS + 6 };
 enum { REF_ROWS = 4 };                        // per-env setpoint page (x, y, z offsets from start_pos, yaw)

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const KParams<T> p, int
     const EnvConsts<T> c = load_consts(p, ro_col, p.per_env_consts != 0);
     const T ctrl[4] = {T(0), T(0), T(0), T(0)};
     substep<T, PEND, false>(s, c, ctrl, p.h);
-    col[21 * kTile] = s.acc.x; col[22 * kTile] = s.acc.y; col[23 * kTile] = s.acc.z;
+    col[S_ACC * kTile] = s.acc.x; col[(S_ACC + 1) * kTile] = s.acc.y; col[(S_ACC + 2) * kTile] = s.acc.z;
     if (refresh_obs) {
         V3<T> ref_off; T ref_yaw; double ref64[3];
         load_ref(p, p.refp ? p.refp + page_elem(REF_ROWS, 0, i) : nullptr, ref_off, ref_yaw, ref64, p.refp != nullptr);
@@ -186,6 +186,7 @@ struct DsimHandle {
     double h;
     int first_reset_done;
     int ro_dirty;                      // a kernel that rewrote the read-only pages was queued since the last step
+    int inputs_ready;                  // dsim_set_inputs_ready
     cudaStream_t hs[3];                // host entry point: copy-in, compute, copy-out streams (created on first use)
     cudaEvent_t ev_in[kHostChunks], ev_k[kHostChunks], ev_a, ev_b, ev_c;
     int host_pipeline_ready;
@@ -256,6 +257,7 @@ template <typename T> static KParams<T> make_params(const DsimHandle *h, const v
     p.seed = c.seed; p.env_base = (unsigned)c.env_id_offset;
     p.timeline = h->timeline; p.ticket = h->ticket;
     p.early_ro = h->ro_dirty ? 0 : 1;
+    p.early_in = h->inputs_ready ? 1 : 0;
     return p;
 }
 
@@ -326,6 +328,14 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
         if (e2 != cudaSuccess) { fail(nullptr, e2 == cudaErrorMemoryAllocation ? DSIM_ENOMEM : DSIM_ECUDA, "allocation failed: %s", cudaGetErrorString(e2)); dsim_destroy(h); return e2 == cudaErrorMemoryAllocation ? DSIM_ENOMEM : DSIM_ECUDA; } \
     } while (0)
     if ((e = cudaSetDevice(device)) != cudaSuccess) { delete h; return fail(nullptr, DSIM_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); }
+    if (const char *mb = getenv("DSIM_L2_PERSIST_MB")) {      // experiment knob: L2 set-aside for the evict_last (read-only page) lines
+        int maxb = 0;
+        cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, device);
+        size_t want = (size_t)atoi(mb) << 20;
+        if (want > (size_t)maxb) want = (size_t)maxb;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        if (getenv("DSIM_VERBOSE")) fprintf(stderr, "dsim: persisting L2 set-aside %zu MB (max %d MB)\n", want >> 20, maxb >> 20);
+    }
     const size_t ld = h->ld, n = h->n, rs = h->rs;
     ALLOC(h->rw, (size_t)RW_ROWS * ld * rs);
     ALLOC(h->ro, (size_t)RO_ROWS * ld * rs);
@@ -488,7 +498,8 @@ extern "C" int dsim_reset_at(DsimHandle *h, int index, void *stream) {
 extern "C" int dsim_zero_act(DsimHandle *h, void *stream) {
     if (!h) return DSIM_EINVAL;
     CK(cudaSetDevice(h->device));
-    for (int r = S_ACT; r < S_ROWS; r++) {                                   // act + sensordata of a fresh MjData
+    for (int r = S_ACT; r < RW_ROWS; r++) {                                  // act + sensordata of a fresh MjData
+        if (r >= S_ROWS && r < S_ACC) continue;
         if (h->rs == 4) fill_row_kernel<float><<<(h->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->n, (float *)h->rw, RW_ROWS, r, 0.0f);
         else fill_row_kernel<double><<<(h->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->n, (double *)h->rw, RW_ROWS, r, 0.0);
         h->launches++;
@@ -541,7 +552,11 @@ template <typename T> static cudaError_t launch_step(DsimHandle *h, const KParam
     const unsigned smem = kp.smem_per_slot * kStages * kStepWarps;
     const int pages = kp.npages - kp.page0;
     if (!h->cfg.pendulum) return launch_one(h, step_kernel<T, false, -1, -1>, smem, st, &kp, pages);
+#ifdef DSIM_TL_ALL
+    if (std::is_same<T, float>::value && !kp.eval_only) {
+#else
     if (std::is_same<T, float>::value && !kp.eval_only && !kp.timeline) {   // specialised instantiations: plain steps only
+#endif
         const int o = kp.obs_id, r = kp.reward_id;
         const int cfg = (kp.per_env_consts ? 1 : 0) | (kp.refp ? 2 : 0) | (kp.frame_skip == 1 ? 4 : 0);
         // BASELINE configs 4 / 5 (per-env randomised parameters), 3 (moving per-env setpoints), 2 (one parameter set)
@@ -697,6 +712,12 @@ extern "C" int dsim_step_host(DsimHandle *h, const float *actions_host, float *o
     CK(cudaEventRecord(h->ev_b, h->hs[1]));
     CK(cudaStreamWaitEvent(st, h->ev_b, 0));
     CK(cudaStreamSynchronize(h->hs[1]));
+    return DSIM_OK;
+}
+
+extern "C" int dsim_set_inputs_ready(DsimHandle *h, int ready) {
+    if (!h) return DSIM_EINVAL;
+    h->inputs_ready = ready ? 1 : 0;
     return DSIM_OK;
 }
 
@@ -860,6 +881,7 @@ extern "C" int dsim_buffer(DsimHandle *h, int id, void **ptr, int64_t *rows, int
     case DSIM_BUF_TRUNCATED: *ptr = h->trunc; *rows = 1; *cols = n; *ld = L; *dtype = DSIM_DT_U8; break;
     case DSIM_BUF_RESET_COUNT: *ptr = rw + RW_RESET_COUNT * row_bytes; *rows = 1; *cols = n; *ld = L; *dtype = idt; *page_rows = RW_ROWS; break;
     case DSIM_BUF_STATES33: *ptr = h->states33; *rows = n; *cols = h->state_width; *ld = h->state_width; *dtype = rdt; break;
+    case DSIM_BUF_SENSORDATA: *ptr = rw + S_ACC * row_bytes; *rows = 3; *cols = n; *ld = L; *dtype = rdt; *page_rows = RW_ROWS; break;
     case DSIM_BUF_STATS: *ptr = h->stats; *rows = 1; *cols = 8; *ld = 8; *dtype = DSIM_DT_F64; break;
     default: return fail(h, DSIM_EINVAL, "unknown buffer id%s", "");
     }

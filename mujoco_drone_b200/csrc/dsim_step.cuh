@@ -53,14 +53,38 @@ DSIM_DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// L2 eviction priorities for the bulk copies (createpolicy): the read-only pages (compiled constants + raw parameters, 76 B
+// per env) are the only data a step re-reads unchanged next step, so they are fetched evict_last and stay in the 126 MB L2
+// across steps even when the streaming data (state pages, actions, observations: evict_first) is far larger than L2 -
+// at 524288 envs the 40 MB of constants stay resident while 170 MB stream past them each step.
+#ifndef DSIM_L2HINT
+#define DSIM_L2HINT 1
+#endif
+DSIM_DEV uint64_t l2_policy_keep() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+DSIM_DEV uint64_t l2_policy_stream() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
 // HBM -> shared, completion counted in bytes on the mbarrier.  size % 16 == 0, both addresses 16-byte aligned.
 DSIM_DEV void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+DSIM_DEV void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+#if DSIM_L2HINT
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+#else
+    (void)policy; bulk_g2s(smem_dst, gmem_src, bytes, bar);
+#endif
+}
 // shared -> HBM, tracked by the issuing thread's bulk async-group
 DSIM_DEV void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+DSIM_DEV void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes, uint64_t policy) {
+#if DSIM_L2HINT
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
+#else
+    (void)policy; bulk_s2g(gmem_dst, smem_src, bytes);
+#endif
 }
 DSIM_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DSIM_DEV void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -83,6 +107,8 @@ template <typename T> struct KParams {
     int per_env_consts, auto_reset, obs_id, reward_id, obs_dim, frame_skip, max_steps;
     int eval_only;            // 1: termination / reward / obs of the CURRENT state, nothing advanced or stored
     int early_ro;             // 1: the read-only rows may be fetched before the dependency wait (no kernel that writes them is in flight)
+    int early_in;             // 1: so may the state / action / setpoint rows (dsim_set_inputs_ready: the caller guarantees that the kernel
+                              //    running ahead of this one in the stream does not write them - e.g. it steps another shard)
     unsigned smem_per_slot;   // bytes of one page slot (each warp owns kStages of them)
     T h, max_distance_t;
     T ref_off[3], ref_yaw, start_t[3];
@@ -116,7 +142,7 @@ template <typename T> DSIM_DEV EnvState<T> load_state(const T *col) {
     s.hvx = col[15 * kTile]; s.hvy = col[16 * kTile];
     #pragma unroll
     for (int k = 0; k < 4; k++) s.act[k] = col[(S_ACT + k) * kTile];
-    s.acc = mk(col[21 * kTile], col[22 * kTile], col[23 * kTile]);
+    s.acc = mk(col[S_ACC * kTile], col[(S_ACC + 1) * kTile], col[(S_ACC + 2) * kTile]);
     return s;
 }
 template <typename T> DSIM_DEV void store_state(T *col, const EnvState<T> &s) {
@@ -128,7 +154,7 @@ template <typename T> DSIM_DEV void store_state(T *col, const EnvState<T> &s) {
     col[15 * kTile] = s.hvx; col[16 * kTile] = s.hvy;
     #pragma unroll
     for (int k = 0; k < 4; k++) col[(S_ACT + k) * kTile] = s.act[k];
-    col[21 * kTile] = s.acc.x; col[22 * kTile] = s.acc.y; col[23 * kTile] = s.acc.z;
+    col[S_ACC * kTile] = s.acc.x; col[(S_ACC + 1) * kTile] = s.acc.y; col[(S_ACC + 2) * kTile] = s.acc.z;
 }
 template <typename T> DSIM_DEV EnvConsts<T> consts_from(const T v[C_ROWS]) {
     EnvConsts<T> c;
@@ -272,20 +298,21 @@ template <typename T> DSIM_DEV void load_action(const T *row, T a[4]) {
 }
 
 // lane 0: arm the slot's mbarrier and start the page loads HBM -> slot
-// `parts`: bit 0 = arm the barrier with the page's total byte count and load the READ-ONLY rows (compiled constants + raw
-// parameters: never written by a step kernel), bit 1 = load everything an earlier kernel of the stream may have written
-// (state rows, the policy's actions, the setpoint rows).  3 = the whole page.
-template <typename T> DSIM_DEV void issue_page_loads(const KParams<T> &p, int page, T *slot, uint64_t *bar, int parts, bool pec, bool pref) {
-    constexpr uint32_t rwb = RW_ROWS * kTile * sizeof(T), rob = RO_ROWS * kTile * sizeof(T), rfb = REF_ROWS * kTile * sizeof(T);
+// `parts`: bit 2 = arm the barrier with the page's total byte count, bit 0 = load the READ-ONLY rows (compiled constants +
+// raw parameters: never written by a step kernel), bit 1 = load everything an earlier kernel of the stream may have
+// written (state rows, the policy's actions, the setpoint rows).  7 = the whole page.
+// `all_rows`: also fetch the sensordata rows (evaluate-only launches emit the STORED accelerometer; a step recomputes it)
+template <typename T> DSIM_DEV void issue_page_loads(const KParams<T> &p, int page, T *slot, uint64_t *bar, int parts, bool pec, bool pref, bool all_rows,
+                                                     uint64_t pol_keep, uint64_t pol_stream) {
+    constexpr uint32_t rob = RO_ROWS * kTile * sizeof(T), rfb = REF_ROWS * kTile * sizeof(T);
+    const uint32_t rwb = (all_rows ? RW_ROWS : RW_IN_ROWS) * kTile * (uint32_t)sizeof(T);
     const uint32_t acb = (uint32_t)min(kTile, p.n - page * kTile) * 4u * (uint32_t)sizeof(T);   // the policy's [n][4] action rows of this page
-    if (parts & 1) {
-        mbar_arrive_expect_tx(bar, rwb + acb + (pec ? rob : 0u) + (pref ? rfb : 0u));
-        if (pec) bulk_g2s(slot + RW_ROWS * kTile, p.ro + (size_t)page * (RO_ROWS * kTile), rob, bar);
-    }
+    if (parts & 4) mbar_arrive_expect_tx(bar, rwb + acb + (pec ? rob : 0u) + (pref ? rfb : 0u));
+    if ((parts & 1) && pec) bulk_g2s(slot + RW_ROWS * kTile, p.ro + (size_t)page * (RO_ROWS * kTile), rob, bar, pol_keep);
     if (parts & 2) {
-        bulk_g2s(slot, p.rw + (size_t)page * (RW_ROWS * kTile), rwb, bar);
-        bulk_g2s(slot + kSlotActOff, p.actions + (size_t)page * (kTile * 4), acb, bar);
-        if (pref) bulk_g2s(slot + (RW_ROWS + RO_ROWS) * kTile, p.refp + (size_t)page * (REF_ROWS * kTile), rfb, bar);
+        bulk_g2s(slot, p.rw + (size_t)page * (RW_ROWS * kTile), rwb, bar, pol_stream);
+        bulk_g2s(slot + kSlotActOff, p.actions + (size_t)page * (kTile * 4), acb, bar, pol_stream);
+        if (pref) bulk_g2s(slot + (RW_ROWS + RO_ROWS) * kTile, p.refp + (size_t)page * (REF_ROWS * kTile), rfb, bar, pol_stream);
     }
 }
 
@@ -310,7 +337,11 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     const bool pec = CFG >= 0 ? (CFG & 1) != 0 : (p.per_env_consts != 0);
     const bool pref = CFG >= 0 ? (CFG & 2) != 0 : (p.refp != nullptr);
     const int frame_skip = (CFG >= 0 && (CFG & 4)) ? 1 : p.frame_skip;
+#ifdef DSIM_TL_ALL                        // instrumented experiment builds: the debug timeline stays in the specialised kernels too
+    unsigned long long *const timeline = p.timeline;
+#else
     unsigned long long *const timeline = kPlain ? nullptr : p.timeline;
+#endif
     const bool eval_only = kPlain ? false : (p.eval_only != 0);
     // warp-uniform values (warp index, page numbers) go through redux.sync: the compiler then knows they are uniform, keeps
     // the page / slot address arithmetic in the uniform datapath and hands the bulk-copy instructions uniform registers
@@ -324,17 +355,74 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     // touched after griddepcontrol.wait.
     unsigned long long t_entry = 0;
     if (timeline) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // measured variants (tools/gpu_r2e.sh, C4, us per step, inputs-ready / strict): both static pages fetched up front
+    // (DSIM_EARLY2) 10.48 / 11.41 against 10.00 / 11.14 without - the second wave delays the first pages; page-less warp slot
+    // rotating over the schedulers (DSIM_DEAL) 10.48 / 11.41 against 10.40 / 11.31; dependents released after the wait in
+    // strict mode too: 11.1-11.4 against 10.6 with the release at entry.  Defaults = the fastest of each.
+#ifndef DSIM_EARLY2
+#define DSIM_EARLY2 0
+#endif
+#ifndef DSIM_LATEWAIT
+#define DSIM_LATEWAIT 1
+#endif
+#ifndef DSIM_DEAL
+#define DSIM_DEAL 0
+#endif
+    // Strict mode releases the dependent kernel at entry (its CTAs are scheduled as this grid's CTAs retire; it touches
+    // nothing before its own wait).  Inputs-ready mode releases it only AFTER this kernel's own wait: a kernel that starts
+    // early then knows that everything up to its predecessor's predecessor has completed, which is what makes its early
+    // loads of state written R launches ago safe by construction.
+    const bool trigger_late = p.early_in != 0;
+    if (!trigger_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int my_pages = p.npages - p.page0;                       // pages of THIS launch
     const bool has_work = wid < my_pages;
     unsigned char *wslots = smem_raw + (size_t)warp * kStages * p.smem_per_slot;
+    const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+    // Page assignment.  The first two pages of a warp are static: page `wid`, then one of the next `nwarps` pages, dealt so
+    // that every CTA gets the same number of second pages (+-1) and the page-less warp slot rotates with the CTA index
+    // (warp slot w of a CTA lives on scheduler w of its SM: a fixed page-less slot would leave one of the four schedulers
+    // with half the work of the others).
+    int page = p.page0 + wid;
+#ifdef DSIM_DYN2      // experiment: second pages are claimed from a counter when the first page has landed (early warps take them)
+    int next = p.npages;
+    bool first_iter = my_pages > nwarps;
+#elif DSIM_DEAL
+    int next = p.page0 + nwarps + ((warp + (int)blockIdx.x) & (kStepWarps - 1)) * (int)gridDim.x + (int)blockIdx.x;
+#else
+    int next = p.page0 + nwarps + warp * (int)gridDim.x + (int)blockIdx.x;
+#endif
+    // Loads that may start BEFORE the dependency wait: the read-only rows (`early_ro`), and with dsim_set_inputs_ready also
+    // the state / action / setpoint rows (`early_in`) - of both static pages: each warp owns two slots and both are free.
+    const int pre = (p.early_ro ? 1 : 0) | (p.early_in ? 2 : 0);
+    bool next_issued = false;
     if (has_work && lane == 0) {
         #pragma unroll
         for (int k = 0; k < kStages; k++) mbar_init(&s_bar[warp][k], 1);
-        if (p.early_ro) issue_page_loads(p, p.page0 + wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0], 1, pec, pref);
+        issue_page_loads(p, page, reinterpret_cast<T *>(wslots), &s_bar[warp][0], 4 | pre, pec, pref, eval_only, pol_keep, pol_stream);
+#if DSIM_EARLY2 && !defined(DSIM_DYN2)
+        if (next < p.npages)
+            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + p.smem_per_slot), &s_bar[warp][1], 4 | pre, pec, pref, eval_only, pol_keep, pol_stream);
+#endif
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (!has_work) return;                                         // warps are autonomous: no CTA-wide barrier below
+#if DSIM_EARLY2 && !defined(DSIM_DYN2)
+    next_issued = next < p.npages;
+#endif
+    // With inputs_ready the wait moves to just before this warp's first store (the physics of the first page overlaps the
+    // tail of the kernel ahead); otherwise nothing an earlier kernel may have written is touched before it.  The dependents
+    // are released only AFTER the wait: a kernel that starts early therefore knows that everything before its predecessor
+    // has completed (the early loads of the inputs-ready mode rely on exactly that).
+    bool waited = !(DSIM_LATEWAIT && p.early_in);
+    if (waited) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (trigger_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
+    if (!has_work) {
+        if (!waited) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        }
+        return;                                                    // warps are autonomous: no CTA-wide barrier below
+    }
     int tl_k = 1;
     auto stamp = [&]() {
         if (timeline && lane == 0 && tl_k < 8) {
@@ -344,10 +432,14 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         }
     };
     if (timeline && lane == 0) timeline[(size_t)wid * 8] = t_entry;
-    stamp();                                                       // [1] dependency wait passed                                   // warps are autonomous: no CTA-wide barrier below
+    stamp();                                                       // [1] dependency wait passed (inputs-ready mode: prologue done, the wait comes later)
     const int obs_id = OBS >= 0 ? OBS : p.obs_id, reward_id = REW >= 0 ? REW : p.reward_id;
     const int D = DC > 0 ? DC : p.obs_dim;
-    if (lane == 0) issue_page_loads(p, p.page0 + wid, reinterpret_cast<T *>(wslots), &s_bar[warp][0], p.early_ro ? 2 : 3, pec, pref);
+    if (lane == 0 && pre != 3) {
+        issue_page_loads(p, page, reinterpret_cast<T *>(wslots), &s_bar[warp][0], 3 & ~pre, pec, pref, eval_only, pol_keep, pol_stream);
+        if (next_issued)
+            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + p.smem_per_slot), &s_bar[warp][1], 3 & ~pre, pec, pref, eval_only, pol_keep, pol_stream);
+    }
     __syncwarp();                                                  // barrier init visible to the waiting lanes
     unsigned parity = 0;                                           // bit b: phase of this warp's barrier b
     int buf = 0;
@@ -371,8 +463,6 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         if (lane == 0 && tk == last_ticket) *p.ticket = 0u;
         return __reduce_max_sync(0xffffffffu, lane == 0 ? p.page0 + 2 * nwarps + (int)tk : 0);
     };
-    int page = p.page0 + wid;
-    int next = p.page0 + nwarps + warp * (int)gridDim.x + (int)blockIdx.x;
     #pragma unroll 1
     while (page < p.npages) {
         const int i = page * kTile + lane;
@@ -382,6 +472,17 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         mbar_wait(&s_bar[warp][buf], (parity >> buf) & 1u);
         parity ^= 1u << buf;
         stamp();                                                   // [2], [4]: page landed
+#ifdef DSIM_DYN2
+        if (first_iter) {
+            first_iter = false;
+            unsigned tk = 0;
+            if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(tk) : "l"(p.ticket + 32));
+            const int cand = __reduce_max_sync(0xffffffffu, lane == 0 ? p.page0 + nwarps + (int)tk : 0);
+            const int second_pages = min(my_pages - nwarps, nwarps);
+            if (lane == 0 && (int)tk == nwarps - 1) p.ticket[32] = 0u;             // every warp draws exactly once: the last draw re-zeroes
+            next = ((int)(cand - p.page0 - nwarps) < second_pages) ? cand : p.npages;
+        }
+#endif
 
         // ---- physics
         T *col = s_rw + lane;
@@ -390,9 +491,9 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         EnvState<T> s = load_state(col);
         // ---- prefetch the next page into the other slot.  Its previous contents left with the bulk stores issued at the
         // end of the previous iteration; their shared-memory reads complete within a few hundred cycles.
-        if (lane == 0 && next < p.npages) {
+        if (lane == 0 && next < p.npages && !next_issued) {
             bulk_wait_read();
-            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + (size_t)(buf ^ 1) * p.smem_per_slot), &s_bar[warp][buf ^ 1], 3, pec, pref);
+            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + (size_t)(buf ^ 1) * p.smem_per_slot), &s_bar[warp][buf ^ 1], 7, pec, pref, eval_only, pol_keep, pol_stream);
         }
 
         {
@@ -444,6 +545,11 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             ObsWriter<T, 1> w; w.base = s_obs + lane * D; w.stride = 1;
             emit_obs<T, PEND>(obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
         }
+        if (!waited) {                                              // inputs-ready mode: first store of this warp (warp-uniform)
+            waited = true;
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        }
         if (active) {
             p.reward[i] = rew;
             p.trunc[i] = trunc ? 1 : 0;
@@ -476,8 +582,8 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         T *gobs = p.obs + (size_t)page * kTile * D;
         const bool obs_bulk = (obs_bytes & 15u) == 0;              // always true for full pages
         if (lane == 0) {
-            if (!eval_only) bulk_s2g(p.rw + (size_t)page * (RW_ROWS * kTile), s_rw, RW_ROWS * kTile * sizeof(T));
-            if (obs_bulk) bulk_s2g(gobs, s_obs, obs_bytes);
+            if (!eval_only) bulk_s2g(p.rw + (size_t)page * (RW_ROWS * kTile), s_rw, RW_ROWS * kTile * sizeof(T), pol_stream);
+            if (obs_bulk) bulk_s2g(gobs, s_obs, obs_bytes, pol_stream);
             if (obs_bulk && p.obs_host) bulk_s2g(p.obs_host + (size_t)page * kTile * D, s_obs, obs_bytes);
             bulk_commit();
         }
@@ -490,6 +596,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             }
         page = next;
         next = claim(drawn);
+        next_issued = false;
         buf ^= 1;
     }
     if (lane == 0) bulk_wait_read();                               // the slots must outlive the bulk reads

@@ -121,6 +121,7 @@ class BaseDroneEnv(_VectorEnv):
         self.per_env_reference = bool(g('per_env_reference', False))
         self.env_id_offset = int(g('env_id_offset', 0))
         self.round_precision = bool(g('round_precision', True))
+        self._inputs_ready = bool(g('inputs_ready', False))
         self._regen_epoch = 0
         # seed: reference uses config.get('worker_index', -1) + 1 + seed (BaseDroneEnv.py:113, Q5)
         self.seed_value = int(g('worker_index', -1) + 1 + g('seed', 1))
@@ -170,6 +171,8 @@ class BaseDroneEnv(_VectorEnv):
         if rc != _lib.OK:
             raise _lib.DsimError(rc, (L.dsim_last_error(None) or b"").decode())
         self._h = h
+        if self._inputs_ready:
+            self.inputs_ready = True
         self._np_dtype = np.float64 if cfg.precision == _lib.FP64 else np.float32
         self.obs_dim = L.dsim_obs_dim(self.OBS_ID, cfg.pendulum)
         self._views = {}
@@ -244,7 +247,7 @@ class BaseDroneEnv(_VectorEnv):
 
     @property
     def state_tensor(self):
-        """[24, npages, 32] zero-copy view of the state rows (see `tensor`)."""
+        """[21, npages, 32] zero-copy view of the state rows qpos / qvel / act (see `tensor`; sensordata: BUF_SENSORDATA)."""
         return self.tensor(_lib.BUF_STATE)
 
     @property
@@ -320,6 +323,17 @@ class BaseDroneEnv(_VectorEnv):
         out = np.zeros(8)
         self._ck(self._L.dsim_stats(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), int(reset)))
         return dict(sum_return=out[0], sum_length=out[1], n_episodes=out[2], n_nonfinite=out[3], n_near_ground=out[4])
+
+    @property
+    def inputs_ready(self):
+        """dsim_set_inputs_ready: promise that the kernel queued right before every step_tensor() call does not write this
+        env's actions / state / setpoints (several independent env shards interleaved on one stream)."""
+        return self._inputs_ready
+
+    @inputs_ready.setter
+    def inputs_ready(self, value):
+        self._inputs_ready = bool(value)
+        self._ck(self._L.dsim_set_inputs_ready(self._h, int(self._inputs_ready)))
 
     # ------------------------------------------------------------------ reference attributes
     @property

@@ -87,6 +87,38 @@ def make_rma_full(num_states=16, num_params=6, num_actions=4, param_embed_dim=8,
     return RMAFull()
 
 
+# the reference module's state_dict names (RLlib SlimFC keeps its nn.Linear at `_model.0`) -> this module's
+_REF_KEYS = {"param_encoder.0._model.0": "param_encoder.0", "param_encoder.1._model.0": "param_encoder.2",
+             "_hidden_layers.0._model.0": "hidden.0", "_hidden_layers.1._model.0": "hidden.2", "_hidden_layers.2": "hidden.4",
+             "_logits.0._model.0": "logits.0", "_logits.1._model.0": "logits.2",
+             "_value_branch.0._model.0": "value_branch.0", "_value_branch.1._model.0": "value_branch.2", "_value_branch.2._model.0": "value_branch.4"}
+
+
+def load_reference_state_dict(model, state_dict):
+    """Copy a checkpoint of the REFERENCE's RMA_full (models/PPO/RMA/RMA_model.py:48-71; keys as saved by RLlib, e.g.
+    `_hidden_layers.0._model.0.weight`) into an RMAFull built by make_rma_full; the adaptation module (unused with
+    train_adaptation=False) is skipped.  Values may be torch tensors or numpy arrays."""
+    import torch
+    own = model.state_dict()
+    seen = set()
+    for k, v in state_dict.items():
+        if k.startswith("adaptation_module"):
+            continue
+        prefix, leaf = k.rsplit(".", 1)
+        if prefix not in _REF_KEYS:
+            raise KeyError(f"unexpected key in the reference state_dict: {k}")
+        name = _REF_KEYS[prefix] + "." + leaf
+        t = torch.as_tensor(v)
+        if tuple(own[name].shape) != tuple(t.shape):
+            raise ValueError(f"{k}: shape {tuple(t.shape)} does not match {tuple(own[name].shape)}")
+        own[name].copy_(t)
+        seen.add(name)
+    missing = [k for k in own if k not in seen]
+    if missing:
+        raise KeyError(f"reference state_dict lacks {missing}")
+    return model
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # Fused tcgen05 inference of RMA_full (csrc/dsim_policy_mlp.cu, C ABI dsim_policy_*)
 

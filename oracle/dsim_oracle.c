@@ -950,3 +950,12 @@ void orc_vector_step_repeat(int reps, int n, const OrcModel *models, int frame_s
         orc_reset_truncated(n, models[0].nq, models[0].nv, c, seed, env0, reset_count, truncated, qpos, qvel, num_steps);
     }
 }
+
+/* mj_step over ONE MjData that holds n drones (drone-major qpos / qvel / act / ctrl / sensordata, BaseDroneEnv.py:367-375):
+ * what `mujoco.mj_step(model, data, nstep)` does for the reference's N-drone model, single-threaded like MuJoCo. */
+void orc_step_batch(int n, const OrcModel *models, double *qpos, double *qvel, double *act, const double *ctrl, double *sens, int nstep) {
+    for (int i = 0; i < n; i++) {
+        const OrcModel *m = &models[i];
+        orc_step(m, qpos + (size_t)m->nq * i, qvel + (size_t)m->nv * i, act + 4 * (size_t)i, ctrl + 4 * (size_t)i, sens + 3 * (size_t)i, nstep);
+    }
+}

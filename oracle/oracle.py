@@ -127,6 +127,8 @@ def lib():
                                              C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, dp, C.c_int, dp, C.POINTER(C.c_uint8), C.c_int,
                                              C.POINTER(OrcResetCfg), C.c_uint32, C.c_uint32, u32p, C.POINTER(C.c_int64)]
         L.orc_vector_step_repeat.restype = None
+        L.orc_step_batch.argtypes = [C.c_int, C.POINTER(OrcModel), dp, dp, dp, dp, dp, C.c_int]
+        L.orc_step_batch.restype = None
         L.orc_control_reference.argtypes = [dp, dp, dp]
         L.orc_control_reference.restype = None
         L.orc_reset_truncated.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(OrcResetCfg), C.c_uint32, C.c_uint32, u32p,

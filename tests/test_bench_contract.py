@@ -24,7 +24,13 @@ def test_bench_native_arm_contract():
               "config", "e2e", "gpu_launches", "roofline", "clocks"):
         assert k in d, k
     assert d["metric"] == "env-steps/sec" and d["n_gpus"] == 1 and d["steps"] == 40 and d["scaling"] == "weak" and d["vs_baseline"] is None
-    assert d["value"] > 0 and d["gpu_launches"] == 40 and "workload" in d["config"]
+    # --steps is a lower bound of the timed region: the graph of steps is replayed until the event window is >= 30 ms
+    ts = d["config"]["timed_steps"]
+    assert d["value"] > 0 and ts >= 40 and d["gpu_launches"] == ts and "workload" in d["config"] and "CUDA graph" in d["config"]["launch"]
+    assert d["config"]["timed_window_ms"] >= 25.0 and abs(d["ms_per_step"] - d["config"]["timed_window_ms"] / ts) < 1e-9
+    assert d["clocks"]["samples"] >= 10
+    er = d["e2e"]["roofline"]
+    assert er["bound"] == "pcie" and er["peak"] > 0 and 0 < er["frac"] < 1.5
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 8192 * 16 and d["e2e"]["d2h_bytes_per_step"] == 8192 * (4 * 22 + 5)
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9

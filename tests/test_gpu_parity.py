@@ -140,7 +140,7 @@ def test_obs_golden(precision):
             continue
         env = _mk(name, num_drones=n, precision=precision, reference=list(g["reference"]), start_pos=[0, 0, 15, 0])
         _set(env, qpos, qvel, S[:, 19:23], S[:, 27:33])
-        env.write_rows(M._lib.BUF_STATE, 21, S[:, 16:19].T)                 # inject sensordata
+        env.write_rows(M._lib.BUF_SENSORDATA, 0, S[:, 16:19].T)            # inject sensordata
         obs, _, _ = env.evaluate_tensor(torch.zeros((n, 4), device="cuda"))
         out = obs.cpu().numpy().astype(np.float64)
         ref = g["out_" + name]
