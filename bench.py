@@ -30,7 +30,10 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[3]: RMA domain randomisation, 1M envs over 8 GPUs = 131072 per GPU (train_RMA.py:66-75)
     "c4": dict(cls="LocalFrameRPYParamsEnv", reward="distance_energy_reward", envs_per_gpu=131072, alg_bytes=104 + 94 + 88 + 24,
-               traffic=26.25e6 + 0.01e6, traffic_src="profiles/r01z_step_kernel.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full; the 19.7 MB of algorithmic writes stay in the 126 MB L2 past the end of the kernel)",
+               traffic=24.50e6 + 24.85e6, traffic_src=("profiles/r02a_dram_steady_state.csv: dram__bytes_read.sum (24.50 MB) + dram__bytes_write.sum (24.85 MB) per launch, mean over the "
+                                                       "18 device-resident launches of a single-pass ncu run of this workload WITHOUT cache control (--cache-control none) after the 1500-step "
+                                                       "pre-roll, 8 replicas round-robin: the write-backs of earlier launches are evicted while later ones run, so the steady-state "
+                                                       "write traffic is visible (an ncu --set full capture flushes the caches and sees reads only)"),
                cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True),
                name="C4: LocalFrameRPYParamsEnv(22 obs)+distance_energy_reward, per-env randomised params, 131072 envs/GPU (1M over 8 GPUs)"),
     # configs[0]: SimpleDrone single env (SimpleDrone.py:41-46: no pendulum, env_gen defaults mass 1.35 / arm 0.15 / force 7.5 / tau 0.015,
@@ -46,7 +49,8 @@ WORKLOADS = {
                cfg=dict(), name="C2: BaseDroneEnv(33 obs)+default_reward_fcn, base_config, 4096 envs"),
     # configs[2]: moving-reference tracking, 65536 envs, per-env joystick-style setpoints
     "c3": dict(cls="LocalFrameRPYEnv", reward="distance_reward_fcn", envs_per_gpu=65536, alg_bytes=104 + 94 + 64 + 16,
-               cfg=dict(per_env_reference=True), name="C3: LocalFrameRPYEnv(16 obs)+distance_reward_fcn, per-env moving setpoints, 65536 envs"),
+               cfg=dict(per_env_reference=True, random_params=False),     # 278 B per env-step = one parameter set (no per-env parameter bytes)
+               name="C3: LocalFrameRPYEnv(16 obs)+distance_reward_fcn, per-env moving setpoints, one parameter set, 65536 envs"),
     # C4 env at the per-GPU size of configs[4] (4M envs over 8 GPUs): working set > L2
     "c4x4": dict(cls="LocalFrameRPYParamsEnv", reward="distance_energy_reward", envs_per_gpu=524288, alg_bytes=104 + 94 + 88 + 24,
                  cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True),
@@ -720,7 +724,12 @@ def main():
                 "host": host_placement},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": wl.get("traffic"),
-                     "traffic_source": wl.get("traffic_src"), "kernel": "step_kernel<float,true>", "algorithmic_bytes_per_launch": wl["alg_bytes"] * n,
+                     "traffic_source": wl.get("traffic_src"),
+                     # bytes the page layout moves per launch: read 24 of the 27 read-write rows (the sensordata rows are write-only) + the 19
+                     # read-only rows when parameters are per env + 16 B of actions (+ 16 B setpoints); write 27 rows + the observation row + 5 B
+                     "traffic_pages": n * ((96 + (76 if wl["cfg"].get("random_params", True) else 0) + 16 + (16 if wl["cfg"].get("per_env_reference") else 0))
+                                           + (108 + 4 * env.obs_dim + 5)),
+                     "kernel": "step_kernel<float,true>", "algorithmic_bytes_per_launch": wl["alg_bytes"] * n,
                      "algorithmic_bytes_per_env_step": wl["alg_bytes"], "peak_source": peak_src},
         "clocks": clocks,
         "episode_stats": {k: stats[k] for k in ("n_episodes", "mean_return", "mean_length", "n_nonfinite", "n_near_ground")},

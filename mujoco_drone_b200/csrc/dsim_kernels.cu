@@ -559,10 +559,10 @@ template <typename T> static cudaError_t launch_step(DsimHandle *h, const KParam
 #endif
         const int o = kp.obs_id, r = kp.reward_id;
         const int cfg = (kp.per_env_consts ? 1 : 0) | (kp.refp ? 2 : 0) | (kp.frame_skip == 1 ? 4 : 0);
-        // BASELINE configs 4 / 5 (per-env randomised parameters), 3 (moving per-env setpoints), 2 (one parameter set)
+        // BASELINE configs 4 / 5 (per-env randomised parameters), 3 (moving per-env setpoints, one parameter set), 2 (base_config: per-env parameters, raw 33-float rows)
         if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2 && cfg == 5) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2, 5>, smem, st, &kp, pages);
         if (o == DSIM_OBS_LOCAL_RPY && r == 1 && cfg == 6) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1, 6>, smem, st, &kp, pages);
-        if (o == DSIM_OBS_BASE && r == 0 && cfg == 4) return launch_one(h, step_kernel<float, true, DSIM_OBS_BASE, 0, 4>, smem, st, &kp, pages);
+        if (o == DSIM_OBS_BASE && r == 0 && cfg == 5) return launch_one(h, step_kernel<float, true, DSIM_OBS_BASE, 0, 5>, smem, st, &kp, pages);
     }
     return launch_one(h, step_kernel<T, true, -1, -1>, smem, st, &kp, pages);
 }
@@ -645,7 +645,7 @@ static int enqueue_host_pipeline(DsimHandle *h, const KParams<float> &base, cons
         CK(cudaEventRecord(h->ev_in[k], s_in));
         CK(cudaStreamWaitEvent(root, h->ev_in[k], 0));
         KParams<float> kp = base;
-        kp.page0 = p0; kp.npages = p1; kp.ticket = h->ticket + k;           // its own work-stealing counter
+        kp.page0 = p0; kp.npages = p1; kp.ticket = h->ticket + 4 * k;       // its own work-stealing counters
         CK(launch_step<float>(h, kp, root));
         CK(cudaEventRecord(h->ev_k[k], root));
         CK(cudaStreamWaitEvent(s_out, h->ev_k[k], 0));

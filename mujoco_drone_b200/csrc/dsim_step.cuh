@@ -115,7 +115,7 @@ template <typename T> struct KParams {
     double start[3], ref64[3], max_d2;         // max_d2: see terminated()
     ResetCfg<T> rc;
     unsigned seed, env_base;
-    unsigned *ticket;               // work-stealing page counter (0 between launches)
+    unsigned *ticket;               // [0] work-stealing page-chunk counter, [1] finished-warp counter (both 0 between launches)
     unsigned long long *timeline;   // debug: [gridDim * warps][8] %globaltimer stamps of the last launch, or nullptr
     // host entry point with pinned buffers: the mapped host copies of the outputs, written by the kernel itself next to the
     // device-resident ones (posted PCIe writes from the same bulk stores; no copy-engine pass), or nullptr
@@ -448,20 +448,27 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     // first page: 2368 warps drawing from one counter at kernel entry cost each of them ~2 us (same-address atomics
     // serialise in L2), more than the page load they were meant to overlap.  From the third page on, work stealing: a warp
     // draws one ticket per processed page, half an iteration before it claims it (raw atom: the compiler's warp-aggregated
-    // atomicAdd consumes its result at once), so the round trip to L2 hides behind the post-processing; the holder of the
-    // last ticket re-zeroes the counter (launches and graph replays need no host reset).  Launches with at most two pages
-    // per warp (C4: 1.73) draw nothing.
+    // atomicAdd consumes its result at once), so the round trip to L2 hides behind the post-processing.  Launches with at
+    // most two pages per warp (C4: 1.73) draw nothing.
+    // Very large batches draw CHUNKS of consecutive pages per ticket: same-address atomics retire at ~3 ns each on the one
+    // L2 slice that owns the counter (measured: 60 800 draws = 182 of the 189 us a 2 M-env launch took, ncu stall reason
+    // long_sb on the ticket's consumer), so a launch that needs more draws than it has time for becomes atomic-bound.  The
+    // chunk keeps >= 8 draws per warp for load balance.  A second counter of finished warps re-zeroes both.
     const bool stealing = my_pages > 2 * nwarps;
-    const unsigned last_ticket = (unsigned)(my_pages - 1);
+    const int chunk = stealing ? max(1, min(8, (my_pages - 2 * nwarps) / (8 * nwarps))) : 1;
+    int chunk_next = 0, chunk_end = 0;                             // pages of the current chunk still to be handed out
     auto draw = [&]() {
         unsigned tk = 0;
-        if (stealing && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(tk) : "l"(p.ticket));
+        if (stealing && chunk_next >= chunk_end && lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(tk) : "l"(p.ticket));
         return tk;
     };
     auto claim = [&](unsigned tk) {                                // tk: lane 0's draw
         if (!stealing) return p.npages;
-        if (lane == 0 && tk == last_ticket) *p.ticket = 0u;
-        return __reduce_max_sync(0xffffffffu, lane == 0 ? p.page0 + 2 * nwarps + (int)tk : 0);
+        if (chunk_next >= chunk_end) {
+            chunk_next = __reduce_max_sync(0xffffffffu, lane == 0 ? p.page0 + 2 * nwarps + (int)tk * chunk : 0);
+            chunk_end = min(chunk_next + chunk, p.npages);
+        }
+        return chunk_next++;
     };
     #pragma unroll 1
     while (page < p.npages) {
@@ -476,10 +483,10 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         if (first_iter) {
             first_iter = false;
             unsigned tk = 0;
-            if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(tk) : "l"(p.ticket + 32));
+            if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(tk) : "l"(p.ticket + 2));
             const int cand = __reduce_max_sync(0xffffffffu, lane == 0 ? p.page0 + nwarps + (int)tk : 0);
             const int second_pages = min(my_pages - nwarps, nwarps);
-            if (lane == 0 && (int)tk == nwarps - 1) p.ticket[32] = 0u;             // every warp draws exactly once: the last draw re-zeroes
+            if (lane == 0 && (int)tk == nwarps - 1) p.ticket[2] = 0u;             // every warp draws exactly once: the last draw re-zeroes
             next = ((int)(cand - p.page0 - nwarps) < second_pages) ? cand : p.npages;
         }
 #endif
@@ -600,6 +607,11 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         buf ^= 1;
     }
     if (lane == 0) bulk_wait_read();                               // the slots must outlive the bulk reads
+    if (stealing && lane == 0) {                                   // the last warp out re-zeroes the counters: launches and graph replays need no host reset
+        unsigned d;
+        asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(d) : "l"(p.ticket + 1));
+        if (d == (unsigned)(nwarps - 1)) { p.ticket[0] = 0u; p.ticket[1] = 0u; }
+    }
     if (timeline && lane == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
