@@ -413,7 +413,8 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
     line = {
         "metric": "env-steps/sec", "value": world * n * timed_steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / timed_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 env step; policy " + ("bf16 operands / f32 accumulate, fused tcgen05 kernel" if args.policy_dtype == "fused" else args.policy_dtype + " torch GEMMs"), "data": "synthetic",
+        "dtype": "f32 env step; policy " + ("bf16 operands / f32 accumulate, fused tcgen05 kernel" if args.policy_dtype == "fused" else
+                                            "f32 operands / f32 accumulate, fused FP32-pipe kernel" if args.policy_dtype == "fused_fp32" else args.policy_dtype + " torch GEMMs"), "data": "synthetic",
         "config": {"workload": wl["name"], "envs_per_gpu": n, "total_envs": n * world, "policy": "RMA_full random init (6->32->8 | 28->256->128+BN | 128->128->8 | 128->128->128->1), " + args.policy_dtype,
                    "sampling": "MyBetaDist, Philox Marsaglia-Tsang", "graph": "one CUDA graph replay per step",
                    "timed_steps": timed_steps, "timed_window_ms": ms,
@@ -422,6 +423,9 @@ def run_rollout_workload(args, wl, rank, world, local_rank):
                 "api": "dsim_step_host (C ABI), host-side policy boundary"},
         # per step: rma_full_forward_kernel (forward + sampling; or torch GEMMs / + beta_policy_kernel when not fused), step_kernel
         "gpu_launches": (2 if (args.policy_dtype == "fused" and args.fuse_sampling) else 3) * timed_steps,
+        "policy_precision": ("bf16 operands: max |d logits| ~1e-2 against the reference's FP32 RMA_full (tests/test_policy_reference.py); --policy-dtype fused_fp32 "
+                             "runs the FP32-faithful fused kernel (~1e-6), extras.baseline_config_c5_fp32 of the default line" if args.policy_dtype == "fused"
+                             else "FP32-faithful" if args.policy_dtype in ("fused_fp32", "fp32") else args.policy_dtype),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "step_kernel<float,true> timed alone at this size", "algorithmic_bytes_per_env_step": wl["alg_bytes"], "peak_source": peak_src,
                      "env_step_kernel_ms": k_ms, "share_of_loop": k_ms / (ms / timed_steps)},
@@ -447,8 +451,9 @@ def main():
     ap.add_argument("--strict-deps", action="store_true", help="do not declare the replicas' inputs ready: every step touches its inputs only after the previous kernel has completed")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads / hot-L2 measurements")
     ap.add_argument("--fuse-sampling", action="store_true", help="c5, fused policy: sample inside the policy kernel (dsim_policy_forward_sample; measured slower at 524288 envs)")
-    ap.add_argument("--policy-dtype", default="fused", choices=["fp32", "tf32", "bf16", "fused"],
-                    help="c5 policy: fused = hand-written tcgen05 kernel (bf16 operands, FP32 accumulate); others = torch / cuBLAS")
+    ap.add_argument("--policy-dtype", default="fused", choices=["fp32", "tf32", "bf16", "fused", "fused_fp32"],
+                    help="c5 policy: fused = hand-written tcgen05 kernel (bf16 operands, FP32 accumulate); fused_fp32 = hand-written FP32-pipe kernel "
+                         "(the reference's precision); others = torch / cuBLAS")
     ap.add_argument("--min-window-ms", type=float, default=30.0, help="the graph of timed steps is replayed until the event window is at least this long")
     ap.add_argument("--preroll", type=int, default=1500, help="untimed steps per replica before the warm-up (reach the steady-state reset rate)")
     args = ap.parse_args()
@@ -671,10 +676,11 @@ def main():
         # configs[4]: the policy-in-the-loop rollout at its per-GPU size of 524288 envs), each as its own short run of this
         # script, for the record next to the headline workload; configs[0] (single SimpleDrone env) is the CPU-runnable case
         if world == 1 and args.workload == "c4" and not args.envs:
-            for name in ("c2", "c3", "c5"):
+            for name in ("c2", "c3", "c5", "c5_fp32"):
                 try:
-                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", str(args.steps), "--warmup", "5",
-                                        "--no-cpu-baseline", "--no-extras"], capture_output=True, text=True, timeout=600)
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name.split("_")[0], "--steps", str(args.steps), "--warmup", "5",
+                                        "--no-cpu-baseline", "--no-extras"] + (["--policy-dtype", "fused_fp32"] if name == "c5_fp32" else []),
+                                       capture_output=True, text=True, timeout=600)
                     sub = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")][-1]
                     extras["baseline_config_" + name] = {"workload": sub["config"]["workload"], "value": sub["value"], "ms_per_step": sub["ms_per_step"],
                                                          "timed_steps": sub["config"].get("timed_steps"), "dtype": sub["dtype"],

@@ -185,6 +185,17 @@ int dsim_policy_forward_sample(DsimPolicy *h, const float *obs_dev, const float 
                                float *logits_dev, float *value_dev, float *actions_dev, float *logp_dev, void *stream);
 int dsim_policy_error(DsimPolicy *h);            /* 1: a launch hit a tensor-core barrier timeout (device sync) */
 
+/* RMA_full inference at the REFERENCE's precision (FP32 operands and accumulation, libm tanh): one fused FP32-pipe kernel
+ * (csrc/dsim_policy_fp32.cu).  The tcgen05 path above uses bf16 operands (~1e-2 on the logits against the reference's FP32
+ * torch module); this one agrees with it to ~1e-6 and is the default of the rollout runner's "fused_fp32" mode.  Weights: one
+ * fp32 blob (transposed per layer, BatchNorm folded) from mujoco_drone_b200/policy.py::pack_rma_full_fp32. */
+typedef struct DsimPolicy32 DsimPolicy32;
+int64_t dsim_policy32_blob_elems(void);
+int dsim_policy32_create(int device, const float *weights_host, DsimPolicy32 **out);
+void dsim_policy32_destroy(DsimPolicy32 *h);
+int dsim_policy32_forward(DsimPolicy32 *h, const float *obs_dev, const float *prev_action_dev, const uint8_t *reset_mask_dev, int n,
+                          float *logits_dev, float *value_dev, void *stream);
+
 /* -- instrumentation */
 int64_t dsim_launch_count(const DsimHandle *h);                                 /* kernels launched by this handle */
 int dsim_debug_timeline(DsimHandle *h, uint64_t *out /*[npages][8] %globaltimer ns*/, int64_t capacity);   /* needs DSIM_TIMELINE=1 at create */

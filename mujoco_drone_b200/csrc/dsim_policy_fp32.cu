@@ -1,0 +1,214 @@
+// dsim_policy_fp32.cu — RMA_full inference (models/PPO/RMA/RMA_model.py:48-71, 79-116, train_adaptation=False) at the
+// REFERENCE's precision: FP32 operands, FP32 accumulation, libm-accurate tanh.  The reference's policy is an FP32 torch
+// module; the tcgen05 kernel (dsim_policy_mlp.cu) trades precision for speed (bf16 operands, ~1e-2 on the logits).  An
+// FP32-faithful tensor-core variant does not fit the fused design: bf16 hi + lo operand splitting (3 MMAs per product)
+// needs both halves of every weight matrix in shared memory, 2 x 180 KB > 227 KB, and kind::tf32 carries 10 mantissa bits
+// (~1e-3 on the logits, and its FP32-sized weights do not fit either).  This kernel is the faithful mode: the whole network
+// fused on the FP32 pipe, activations in shared memory, weights streamed through L1 from their 363 KB L2-resident blob.
+//
+//   tile = 64 rows per CTA pass, 512 threads = 16 warps: warp w owns rows 8 (w % 8) .. +7 and the column half w / 8 (every A
+//   operand is a warp-wide broadcast read of the transposed activation tile At[k][row]; lane l owns output columns l, l+32,
+//   ... of its half, so every W operand is a coalesced 128-byte line of the transposed weights Wt[k][n], shared by eight
+//   warps through L1): 32 FFMA per 2 LDS.128 + 4 LDG at N = 256.  Layers ping-pong between two activation tiles; BatchNorm
+//   (eval) is folded into its two consumers on the host.  tanh(x) = 1 - 2 / (exp(2x) + 1) on the MUFU exp2 / rcp (abs. error
+//   ~2e-7: the logits stay within 1e-6 of the torch FP32 module, tests/test_policy_reference.py).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/dronesim_b200.h"
+
+namespace {
+
+constexpr int S_DIM = 16, P_DIM = 6, A_DIM = 4, E_DIM = 8, OBS_DIM = S_DIM + P_DIM, ENC_H = 32, K1 = S_DIM + A_DIM + E_DIM;   // 28
+constexpr int TM = 64, LDT = TM + 4;       // rows per tile; row pitch of the transposed tiles (68: conflict-free 16-byte stores)
+// fp32 blob (float offsets): transposed weights Wt[k][n] then bias, per layer
+constexpr int F_W1 = 0, F_B1 = F_W1 + K1 * 256;                 // 28 -> 256
+constexpr int F_W2 = F_B1 + 256, F_B2 = F_W2 + 256 * 128;       // 256 -> 128
+constexpr int F_W3 = F_B2 + 128, F_B3 = F_W3 + 128 * 256;       // 128 -> 256: columns 0-127 logits hidden (BN folded), 128-255 value hidden
+constexpr int F_V2 = F_B3 + 256, F_C2 = F_V2 + 128 * 128;       // 128 -> 128 (value branch)
+constexpr int F_W4 = F_C2 + 128, F_B4 = F_W4 + 128 * 8;         // 128 -> 8, stored [k][8]
+constexpr int F_V3 = F_B4 + 8, F_C3 = F_V3 + 128;               // 128 -> 1
+constexpr int F_E1 = F_C3 + 1, F_E1B = F_E1 + ENC_H * P_DIM;    // encoder 6 -> 32 ([j][k])
+constexpr int F_E2 = F_E1B + ENC_H, F_E2B = F_E2 + E_DIM * ENC_H;   // 32 -> 8 ([e][j])
+constexpr int F_ELEMS = F_E2B + E_DIM;
+constexpr int SMEM_BYTES = 2 * 256 * LDT * 4;                   // two activation tiles [256][68] fp32 = 139 264 B
+
+struct P32 {
+    const float *w, *obs, *prev_action;
+    const unsigned char *reset_mask;
+    float *logits, *value;
+    int n, ntiles;
+};
+
+constexpr int NT = 512;                    // threads per CTA
+__device__ __forceinline__ float tanh_acc(float x) {
+    // 1 - 2 / (e^{2x} + 1): exact limits for |x| large (e -> inf: 1; e -> 0: -1), no cancellation near 0 beyond 1 ulp of 1
+    const float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+// Ot[n][row] = act(bias[n] + sum_k Wt[k][n] * At[k][row]) for the 64 rows of the tile; N a multiple of 64
+template <int K, int N, bool TANH>
+__device__ __forceinline__ void dense(const float *__restrict__ Wt_, const float *__restrict__ bias_, const float *At, float *Ot_) {
+    constexpr int CN = N / 64;
+    const int tx = threadIdx.x & 31, wp = threadIdx.x >> 5, ty = wp & 7, half = wp >> 3;
+    const float *Wt = Wt_ + half * (N / 2), *bias = bias_ + half * (N / 2);
+    float *Ot = Ot_ + half * (N / 2) * LDT;
+    float acc[8][CN];
+    #pragma unroll
+    for (int j = 0; j < CN; j++) {
+        const float b = __ldg(bias + tx + 32 * j);
+        #pragma unroll
+        for (int r = 0; r < 8; r++) acc[r][j] = b;
+    }
+    #pragma unroll 4
+    for (int k = 0; k < K; k++) {
+        const float4 a0 = *reinterpret_cast<const float4 *>(At + k * LDT + ty * 8), a1 = *reinterpret_cast<const float4 *>(At + k * LDT + ty * 8 + 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float w[CN];
+        #pragma unroll
+        for (int j = 0; j < CN; j++) w[j] = __ldg(Wt + (size_t)k * N + tx + 32 * j);
+        #pragma unroll
+        for (int r = 0; r < 8; r++)
+            #pragma unroll
+            for (int j = 0; j < CN; j++) acc[r][j] = fmaf(a[r], w[j], acc[r][j]);
+    }
+    #pragma unroll
+    for (int j = 0; j < CN; j++) {
+        float v[8];
+        #pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = TANH ? tanh_acc(acc[r][j]) : acc[r][j];
+        float *o = Ot + (tx + 32 * j) * LDT + ty * 8;
+        *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1) rma_full_forward_fp32_kernel(const P32 p) {
+    extern __shared__ __align__(16) float sm[];
+    float *A = sm, *B = sm + 256 * LDT;
+    const int tid = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        // ---- x0 = [s(16), a_prev(4), z(8)] with z = E2 tanh(E1 e + e1) + e2 (RMA_model.py:94-104), one thread per row -> B[k][row]
+        if (tid < TM) {
+            const int row = tile * TM + tid;
+            const bool live = row < p.n;
+            float o[OBS_DIM], a[A_DIM];
+            #pragma unroll
+            for (int k = 0; k < OBS_DIM; k++) o[k] = live ? __ldg(p.obs + (size_t)row * OBS_DIM + k) : 0.f;
+            const bool fresh = live && p.reset_mask && p.reset_mask[row];
+            #pragma unroll
+            for (int k = 0; k < A_DIM; k++) a[k] = (live && !fresh) ? __ldg(p.prev_action + (size_t)row * A_DIM + k) : 0.f;
+            float hdn[ENC_H];
+            #pragma unroll
+            for (int j = 0; j < ENC_H; j++) {
+                float acc = __ldg(p.w + F_E1B + j);
+                #pragma unroll
+                for (int k = 0; k < P_DIM; k++) acc = fmaf(__ldg(p.w + F_E1 + j * P_DIM + k), o[S_DIM + k], acc);
+                hdn[j] = tanh_acc(acc);
+            }
+            #pragma unroll
+            for (int k = 0; k < S_DIM; k++) B[k * LDT + tid] = o[k];
+            #pragma unroll
+            for (int k = 0; k < A_DIM; k++) B[(S_DIM + k) * LDT + tid] = a[k];
+            #pragma unroll
+            for (int e = 0; e < E_DIM; e++) {
+                float acc = __ldg(p.w + F_E2B + e);
+                #pragma unroll
+                for (int j = 0; j < ENC_H; j++) acc = fmaf(__ldg(p.w + F_E2 + e * ENC_H + j), hdn[j], acc);
+                B[(S_DIM + A_DIM + e) * LDT + tid] = acc;
+            }
+        }
+        __syncthreads();
+        dense<K1, 256, true>(p.w + F_W1, p.w + F_B1, B, A);          // h1 -> A
+        __syncthreads();
+        dense<256, 128, true>(p.w + F_W2, p.w + F_B2, A, B);         // h2 -> B (BatchNorm folded into the consumers)
+        __syncthreads();
+        dense<128, 256, true>(p.w + F_W3, p.w + F_B3, B, A);         // [l1 | v1] -> A
+        __syncthreads();
+        dense<128, 128, true>(p.w + F_V2, p.w + F_C2, A + 128 * LDT, B);   // v2 = tanh(V2 v1 + c2) -> B
+        // logits = W4 l1 + b4: 64 rows x 8 outputs, thread -> (row, output pair)
+        if (tid < 256) {
+            const int row = tid & 63, o2 = (tid >> 6) * 2;
+            float x0 = __ldg(p.w + F_B4 + o2), x1 = __ldg(p.w + F_B4 + o2 + 1);
+            #pragma unroll 8
+            for (int k = 0; k < 128; k++) {
+                const float l = A[k * LDT + row];
+                x0 = fmaf(__ldg(p.w + F_W4 + k * 8 + o2), l, x0);
+                x1 = fmaf(__ldg(p.w + F_W4 + k * 8 + o2 + 1), l, x1);
+            }
+            const int r = tile * TM + row;
+            if (r < p.n) *reinterpret_cast<float2 *>(p.logits + (size_t)r * 8 + o2) = make_float2(x0, x1);
+        }
+        __syncthreads();
+        if (tid < TM) {                                              // value = V3 v2 + c3
+            float v = __ldg(p.w + F_C3);
+            #pragma unroll 8
+            for (int k = 0; k < 128; k++) v = fmaf(__ldg(p.w + F_V3 + k), B[k * LDT + tid], v);
+            const int r = tile * TM + tid;
+            if (r < p.n) p.value[r] = v;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+struct DsimPolicy32 {
+    int device, sms;
+    float *w;
+};
+
+extern "C" int64_t dsim_policy32_blob_elems(void) { return F_ELEMS; }
+
+extern "C" int dsim_policy32_create(int device, const float *weights_host, DsimPolicy32 **out) {
+    if (!weights_host || !out) return DSIM_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return DSIM_ECUDA;     // no CPU fallback
+    if (device < 0 || device >= ndev) return DSIM_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return DSIM_ECUDA;
+    DsimPolicy32 *h = new (std::nothrow) DsimPolicy32();
+    if (!h) return DSIM_ENOMEM;
+    h->device = device;
+    if (cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        cudaMalloc((void **)&h->w, F_ELEMS * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(h->w, weights_host, F_ELEMS * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaFuncSetAttribute(rma_full_forward_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+        if (h->w) cudaFree(h->w);
+        delete h;
+        return DSIM_ECUDA;
+    }
+    *out = h;
+    return DSIM_OK;
+}
+
+extern "C" void dsim_policy32_destroy(DsimPolicy32 *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->w);
+    delete h;
+}
+
+extern "C" int dsim_policy32_forward(DsimPolicy32 *h, const float *obs_dev, const float *prev_action_dev, const uint8_t *reset_mask_dev, int n,
+                                     float *logits_dev, float *value_dev, void *stream) {
+    if (!h || !obs_dev || !prev_action_dev || !logits_dev || !value_dev || n <= 0) return DSIM_EINVAL;
+    if (cudaSetDevice(h->device) != cudaSuccess) return DSIM_ECUDA;
+    P32 p;
+    p.w = h->w; p.obs = obs_dev; p.prev_action = prev_action_dev; p.reset_mask = reset_mask_dev; p.logits = logits_dev; p.value = value_dev;
+    p.n = n; p.ntiles = (n + TM - 1) / TM;
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3(p.ntiles < h->sms ? p.ntiles : h->sms); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = SMEM_BYTES; lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    void *args[] = {&p};
+    if (cudaLaunchKernelExC(&lc, (const void *)rma_full_forward_fp32_kernel, args) != cudaSuccess) return DSIM_ECUDA;
+    return cudaGetLastError() == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
+}

@@ -226,6 +226,26 @@ template <typename T> DSIM_DEV T shfl_(T v, int src) { return __shfl_sync(0xffff
 template <typename T, bool PEND>
 __device__ __noinline__ void resample_page(unsigned need, T *s_rw, const ResetCfg<T> &rc, unsigned seed, unsigned env0) {
     const int lane = threadIdx.x & 31, e = lane >> 3, q = lane & 7;
+    if (__popc(need) > 12) {
+        // mass truncation (a synchronised start, setpoints that ran away from the drones): more than three cooperative passes
+        // cost more than letting every truncated lane draw its own state at once
+        if ((need >> lane) & 1u) {
+            EnvState<T> s;
+            const unsigned rcnt = (unsigned)slot_to_int(s_rw[RW_RESET_COUNT * kTile + lane]) + 1u;
+            sample_state<T, PEND>(s, rc, seed, env0 + (unsigned)lane, rcnt);
+            s_rw[RW_RESET_COUNT * kTile + lane] = int_to_slot<T>((int)rcnt);
+            T *col = s_rw + lane;
+            col[0 * kTile] = s.pos.x; col[1 * kTile] = s.pos.y; col[2 * kTile] = s.pos.z;
+            col[3 * kTile] = s.qw; col[4 * kTile] = s.qx; col[5 * kTile] = s.qy; col[6 * kTile] = s.qz;
+            col[7 * kTile] = s.hx; col[8 * kTile] = s.hy;
+            col[9 * kTile] = s.vel.x; col[10 * kTile] = s.vel.y; col[11 * kTile] = s.vel.z;
+            col[12 * kTile] = s.om.x; col[13 * kTile] = s.om.y; col[14 * kTile] = s.om.z;
+            col[15 * kTile] = s.hvx; col[16 * kTile] = s.hvy;
+            col[RW_NUM_STEPS * kTile] = int_to_slot<T>(0);
+        }
+        __syncwarp();
+        return;
+    }
     while (need) {
         // the (up to) four lowest truncated lanes of this pass: P[k]; this lane computes for env P[e], and owns env `lane` if selected
         int P[4], mine = -1, own = -1;

@@ -245,3 +245,78 @@ class FusedRMAFull:
             self.close()
         except Exception:
             pass
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# FP32-faithful fused inference of RMA_full (csrc/dsim_policy_fp32.cu, C ABI dsim_policy32_*)
+
+def pack_rma_full_fp32(model):
+    """float32 blob for dsim_policy32_create: per layer the TRANSPOSED weight [K][N] then the bias, BatchNorm1d (eval) folded
+    into the two layers that consume it (the same algebra as pack_rma_full, in FP32)."""
+    import torch
+    if model.num_states != 16 or model.num_params != 6 or model.num_actions != 4:
+        raise ValueError("the fused kernels are specialised for RMA_full with 16 states, 6 params, 4 actions (train_RMA.py:47-53)")
+    enc1, enc2 = model.param_encoder[0], model.param_encoder[2]
+    h1, h2, bn = model.hidden[0], model.hidden[2], model.hidden[4]
+    l1, l2 = model.logits[0], model.logits[2]
+    v1, v2, v3 = model.value_branch[0], model.value_branch[2], model.value_branch[4]
+    f = lambda t: t.detach().double().cpu()
+    with torch.no_grad():
+        scale = f(bn.weight) / torch.sqrt(f(bn.running_var) + bn.eps)
+        shift = f(bn.bias) - f(bn.running_mean) * scale
+        w3 = torch.cat([f(l1.weight) * scale[None, :], f(v1.weight) * scale[None, :]], 0)            # [256][128]
+        b3 = torch.cat([f(l1.bias) + f(l1.weight) @ shift, f(v1.bias) + f(v1.weight) @ shift])
+        parts = [f(h1.weight).t(), f(h1.bias), f(h2.weight).t(), f(h2.bias), w3.t(), b3, f(v2.weight).t(), f(v2.bias),
+                 f(l2.weight).t(), f(l2.bias), f(v3.weight).flatten(), f(v3.bias), f(enc1.weight), f(enc1.bias), f(enc2.weight), f(enc2.bias)]
+        blob = torch.cat([x.contiguous().flatten() for x in parts]).float().contiguous()
+    return blob
+
+
+class FP32RMAFull:
+    """RMA_full forward as ONE fused FP32 kernel (FP32 operands / accumulation, libm tanh: the reference's precision).
+    `logits, value = net(obs, prev_action)` on CUDA float32 tensors ([n, 22], [n, 4]) -> ([n, 8], [n]).  No CPU fallback."""
+
+    def __init__(self, model, device=0):
+        import torch
+        self._torch = torch
+        L = self._L = _lib.load()
+        blob = pack_rma_full_fp32(model)
+        assert blob.numel() == L.dsim_policy32_blob_elems(), (blob.numel(), L.dsim_policy32_blob_elems())
+        self.device = torch.device("cuda", int(device))
+        h = C.c_void_p()
+        rc = L.dsim_policy32_create(int(device), C.c_void_p(blob.data_ptr()), C.byref(h))
+        if rc != _lib.OK:
+            raise _lib.DsimError(rc, "dsim_policy32_create failed (needs a CUDA device: there is no CPU fallback)")
+        self._h = h
+
+    def __call__(self, obs, prev_action, logits_out=None, value_out=None, reset_mask=None):
+        torch = self._torch
+        n = obs.shape[0]
+        if obs.shape != (n, 22) or prev_action.shape != (n, 4) or obs.dtype != torch.float32 or prev_action.dtype != torch.float32:
+            raise ValueError("FP32RMAFull expects float32 obs [n, 22] and prev_action [n, 4]")
+        obs, prev_action = obs.contiguous(), prev_action.contiguous()
+        logits = logits_out if logits_out is not None else torch.empty((n, 8), dtype=torch.float32, device=obs.device)
+        value = value_out if value_out is not None else torch.empty((n,), dtype=torch.float32, device=obs.device)
+        if reset_mask is not None and (reset_mask.dtype != torch.uint8 or reset_mask.numel() != n or not reset_mask.is_contiguous()):
+            raise ValueError("reset_mask must be a contiguous uint8 tensor [n]")
+        rc = self._L.dsim_policy32_forward(self._h, C.c_void_p(obs.data_ptr()), C.c_void_p(prev_action.data_ptr()),
+                                           C.c_void_p(reset_mask.data_ptr()) if reset_mask is not None else None, n,
+                                           C.c_void_p(logits.data_ptr()), C.c_void_p(value.data_ptr()),
+                                           C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream))
+        if rc != _lib.OK:
+            raise _lib.DsimError(rc, "dsim_policy32_forward failed")
+        return logits, value
+
+    def check(self):
+        return None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.dsim_policy32_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

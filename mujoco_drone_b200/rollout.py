@@ -58,6 +58,12 @@ class RolloutRunner:
             from .policy import FusedRMAFull
             self._fused = FusedRMAFull(self.policy, device=env.device_index)
             self._logits = torch.zeros((N, 8), dtype=dt, **z)
+        elif policy_dtype == "fused_fp32":             # hand-written FP32-pipe kernel (csrc/dsim_policy_fp32.cu): the reference's precision
+            from .policy import FP32RMAFull
+            if fuse_sampling:
+                raise ValueError("fuse_sampling needs policy_dtype='fused' (the tcgen05 kernel)")
+            self._fused = FP32RMAFull(self.policy, device=env.device_index)
+            self._logits = torch.zeros((N, 8), dtype=dt, **z)
         self.use_graph, self._graph = bool(use_graph), None
         self.total_steps = 0
         if policy_dtype == "tf32":

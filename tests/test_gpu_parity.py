@@ -1,13 +1,16 @@
 """GPU parity tests proper: the CUDA path (through the C ABI, via mujoco_drone_b200.BaseDroneEnv) against the CPU
 oracle on identical seeded inputs and against the committed golden fixtures.  Nothing here reads /root/reference.
 
-Stated tolerances (FP32 product path; FP64 build of the same kernel source in brackets):
-  per substep  |d pos| <= 2e-6 m [1e-12], |d quat| <= 2e-6 [1e-12], |d v_lin| <= 2e-5 (1+|v|) [1e-11],
-               |d omega|, |d hinge rate| <= 1e-4 (1+|w|) [1e-11]  (cond(M) ~ 5e2: the body-vs-pendulum relative
-               rotation is the ill-conditioned direction; the SUM omega + hinge rate is held to 2e-5),
-               accelerometer <= 2e-4 (1+|a|) [1e-10]
-  obs / reward on identical states: <= 5e-5 (1+|x|) [1e-10]
-  100-step open-loop trajectory: |d pos| <= 1e-3 m
+Stated tolerances (FP32 product path; FP64 build of the same kernel source in brackets).  Every FP32 number is 3-5x the
+largest deviation MEASURED over 4096 random envs (profiles/r02_fp32_error_histogram.txt, tools/fp32_error_hist.py; max in
+parentheses) and at or below what SURVEY.md A.7 proposed, except the two rates of the ill-conditioned direction:
+  per substep  |d pos| <= 1e-6 m (1.2e-7) [1e-12], |d quat|, |d hinge| <= 1e-6 (3.6e-7) [1e-12],
+               |d v_lin| <= 1e-5 (1+|v|) (1.7e-7) [1e-11],
+               |d omega|, |d hinge rate| <= 1e-4 (1+|w|) (2.6e-5; p99.9 1.7e-5) [1e-11]  - cond(M) ~ 5e2: the body-vs-pendulum
+               relative rotation is the ill-conditioned direction; the SUM omega_x + hinge_x rate is held to 6e-5 (2.3e-5; p99 4.4e-6),
+               accelerometer <= 1e-4 (1+|a|) (3.1e-5) [1e-10], act <= 1e-6 (1.8e-7)
+  obs on identical states: <= 1e-5 (1+|x|) (9.1e-7) [1e-9]; reward: <= 5e-5 (1+|r|) over all 17 functions (3.4e-6 on the three sampled) [1e-9]
+  100-step open-loop trajectory: |d pos| <= 1e-4 m (1.2e-5)
   truncation bits, step counters, reset index sets: exact
 """
 import numpy as np
@@ -63,7 +66,7 @@ def test_substep_matches_oracle(oracle, precision, frame_skip, pend):
     qp, qv, ac, sens, ns = env.get_state()
     a_in = actions.astype(np.float32).astype(np.float64) if precision == "fp32" else actions
     prm = env.drone_params
-    tol = dict(pos=1e-12, quat=1e-12, vel=1e-11, rot=1e-11, acc=1e-10) if precision == "fp64" else dict(pos=2e-6, quat=2e-6, vel=2e-5, rot=1e-4, acc=2e-4)
+    tol = dict(pos=1e-12, quat=1e-12, vel=1e-11, rot=1e-11, acc=1e-10, sumrate=1e-11) if precision == "fp64" else dict(pos=1e-6, quat=1e-6, vel=1e-5, rot=1e-4, acc=1e-4, sumrate=6e-5)
     for i in range(n):
         p = np.array(list(prm[i].values()))
         m = oracle.compile_model(p, pend, 100, True)
@@ -73,9 +76,9 @@ def test_substep_matches_oracle(oracle, precision, frame_skip, pend):
         assert (np.abs(qv[i, :3] - oqv[:3]) <= tol["vel"] * frame_skip * (1 + np.abs(oqv[:3]))).all()
         assert (np.abs(qv[i, 3:] - oqv[3:]) <= tol["rot"] * frame_skip * (1 + np.abs(oqv[3:]))).all()
         if pend:   # well-conditioned combination: absolute pendulum rate about the hinge axes
-            assert abs((qv[i, 3] + qv[i, 6]) - (oqv[3] + oqv[6])) <= tol["vel"] * frame_skip * (1 + abs(oqv[3]) + abs(oqv[6]))
+            assert abs((qv[i, 3] + qv[i, 6]) - (oqv[3] + oqv[6])) <= tol["sumrate"] * frame_skip * (1 + abs(oqv[3]) + abs(oqv[6]))
         assert (np.abs(sens[i] - osens) <= tol["acc"] * frame_skip * (1 + np.abs(osens))).all()
-        assert np.abs(ac[i] - oact).max() <= (1e-12 if precision == "fp64" else 5e-6)
+        assert np.abs(ac[i] - oact).max() <= (1e-12 if precision == "fp64" else 1e-6)
     assert (ns == 1).all()
     env.close()
 
@@ -120,7 +123,7 @@ def test_rewards_golden(precision):
         _, rew, _ = env.evaluate_tensor(torch.as_tensor(g["actions"], device="cuda"))
         out = rew.cpu().numpy().astype(np.float64)
         ref = g["out_" + name]
-        tol = 1e-9 if precision == "fp64" else 2e-4
+        tol = 1e-9 if precision == "fp64" else 5e-5          # all 17 functions, incl. the energy variants (more terms than the histogram's three)
         assert (np.abs(out - ref) <= tol * (1 + np.abs(ref))).all(), (name, np.abs(out - ref).max())
         env.close()
 
@@ -145,7 +148,7 @@ def test_obs_golden(precision):
         out = obs.cpu().numpy().astype(np.float64)
         ref = g["out_" + name]
         assert out.shape == ref.shape, name
-        tol = 1e-9 if precision == "fp64" else 5e-5
+        tol = 1e-9 if precision == "fp64" else 1e-5
         assert (np.abs(out - ref) <= tol * (1 + np.abs(ref))).all(), (name, np.abs(out - ref).max())
         # get_drone_states rows (BaseDroneEnv.py:357-380)
         st = np.array(env.get_drone_states())
@@ -318,7 +321,7 @@ def test_auto_reset_state_matches_oracle(oracle, precision):
 
 
 def test_open_loop_trajectory_fp32_vs_oracle(oracle):
-    """100 steps open loop near hover: FP32 kernel trajectory vs FP64 oracle, |d pos| <= 1e-3 m"""
+    """100 steps open loop near hover: FP32 kernel trajectory vs FP64 oracle, |d pos| <= 1e-4 m (measured max 1.2e-5)"""
     import torch
     n = 64
     rng = np.random.default_rng(5)
@@ -334,7 +337,7 @@ def test_open_loop_trajectory_fp32_vs_oracle(oracle):
         for i in range(n):
             oqp[i], oqv[i], oact[i], _ = oracle.step(m, oqp[i], oqv[i], oact[i], 0.1 + 0.9 * a[i].astype(np.float64), 1)
     qp, qv, _, _, _ = env.get_state()
-    assert np.abs(qp[:, :3] - oqp[:, :3]).max() <= 1e-3
+    assert np.abs(qp[:, :3] - oqp[:, :3]).max() <= 1e-4
     assert np.abs(qv - oqv).max() <= 2e-2
     env.close()
 
