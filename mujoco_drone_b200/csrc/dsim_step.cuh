@@ -86,6 +86,11 @@ DSIM_DEV void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes, uin
     (void)policy; bulk_s2g(gmem_dst, smem_src, bytes);
 #endif
 }
+// HBM -> L2 only.  Always safe ahead of the dependency wait: L2 is the point of coherence, a line that an earlier kernel still
+// writes is simply updated in place, nothing becomes visible to this SM before the real load is issued.
+DSIM_DEV void bulk_prefetch_l2(const void *gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 DSIM_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DSIM_DEV void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (the bulk store that follows)
@@ -426,6 +431,28 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     }
 #if DSIM_EARLY2 && !defined(DSIM_DYN2)
     next_issued = next < p.npages;
+#endif
+#ifndef DSIM_PREFETCH
+#define DSIM_PREFETCH 0
+#endif
+#if DSIM_PREFETCH
+    // Experiment, off by default.  Strict mode: the state / action / setpoint rows may not be LOADED before the wait, but they
+    // may be pulled from HBM into L2 (both static pages), so that the first-page burst after the wait hits L2.  It does
+    // (page landed 1.15 us after the release instead of 2.0), but the prefetch traffic competes with the tail of the kernel
+    // ahead, whose completion - and with it the release - moves 1.6 us later: C4 strict 11.55 against 10.82 us without
+    // (tools/gpu_r2k.sh).  HBM is ~72 % busy over a step: there is no idle bandwidth to prefetch into.
+    if (has_work && lane == 0 && !p.early_in) {
+        #pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int pg = k == 0 ? page : next;
+            if (pg < p.npages) {
+                bulk_prefetch_l2(p.rw + (size_t)pg * (RW_ROWS * kTile), (eval_only ? RW_ROWS : RW_IN_ROWS) * kTile * (uint32_t)sizeof(T));
+                bulk_prefetch_l2(p.actions + (size_t)pg * (kTile * 4), (uint32_t)min(kTile, p.n - pg * kTile) * 4u * (uint32_t)sizeof(T));
+                if (pref) bulk_prefetch_l2(p.refp + (size_t)pg * (REF_ROWS * kTile), REF_ROWS * kTile * (uint32_t)sizeof(T));
+                if (pec && !p.early_ro) bulk_prefetch_l2(p.ro + (size_t)pg * (RO_ROWS * kTile), RO_ROWS * kTile * (uint32_t)sizeof(T));
+            }
+        }
+    }
 #endif
     // With inputs_ready the wait moves to just before this warp's first store (the physics of the first page overlaps the
     // tail of the kernel ahead); otherwise nothing an earlier kernel may have written is touched before it.  The dependents
