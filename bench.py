@@ -623,6 +623,7 @@ def main():
     pcie = pcie_probe(torch, dist, dev, world, d2h_bytes, h2d_bytes, barrier)
 
     extras = {}
+    k_ms_est = ms / timed_steps
     if not args.no_extras and rank == 0:
         # (0) the same graph of steps without the inputs-ready promise (what a single-shard policy -> step loop pays per step)
         if graph is not None and overlap:
@@ -647,15 +648,31 @@ def main():
                                      "note": "same CUDA graph of steps, inputs_ready off: each step fetches its pages only after the previous kernel has completed"}
             for e in envs:
                 e.inputs_ready = True
-        # (a) one replica only: its ~40 MB working set stays L2-resident between steps, as in a tight rollout loop
+        # (a) one replica only, stepped back to back from a CUDA graph: its ~50 MB working set stays L2-resident between steps,
+        # as in a tight single-shard rollout loop.  Consecutive launches now belong to the SAME handle: strict mode.
+        for e in envs:
+            e.inputs_ready = False
         run_steps(5, envs[:1])
         torch.cuda.synchronize(dev)
-        eh0, eh1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kh = min(args.steps, 200)
-        eh0.record(); run_steps(kh, envs[:1]); eh1.record()
+        gh = torch.cuda.CUDAGraph()
+        saved_axes3, axes = axes, None
+        with torch.cuda.graph(gh):
+            run_steps(40, envs[:1])
+        axes = saved_axes3
+        for _ in range(10):
+            gh.replay()
         torch.cuda.synchronize(dev)
-        msh = eh0.elapsed_time(eh1)
-        extras["hot_l2"] = {"value": n * kh / (msh * 1e-3), "ms_per_step": msh / kh, "note": "single replica, L2-resident between steps (1 GPU, rank 0)"}
+        eh0, eh1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps_h = max(1, int(np.ceil(10.0 / max(40 * k_ms_est, 1e-3))))
+        eh0.record()
+        for _ in range(reps_h):
+            gh.replay()
+        eh1.record()
+        torch.cuda.synchronize(dev)
+        msh = eh0.elapsed_time(eh1) / (40 * reps_h)
+        extras["hot_l2"] = {"value": n / (msh * 1e-3), "ms_per_step": msh,
+                            "note": "ONE replica stepped back to back (CUDA graph, strict dependency chain): state, constants and outputs stay in the 126 MB L2 "
+                                    "between steps, what a single-shard rollout loop sees; not the headline (the contract asks for L2-cold inputs)"}
         # (b) explicit L2 flush (256 MiB write then 256 MiB read) before every step, each step timed with its own event pair
         flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
         flush_rd = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)

@@ -517,6 +517,13 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         }
         return chunk_next++;
     };
+#ifndef DSIM_DEFER
+#define DSIM_DEFER 0       // measured (tools/gpu_r2m.sh, C4 inputs-ready): holding the first page back 10.29 us, publishing it at once 9.32 us
+#endif
+    int held_page = -1;                                            // first page of an inputs-ready warp, waiting for the dependency wait
+    T *held_slot = nullptr;
+    T held_rew = T(0);
+    bool held_trunc = false;
     #pragma unroll 1
     while (page < p.npages) {
         const int i = page * kTile + lane;
@@ -599,18 +606,13 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             ObsWriter<T, 1> w; w.base = s_obs + lane * D; w.stride = 1;
             emit_obs<T, PEND>(obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
         }
-        if (!waited) {                                              // inputs-ready mode: first store of this warp (warp-uniform)
-            waited = true;
-            asm volatile("griddepcontrol.wait;" ::: "memory");
-            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        }
-        if (active) {
-            p.reward[i] = rew;
-            p.trunc[i] = trunc ? 1 : 0;
-            if (p.reward_host) p.reward_host[i] = rew;
-            if (p.trunc_host) p.trunc_host[i] = trunc ? 1 : 0;
-        }
-
+        // Experiment (DSIM_DEFER, off): inputs-ready mode, launches with at most two pages per warp (both slots stay private):
+        // the FIRST page is not published when it is done - its reward / truncated flag ride in two registers, its rows stay
+        // in the slot - so that the second page's physics also runs ahead of the dependency wait and both pages leave after
+        // it.  Measured slower: the stores bunch up at the end of the grid and lengthen its straggler tail (last exit 15.9
+        // against 14.3 us after the first entry).  What did pay is the placement of the wait itself: as the very last thing
+        // before the first global store, after the statistics, the state write-back into the slot and the reset path.
+        const bool hold = DSIM_DEFER && !waited && !stealing && next < p.npages;
         if (!eval_only) {
             // would-be ground contact (the floor plane is out of reach in the BASELINE configs; detected, never ignored)
             if (active && p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(p.stats + 4, 1.0);
@@ -627,27 +629,46 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             const unsigned need = __ballot_sync(0xffffffffu, !eval_only && active && trunc && (p.auto_reset || bad));
             if (need) resample_page<T, PEND>(need, s_rw, p.rc, p.seed, p.env_base + (unsigned)(page * kTile));
         }
-
-        // ---- publish: slot -> HBM
-        fence_async_smem();
+        fence_async_smem();                                        // generic-proxy writes of the slot -> visible to the bulk stores
         __syncwarp();
-        const int nvalid = min(kTile, p.n - page * kTile);
-        const uint32_t obs_bytes = (uint32_t)(nvalid * D) * (uint32_t)sizeof(T);
-        T *gobs = p.obs + (size_t)page * kTile * D;
-        const bool obs_bulk = (obs_bytes & 15u) == 0;              // always true for full pages
-        if (lane == 0) {
-            if (!eval_only) bulk_s2g(p.rw + (size_t)page * (RW_ROWS * kTile), s_rw, RW_ROWS * kTile * sizeof(T), pol_stream);
-            if (obs_bulk) bulk_s2g(gobs, s_obs, obs_bytes, pol_stream);
-            if (obs_bulk && p.obs_host) bulk_s2g(p.obs_host + (size_t)page * kTile * D, s_obs, obs_bytes);
-            bulk_commit();
-        }
-        stamp();                                                   // [3], [5]: page published
-        if (!obs_bulk)                                             // ragged last page whose byte count is not a multiple of 16
-            #pragma unroll 1
-            for (int e = lane; e < nvalid * D; e += kTile) {
-                gobs[e] = s_obs[e];
-                if (p.obs_host) p.obs_host[(size_t)page * kTile * D + e] = s_obs[e];
+        // ---- publish: slot -> HBM (plus the two per-env scalars that go straight to global memory)
+        auto publish = [&](int pg, T *pslot, T prew, bool ptrunc) {
+            const int pi = pg * kTile + lane;
+            if (pi < p.n) {
+                p.reward[pi] = prew;
+                p.trunc[pi] = ptrunc ? 1 : 0;
+                if (p.reward_host) p.reward_host[pi] = prew;
+                if (p.trunc_host) p.trunc_host[pi] = ptrunc ? 1 : 0;
             }
+            const int nvalid = min(kTile, p.n - pg * kTile);
+            const uint32_t obs_bytes = (uint32_t)(nvalid * D) * (uint32_t)sizeof(T);
+            T *gobs = p.obs + (size_t)pg * kTile * D, *pobs = pslot + kSlotObsOff;
+            const bool obs_bulk = (obs_bytes & 15u) == 0;          // always true for full pages
+            if (lane == 0) {
+                if (!eval_only) bulk_s2g(p.rw + (size_t)pg * (RW_ROWS * kTile), pslot, RW_ROWS * kTile * sizeof(T), pol_stream);
+                if (obs_bulk) bulk_s2g(gobs, pobs, obs_bytes, pol_stream);
+                if (obs_bulk && p.obs_host) bulk_s2g(p.obs_host + (size_t)pg * kTile * D, pobs, obs_bytes);
+                bulk_commit();
+            }
+            if (!obs_bulk)                                         // ragged last page whose byte count is not a multiple of 16
+                #pragma unroll 1
+                for (int e = lane; e < nvalid * D; e += kTile) {
+                    gobs[e] = pobs[e];
+                    if (p.obs_host) p.obs_host[(size_t)pg * kTile * D + e] = pobs[e];
+                }
+        };
+        if (hold) {
+            held_page = page; held_slot = slot; held_rew = rew; held_trunc = trunc;
+        } else {
+            if (!waited) {                                          // inputs-ready mode: first store of this warp (warp-uniform)
+                waited = true;
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+            }
+            if (held_page >= 0) { publish(held_page, held_slot, held_rew, held_trunc); held_page = -1; }
+            publish(page, slot, rew, trunc);
+        }
+        stamp();                                                   // [3], [5]: page published (or held)
         page = next;
         next = claim(drawn);
         next_issued = false;
