@@ -197,6 +197,7 @@ int dsim_policy32_forward(DsimPolicy32 *h, const float *obs_dev, const float *pr
                           float *logits_dev, float *value_dev, void *stream);
 
 /* -- instrumentation */
+int64_t dsim_debug_guard_check(DsimHandle *h);   /* handles created with DSIM_GUARD=1 in the environment: canary bytes overwritten so far (0 = none), -1 = no canaries */
 int64_t dsim_launch_count(const DsimHandle *h);                                 /* kernels launched by this handle */
 int dsim_debug_timeline(DsimHandle *h, uint64_t *out /*[npages][8] %globaltimer ns*/, int64_t capacity);   /* needs DSIM_TIMELINE=1 at create */
 int dsim_kernel_info(int which /*0 step fp32, 1 step fp64*/, int32_t *regs, int32_t *local_bytes, int32_t *max_threads);

@@ -23,7 +23,7 @@ EXPORTS = [
     "dsim_set_params", "dsim_get_params", "dsim_get_consts", "dsim_reset_all", "dsim_reset_masked", "dsim_reset_at",
     "dsim_forward", "dsim_zero_act", "dsim_step", "dsim_evaluate", "dsim_step_host", "dsim_set_inputs_ready", "dsim_set_reference", "dsim_control_reference",
     "dsim_set_state", "dsim_get_state", "dsim_compute_states", "dsim_buffer", "dsim_stats", "dsim_sync",
-    "dsim_launch_count", "dsim_kernel_info", "dsim_debug_timeline", "dsim_beta_policy", "dsim_trajectory_reference", "dsim_policy_blob_sizes", "dsim_policy_create", "dsim_policy_destroy", "dsim_policy_forward", "dsim_policy_forward_sample", "dsim_policy_error", "dsim_policy32_blob_elems", "dsim_policy32_create", "dsim_policy32_destroy", "dsim_policy32_forward",
+    "dsim_launch_count", "dsim_debug_guard_check", "dsim_kernel_info", "dsim_debug_timeline", "dsim_beta_policy", "dsim_trajectory_reference", "dsim_policy_blob_sizes", "dsim_policy_create", "dsim_policy_destroy", "dsim_policy_forward", "dsim_policy_forward_sample", "dsim_policy_error", "dsim_policy32_blob_elems", "dsim_policy32_create", "dsim_policy32_destroy", "dsim_policy32_forward",
 ]
 
 
@@ -93,6 +93,8 @@ def load():
     L.dsim_sync.argtypes = [vp, vp]
     L.dsim_launch_count.argtypes = [vp]
     L.dsim_launch_count.restype = C.c_int64
+    L.dsim_debug_guard_check.argtypes = [vp]
+    L.dsim_debug_guard_check.restype = C.c_int64
     L.dsim_debug_timeline.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int64]
     L.dsim_beta_policy.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.c_int64, C.c_uint32, vp, C.c_int, vp, vp, vp]
     L.dsim_policy_blob_sizes.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

@@ -187,6 +187,8 @@ struct DsimHandle {
     int first_reset_done;
     int ro_dirty;                      // a kernel that rewrote the read-only pages was queued since the last step
     int inputs_ready;                  // dsim_set_inputs_ready
+    int guard;                         // DSIM_GUARD=1 at create: every device buffer sits between two 4 KB canary regions (dsim_debug_guard_check)
+    void *gbase[16]; size_t gsize[16]; int ng;
     cudaStream_t hs[3];                // host entry point: copy-in, compute, copy-out streams (created on first use)
     cudaEvent_t ev_in[kHostChunks], ev_k[kHostChunks], ev_a, ev_b, ev_c;
     int host_pipeline_ready;
@@ -195,6 +197,7 @@ struct DsimHandle {
 };
 
 static char g_create_err[512] = "";
+constexpr size_t kGuardBytes = 4096;
 
 static int fail(DsimHandle *h, int code, const char *fmt, const char *detail) {
     char *dst = h ? h->err : g_create_err;
@@ -323,8 +326,12 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
     h->h = cfg->round_precision ? round_prec5(1.0 / cfg->frequency) : 1.0 / cfg->frequency;
 #define ALLOC(ptr, bytes)                                                                                  \
     do {                                                                                                   \
-        cudaError_t e2 = cudaMalloc((void **)&(ptr), (bytes));                                             \
-        if (e2 == cudaSuccess) e2 = cudaMemset((ptr), 0, (bytes));                                         \
+        const size_t g_ = h->guard ? kGuardBytes : 0, b_ = ((size_t)(bytes) + 15) / 16 * 16;               \
+        char *base_ = nullptr;                                                                             \
+        cudaError_t e2 = cudaMalloc((void **)&base_, b_ + 2 * g_);                                         \
+        if (e2 == cudaSuccess && g_) e2 = cudaMemset(base_, 0xA5, b_ + 2 * g_);                            \
+        if (e2 == cudaSuccess) e2 = cudaMemset(base_ + g_, 0, b_);                                         \
+        if (e2 == cudaSuccess) { *(void **)&(ptr) = base_ + g_; if (g_ && h->ng < 16) { h->gbase[h->ng] = base_; h->gsize[h->ng++] = b_; } } \
         if (e2 != cudaSuccess) { fail(nullptr, e2 == cudaErrorMemoryAllocation ? DSIM_ENOMEM : DSIM_ECUDA, "allocation failed: %s", cudaGetErrorString(e2)); dsim_destroy(h); return e2 == cudaErrorMemoryAllocation ? DSIM_ENOMEM : DSIM_ECUDA; } \
     } while (0)
     if ((e = cudaSetDevice(device)) != cudaSuccess) { delete h; return fail(nullptr, DSIM_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); }
@@ -337,17 +344,18 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
         if (getenv("DSIM_VERBOSE")) fprintf(stderr, "dsim: persisting L2 set-aside %zu MB (max %d MB)\n", want >> 20, maxb >> 20);
     }
     const size_t ld = h->ld, n = h->n, rs = h->rs;
+    h->guard = getenv("DSIM_GUARD") ? 1 : 0;                  // debug: exact-size buffers between canaries (compute-sanitizer is closed on the pool)
     ALLOC(h->rw, (size_t)RW_ROWS * ld * rs);
     ALLOC(h->ro, (size_t)RO_ROWS * ld * rs);
     ALLOC(h->refp, (size_t)REF_ROWS * ld * rs);
-    ALLOC(h->obs, (size_t)DSIM_MAX_OBS * ld * rs);
-    ALLOC(h->reward, ld * rs);
+    ALLOC(h->obs, h->guard ? (size_t)h->obs_dim * n * rs : (size_t)DSIM_MAX_OBS * ld * rs);
+    ALLOC(h->reward, (h->guard ? n : ld) * rs);
     ALLOC(h->states33, (size_t)h->state_width * n * rs);
-    ALLOC(h->actions_stage, 4 * ld * rs);
+    ALLOC(h->actions_stage, 4 * (h->guard ? n : ld) * rs);
     ALLOC(h->params64, 6 * ld * sizeof(double));
     ALLOC(h->stats, 8 * sizeof(double));
     ALLOC(h->center_hw, 12 * sizeof(double));
-    ALLOC(h->trunc, ld);
+    ALLOC(h->trunc, h->guard ? n : ld);
     ALLOC(h->ticket, 256);
     if (getenv("DSIM_TIMELINE")) ALLOC(h->timeline, (size_t)h->npages * 8 * sizeof(unsigned long long));   // debug instrumentation
 #undef ALLOC
@@ -380,7 +388,7 @@ extern "C" void dsim_destroy(DsimHandle *h) {
     }
     void *ptrs[] = {h->rw, h->ro, h->refp, h->obs, h->reward, h->states33, h->actions_stage,
                     h->params64, h->stats, h->center_hw, h->trunc, h->timeline, h->ticket};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : ptrs) if (p) cudaFree(h->guard ? (char *)p - kGuardBytes : (char *)p);
     delete h;
 }
 
@@ -934,6 +942,22 @@ extern "C" int dsim_beta_policy(const void *logits_dev, int n, int precision, ui
     const void *fn = precision == DSIM_FP32 ? (const void *)beta_policy_kernel<float, 4> : (const void *)beta_policy_kernel<double, 4>;
     if (cudaLaunchKernelExC(&lc, fn, args) != cudaSuccess) return DSIM_ECUDA;
     return cudaGetLastError() == cudaSuccess ? DSIM_OK : DSIM_ECUDA;
+}
+
+// debug (handles created with DSIM_GUARD=1): number of canary bytes around the handle's device buffers that no longer hold
+// their pattern = out-of-bounds device writes since dsim_create; -1 when the handle has no canaries
+extern "C" int64_t dsim_debug_guard_check(DsimHandle *h) {
+    if (!h || !h->guard) return -1;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -2;
+    std::vector<unsigned char> t(kGuardBytes);
+    int64_t bad = 0;
+    for (int k = 0; k < h->ng; k++)
+        for (int side = 0; side < 2; side++) {
+            const char *src = (const char *)h->gbase[k] + (side ? kGuardBytes + h->gsize[k] : 0);
+            if (cudaMemcpy(t.data(), src, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+            for (unsigned char c : t) bad += c != 0xA5;
+        }
+    return bad;
 }
 
 extern "C" int64_t dsim_launch_count(const DsimHandle *h) { return h ? h->launches : 0; }

@@ -523,6 +523,10 @@ class BaseDroneEnv(_VectorEnv):
             self._L.dsim_destroy(h)
             self._h = C.c_void_p()
 
+    def guard_check(self):
+        """envs created with DSIM_GUARD=1 in the environment: canary bytes around the device buffers overwritten so far"""
+        return int(self._L.dsim_debug_guard_check(self._h))
+
     def launch_count(self):
         return int(self._L.dsim_launch_count(self._h))
 

@@ -262,3 +262,20 @@ def test_inputs_ready_mode_is_bit_identical_to_strict_stepping(n):
         assert a.episode_stats()["n_episodes"] == b.episode_stats()["n_episodes"] > 0
     for envs in sets:
         [e.close() for e in envs]
+
+
+def test_no_out_of_bounds_device_writes_canaries():
+    """compute-sanitizer is closed on the pool: own check instead.  DSIM_GUARD=1 allocates every device buffer of a handle at
+    its exact size between two 4 KB canary regions; tools/sanitize_smoke.py drives ragged sizes (1, 33, 65, 97, 1000, 4129,
+    76007 envs) through every step-kernel instantiation, both dependency modes, in-kernel resets, evaluate, the host entry
+    point and the auxiliary kernels, and asserts that no canary byte changed."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DSIM_GUARD="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_smoke.py")], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = re.search(r"handles with intact canaries: (\d+)", r.stdout)
+    assert m and int(m.group(1)) >= 30, r.stdout[-500:]
