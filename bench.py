@@ -733,7 +733,9 @@ def main():
                           if R > 1 else "not flushed (single replica)"),
                    "replicas": R,
                    "inputs_ready": (("dsim_set_inputs_ready(1) on every replica: the kernel queued before a replica's step belongs to another replica, so the step "
-                                     "prefetches its first state / action pages before the programmatic-dependency wait (PDL); extras.strict_deps is the same run without it")
+                                     "fetches its pages and runs its physics ahead of the programmatic-dependency wait (PDL) and waits just before its first store; "
+                                     "results are bit-identical (tests/test_gpu_parity_r2.py); extras.strict_deps is the same graph without the promise, "
+                                     "extras.hot_l2 one replica stepped back to back")
                                     if overlap else "off: inputs are touched only after the previous kernel has completed"),
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
