@@ -63,17 +63,41 @@ __device__ __forceinline__ void dense(const float *__restrict__ Wt_, const float
         #pragma unroll
         for (int r = 0; r < 8; r++) acc[r][j] = b;
     }
-    #pragma unroll 4
-    for (int k = 0; k < K; k++) {
-        const float4 a0 = *reinterpret_cast<const float4 *>(At + k * LDT + ty * 8), a1 = *reinterpret_cast<const float4 *>(At + k * LDT + ty * 8 + 4);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        float w[CN];
+    // software pipeline over k in blocks of KB: the W and A operands of block b + 1 are fetched while block b is multiplied
+    // (an unpipelined loop sat 28 % of its time on the first FFMA of every block waiting for the L1 / L2 round trip)
+    constexpr int KB = 2;
+    static_assert(K % KB == 0, "K must be a multiple of the pipeline block");
+    const float *wq = Wt + tx;
+    const float *ap = At + ty * 8;
+    float w[2][KB][CN];
+    float4 a[2][KB][2];
+    #pragma unroll
+    for (int u = 0; u < KB; u++) {
         #pragma unroll
-        for (int j = 0; j < CN; j++) w[j] = __ldg(Wt + (size_t)k * N + tx + 32 * j);
-        #pragma unroll
-        for (int r = 0; r < 8; r++)
+        for (int j = 0; j < CN; j++) w[0][u][j] = __ldg(wq + u * N + 32 * j);
+        a[0][u][0] = *reinterpret_cast<const float4 *>(ap + u * LDT); a[0][u][1] = *reinterpret_cast<const float4 *>(ap + u * LDT + 4);
+    }
+    #pragma unroll 2
+    for (int kb = 0; kb < K / KB; kb++) {
+        const int cur = kb & 1, nxt = cur ^ 1;
+        if (kb + 1 < K / KB) {
+            const float *wn = wq + (size_t)(kb + 1) * KB * N;
+            const float *an = ap + (kb + 1) * KB * LDT;
             #pragma unroll
-            for (int j = 0; j < CN; j++) acc[r][j] = fmaf(a[r], w[j], acc[r][j]);
+            for (int u = 0; u < KB; u++) {
+                #pragma unroll
+                for (int j = 0; j < CN; j++) w[nxt][u][j] = __ldg(wn + u * N + 32 * j);
+                a[nxt][u][0] = *reinterpret_cast<const float4 *>(an + u * LDT); a[nxt][u][1] = *reinterpret_cast<const float4 *>(an + u * LDT + 4);
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < KB; u++) {
+            const float av[8] = {a[cur][u][0].x, a[cur][u][0].y, a[cur][u][0].z, a[cur][u][0].w, a[cur][u][1].x, a[cur][u][1].y, a[cur][u][1].z, a[cur][u][1].w};
+            #pragma unroll
+            for (int r = 0; r < 8; r++)
+                #pragma unroll
+                for (int j = 0; j < CN; j++) acc[r][j] = fmaf(av[r], w[cur][u][j], acc[r][j]);
+        }
     }
     #pragma unroll
     for (int j = 0; j < CN; j++) {
