@@ -502,7 +502,10 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     // long_sb on the ticket's consumer), so a launch that needs more draws than it has time for becomes atomic-bound.  The
     // chunk keeps >= 8 draws per warp for load balance.  A second counter of finished warps re-zeroes both.
     const bool stealing = my_pages > 2 * nwarps;
-    const int chunk = stealing ? max(1, min(8, (my_pages - 2 * nwarps) / (8 * nwarps))) : 1;
+#ifndef DSIM_CHUNK_DIV
+#define DSIM_CHUNK_DIV 8
+#endif
+    const int chunk = stealing ? max(1, min(16, (my_pages - 2 * nwarps) / (DSIM_CHUNK_DIV * nwarps))) : 1;
     int chunk_next = 0, chunk_end = 0;                             // pages of the current chunk still to be handed out
     auto draw = [&]() {
         unsigned tk = 0;
