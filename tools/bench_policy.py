@@ -30,7 +30,11 @@ def timeit(fn, reps=30):
 flops = 2 * n * (6 * 32 + 32 * 8 + 28 * 256 + 256 * 128 + 3 * 128 * 128 + 128 * 8 + 128)
 t = timeit(lambda: fused(obs, prev, logits_out=lg, value_out=val))
 fused.check()
-print(f"fused tcgen05     {t:9.1f} us  {flops / t / 1e6:8.1f} TFLOP/s (useful)  {n / t:8.1f} M rows/s")
+print(f"fused tcgen05     {t:9.1f} us  {flops / t / 1e6:8.1f} TFLOP/s (useful)  {n / t:8.1f} M rows/s   (bf16 operands)")
+f32 = M.policy.FP32RMAFull(model)
+t = timeit(lambda: f32(obs, prev, logits_out=lg, value_out=val), 10)
+print(f"fused FP32 pipe   {t:9.1f} us  {flops / t / 1e6:8.1f} TFLOP/s (useful)  {n / t:8.1f} M rows/s   (FP32-faithful)")
+fused(obs, prev, logits_out=lg, value_out=val)
 with torch.no_grad():
     t = timeit(lambda: model(obs, prev), 10)
     print(f"torch fp32        {t:9.1f} us  {flops / t / 1e6:8.1f} TFLOP/s")
