@@ -185,9 +185,13 @@ class BaseDroneEnv(_VectorEnv):
         self._h_reward = torch.empty((n,), dtype=tdt, **pin)
         self._h_trunc = torch.empty((n,), dtype=torch.uint8, **pin)
         self._d_actions = torch.empty((n, 4), dtype=tdt, device=self._device)
+        # numpy views / raw pointers of the pinned staging buffers (the compat vector_step path)
+        self._np_actions, self._np_obs = self._h_actions.numpy(), self._h_obs.numpy()
+        self._p_actions, self._p_obs = self._h_actions.data_ptr(), self._h_obs.data_ptr()
+        self._p_reward, self._p_trunc = self._h_reward.data_ptr(), self._h_trunc.data_ptr()
         self._last_obs = None
         self._sensor_stale = False
-        self._states_cache = None
+        self._states_cache = None; self._states_frozen = False
         _VectorEnv.__init__(self, self.observation_space, self.action_space, self.num_drones)
 
     # ------------------------------------------------------------------ plumbing
@@ -271,7 +275,7 @@ class BaseDroneEnv(_VectorEnv):
         self._ck(self._L.dsim_step(self._h, C.c_void_p(actions.data_ptr()), self._stream()))
         self.total_steps += 1
         self._sensor_stale = False
-        self._states_cache = None
+        self._states_cache = None; self._states_frozen = False
         return self.obs_tensor, self.reward_tensor, self.truncated_tensor
 
     def evaluate_tensor(self, actions):
@@ -286,7 +290,7 @@ class BaseDroneEnv(_VectorEnv):
     def reset_tensor(self):
         self._ck(self._L.dsim_reset_all(self._h, self._stream()))
         self._sensor_stale = False                                          # dsim_reset_all ends with mj_forward
-        self._states_cache = None
+        self._states_cache = None; self._states_frozen = False
         return self.obs_tensor
 
     def reset_masked(self, mask):
@@ -294,7 +298,7 @@ class BaseDroneEnv(_VectorEnv):
         m = mask.to(device=self._device, dtype=self._torch.uint8).contiguous()
         self._ck(self._L.dsim_reset_masked(self._h, C.c_void_p(m.data_ptr()), self._stream()))
         self._sensor_stale = True
-        self._states_cache = None
+        self._states_cache = None; self._states_frozen = False
 
     def step_host(self, actions, obs_out=None, reward_out=None, trunc_out=None):
         """End-to-end path with HOST float32 arrays.  Pinned arrays (e.g. views of torch `pin_memory()` tensors): one kernel
@@ -316,7 +320,7 @@ class BaseDroneEnv(_VectorEnv):
         self._ck(self._L.dsim_step_host(self._h, ptr(a), ptr(obs_out), ptr(reward_out), ptr(trunc_out), self._stream()))
         self.total_steps += 1
         self._sensor_stale = False
-        self._states_cache = None
+        self._states_cache = None; self._states_frozen = False
         return obs_out, reward_out, trunc_out
 
     def episode_stats(self, reset=False):
@@ -350,14 +354,17 @@ class BaseDroneEnv(_VectorEnv):
                 off = self._reference.copy()
                 off[:3] -= np.asarray(self.start_pos[:3], dtype=np.float64)
                 r[:, :, :] = self._torch.as_tensor(off, dtype=r.dtype, device=self._device)[:, None, None]
-            self._states_cache = None
+            self._states_cache = None; self._states_frozen = False
 
     @property
     def states(self):
         """`self.states` of the reference (:148,273,325): refreshed by vector_step / reset_model, NOT by reset_at (Q1).
         Computed lazily; reset_at freezes the pre-reset rows first so the staleness is preserved."""
         if self._states_cache is None:
-            self._states_cache = self.get_drone_states()
+            if self._states_frozen:      # rows computed on the device before a reset_at changed the state: only the read-back was deferred
+                self._states_cache = list(self.tensor(_lib.BUF_STATES33).to('cpu').numpy().astype(np.float64))
+            else:
+                self._states_cache = self.get_drone_states()
         return self._states_cache
 
     @property
@@ -408,7 +415,7 @@ class BaseDroneEnv(_VectorEnv):
                                         None if a is None else a.ctypes.data_as(dp),
                                         None if ns is None else ns.ctypes.data_as(C.POINTER(C.c_int32)), self._stream()))
         self._ck(self._L.dsim_forward(self._h, 0, self._stream()))
-        self._states_cache = None
+        self._states_cache = None; self._states_frozen = False
 
     # ------------------------------------------------------------------ RLlib VectorEnv surface
     def _obs_to_list(self):
@@ -425,15 +432,26 @@ class BaseDroneEnv(_VectorEnv):
         a = np.asarray(actions, dtype=np.float64)
         if a.size != 4 * self.num_drones:
             raise ValueError("Action dimension mismatch")                       # mujoco_env_custom.py:200-201
-        self._h_actions.copy_(self._torch.from_numpy(a.reshape(self.num_drones, 4)))
-        self._d_actions.copy_(self._h_actions, non_blocking=True)
-        self._ck(self._L.dsim_step(self._h, C.c_void_p(self._d_actions.data_ptr()), self._stream()))
-        self.total_steps += 1
-        self._sensor_stale = False
-        self._states_cache = None
-        self._h_reward.copy_(self.reward_tensor, non_blocking=True)
-        self._h_trunc.copy_(self.truncated_tensor, non_blocking=True)
-        obs = self._fetch_obs()
+        if self._np_dtype == np.float32:
+            # pinned staging buffers + the zero-copy host entry point: ONE kernel launch whose bulk loads / stores move the
+            # actions and the outputs over PCIe, one stream synchronise - no separate copies
+            self._np_actions[...] = a.reshape(self.num_drones, 4)
+            self._ck(self._L.dsim_step_host(self._h, self._p_actions, self._p_obs, self._p_reward, self._p_trunc, self._stream()))
+            self.total_steps += 1
+            self._sensor_stale = False
+            self._states_cache = None; self._states_frozen = False
+            self._last_obs = self._np_obs.astype(np.float64)
+            obs = list(self._last_obs)
+        else:
+            self._h_actions.copy_(self._torch.from_numpy(a.reshape(self.num_drones, 4)))
+            self._d_actions.copy_(self._h_actions, non_blocking=True)
+            self._ck(self._L.dsim_step(self._h, C.c_void_p(self._d_actions.data_ptr()), self._stream()))
+            self.total_steps += 1
+            self._sensor_stale = False
+            self._states_cache = None; self._states_frozen = False
+            self._h_reward.copy_(self.reward_tensor, non_blocking=True)
+            self._h_trunc.copy_(self.truncated_tensor, non_blocking=True)
+            obs = self._fetch_obs()
         rewards = list(self._h_reward.numpy().astype(np.float64))
         truncated = [bool(t) for t in self._h_trunc.numpy()]
         dones = [False] * self.num_drones                                        # Q7
@@ -453,7 +471,7 @@ class BaseDroneEnv(_VectorEnv):
             self._ck(self._L.dsim_zero_act(self._h, self._stream()))
         self._ck(self._L.dsim_reset_all(self._h, self._stream()))
         self._sensor_stale = False
-        self._states_cache = None
+        self._states_cache = None; self._states_frozen = False
         return self._fetch_obs()
 
     def vector_reset(self, seeds=None, options=None):
@@ -467,7 +485,14 @@ class BaseDroneEnv(_VectorEnv):
         if index is None:
             index = 0
         assert index < self.num_drones
-        _ = self.states                     # freeze the stale rows before the state changes
+        if self._states_cache is None and not self._states_frozen:
+            # freeze the stale rows before the state changes: computed on the device now (one launch, no sync), read back
+            # only if somebody looks at `env.states` before the next vector_step
+            if self._sensor_stale:
+                self._ck(self._L.dsim_forward(self._h, 0, self._stream()))
+                self._sensor_stale = False
+            self._ck(self._L.dsim_compute_states(self._h, self._stream()))
+            self._states_frozen = True
         self._ck(self._L.dsim_reset_at(self._h, int(index), self._stream()))
         self._sensor_stale = True          # reference: set_state -> mj_forward refreshes sensordata of ALL drones (Q2)
         if self._last_obs is None:
@@ -485,6 +510,8 @@ class BaseDroneEnv(_VectorEnv):
 
     def get_drone_states(self):
         """(:357-380) list of per-drone 33-vectors (29 without pendulum), float64."""
+        if self._states_frozen and self._states_cache is None:
+            _ = self.states                  # the buffer still holds the rows frozen by reset_at: materialise them before it is overwritten
         if self._sensor_stale:
             self._ck(self._L.dsim_forward(self._h, 0, self._stream()))
             self._sensor_stale = False
@@ -508,7 +535,7 @@ class BaseDroneEnv(_VectorEnv):
             buf[:, :self.num_drones] = axes
             axes = buf
         self._ck(self._L.dsim_control_reference(self._h, C.c_void_p(axes.data_ptr()), self._stream()))
-        self._states_cache = None
+        self._states_cache = None; self._states_frozen = False
 
     def render(self, *a, **k):
         return None

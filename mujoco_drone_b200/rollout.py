@@ -139,7 +139,7 @@ class RolloutRunner:
         if self._graph is not None:
             self._graph.replay()
             self.env.total_steps += 1            # what step_tensor does on the eager path
-            self.env._states_cache = None
+            self.env._states_cache = None; self.env._states_frozen = False
         else:
             self._one_step()
         self.values[t].copy_(self._val)
