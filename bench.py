@@ -56,10 +56,10 @@ WORKLOADS = {
                  cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True),
                  name="C4 env at 524288 envs/GPU (the per-GPU env count of config 5)"),
     # BASELINE.json configs[4]: the full rollout loop, 4M envs over 8 GPUs = 524288 per GPU: RMA_full forward (random init,
-    # param_embed_dim 8, train_adaptation False) -> MyBetaDist sampling -> fused env step, CUDA-graph replayed
+    # param_embed_dim 8, train_adaptation False; hand-written fused kernel) -> MyBetaDist sampling -> fused env step, CUDA-graph replayed
     "c5": dict(cls="LocalFrameRPYParamsEnv", reward="distance_energy_reward", envs_per_gpu=524288, alg_bytes=104 + 94 + 88 + 24,
                cfg=dict(param_difficulty=1.0, state_difficulty=0.3, max_steps=1024, random_params=True), rollout=True,
-               name="C5: rollout loop = RMA_full policy (library GEMMs) + MyBetaDist sampling kernel + fused env-step kernel, 524288 envs/GPU (4M over 8 GPUs)"),
+               name="C5: rollout loop = RMA_full policy kernel (--policy-dtype: fused tcgen05 bf16 | fused_fp32 | torch) + MyBetaDist sampling kernel + fused env-step kernel, 524288 envs/GPU (4M over 8 GPUs)"),
 }
 
 
