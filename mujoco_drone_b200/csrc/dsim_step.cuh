@@ -86,11 +86,6 @@ DSIM_DEV void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes, uin
     (void)policy; bulk_s2g(gmem_dst, smem_src, bytes);
 #endif
 }
-// HBM -> L2 only.  Always safe ahead of the dependency wait: L2 is the point of coherence, a line that an earlier kernel still
-// writes is simply updated in place, nothing becomes visible to this SM before the real load is issued.
-DSIM_DEV void bulk_prefetch_l2(const void *gmem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
-}
 DSIM_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DSIM_DEV void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (the bulk store that follows)
@@ -380,19 +375,9 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     // touched after griddepcontrol.wait.
     unsigned long long t_entry = 0;
     if (timeline) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
-    // measured variants (tools/gpu_r2e.sh, C4, us per step, inputs-ready / strict): both static pages fetched up front
-    // (DSIM_EARLY2) 10.48 / 11.41 against 10.00 / 11.14 without - the second wave delays the first pages; page-less warp slot
-    // rotating over the schedulers (DSIM_DEAL) 10.48 / 11.41 against 10.40 / 11.31; dependents released after the wait in
-    // strict mode too: 11.1-11.4 against 10.6 with the release at entry.  Defaults = the fastest of each.
-#ifndef DSIM_EARLY2
-#define DSIM_EARLY2 0
-#endif
-#ifndef DSIM_LATEWAIT
-#define DSIM_LATEWAIT 1
-#endif
-#ifndef DSIM_DEAL
-#define DSIM_DEAL 0
-#endif
+    // (Scheduling variants that were measured and dropped - both static pages fetched up front, rotating page-less warp slot,
+    // dynamically claimed second pages, L2 prefetch ahead of the wait, deferred first-page publish, late release in strict
+    // mode - are listed with their numbers in DESIGN.md 4.1 item 6; the code is in the history, not here.)
     // Strict mode releases the dependent kernel at entry (its CTAs are scheduled as this grid's CTAs retire; it touches
     // nothing before its own wait).  Inputs-ready mode releases it only AFTER this kernel's own wait: a kernel that starts
     // early then knows that everything up to its predecessor's predecessor has completed, which is what makes its early
@@ -403,62 +388,23 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     const bool has_work = wid < my_pages;
     unsigned char *wslots = smem_raw + (size_t)warp * kStages * p.smem_per_slot;
     const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
-    // Page assignment.  The first two pages of a warp are static: page `wid`, then one of the next `nwarps` pages, dealt so
-    // that every CTA gets the same number of second pages (+-1) and the page-less warp slot rotates with the CTA index
-    // (warp slot w of a CTA lives on scheduler w of its SM: a fixed page-less slot would leave one of the four schedulers
-    // with half the work of the others).
+    // Page assignment.  The first two pages of a warp are static: page `wid`, then one of the next `nwarps` pages, dealt
+    // round-robin over the CTAs so that every CTA (hence every SM) gets the same number of second pages (+-1).
     int page = p.page0 + wid;
-#ifdef DSIM_DYN2      // experiment: second pages are claimed from a counter when the first page has landed (early warps take them)
-    int next = p.npages;
-    bool first_iter = my_pages > nwarps;
-#elif DSIM_DEAL
-    int next = p.page0 + nwarps + ((warp + (int)blockIdx.x) & (kStepWarps - 1)) * (int)gridDim.x + (int)blockIdx.x;
-#else
     int next = p.page0 + nwarps + warp * (int)gridDim.x + (int)blockIdx.x;
-#endif
-    // Loads that may start BEFORE the dependency wait: the read-only rows (`early_ro`), and with dsim_set_inputs_ready also
-    // the state / action / setpoint rows (`early_in`) - of both static pages: each warp owns two slots and both are free.
+    // Loads of the first page that may start BEFORE the dependency wait: the read-only rows (`early_ro`), and with
+    // dsim_set_inputs_ready also the state / action / setpoint rows (`early_in`).
     const int pre = (p.early_ro ? 1 : 0) | (p.early_in ? 2 : 0);
-    bool next_issued = false;
     if (has_work && lane == 0) {
         #pragma unroll
         for (int k = 0; k < kStages; k++) mbar_init(&s_bar[warp][k], 1);
         issue_page_loads(p, page, reinterpret_cast<T *>(wslots), &s_bar[warp][0], 4 | pre, pec, pref, eval_only, pol_keep, pol_stream);
-#if DSIM_EARLY2 && !defined(DSIM_DYN2)
-        if (next < p.npages)
-            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + p.smem_per_slot), &s_bar[warp][1], 4 | pre, pec, pref, eval_only, pol_keep, pol_stream);
-#endif
     }
-#if DSIM_EARLY2 && !defined(DSIM_DYN2)
-    next_issued = next < p.npages;
-#endif
-#ifndef DSIM_PREFETCH
-#define DSIM_PREFETCH 0
-#endif
-#if DSIM_PREFETCH
-    // Experiment, off by default.  Strict mode: the state / action / setpoint rows may not be LOADED before the wait, but they
-    // may be pulled from HBM into L2 (both static pages), so that the first-page burst after the wait hits L2.  It does
-    // (page landed 1.15 us after the release instead of 2.0), but the prefetch traffic competes with the tail of the kernel
-    // ahead, whose completion - and with it the release - moves 1.6 us later: C4 strict 11.55 against 10.82 us without
-    // (tools/gpu_r2k.sh).  HBM is ~72 % busy over a step: there is no idle bandwidth to prefetch into.
-    if (has_work && lane == 0 && !p.early_in) {
-        #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int pg = k == 0 ? page : next;
-            if (pg < p.npages) {
-                bulk_prefetch_l2(p.rw + (size_t)pg * (RW_ROWS * kTile), (eval_only ? RW_ROWS : RW_IN_ROWS) * kTile * (uint32_t)sizeof(T));
-                bulk_prefetch_l2(p.actions + (size_t)pg * (kTile * 4), (uint32_t)min(kTile, p.n - pg * kTile) * 4u * (uint32_t)sizeof(T));
-                if (pref) bulk_prefetch_l2(p.refp + (size_t)pg * (REF_ROWS * kTile), REF_ROWS * kTile * (uint32_t)sizeof(T));
-                if (pec && !p.early_ro) bulk_prefetch_l2(p.ro + (size_t)pg * (RO_ROWS * kTile), RO_ROWS * kTile * (uint32_t)sizeof(T));
-            }
-        }
-    }
-#endif
     // With inputs_ready the wait moves to just before this warp's first store (the physics of the first page overlaps the
     // tail of the kernel ahead); otherwise nothing an earlier kernel may have written is touched before it.  The dependents
     // are released only AFTER the wait: a kernel that starts early therefore knows that everything before its predecessor
     // has completed (the early loads of the inputs-ready mode rely on exactly that).
-    bool waited = !(DSIM_LATEWAIT && p.early_in);
+    bool waited = p.early_in == 0;
     if (waited) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (trigger_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -482,17 +428,12 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     stamp();                                                       // [1] dependency wait passed (inputs-ready mode: prologue done, the wait comes later)
     const int obs_id = OBS >= 0 ? OBS : p.obs_id, reward_id = REW >= 0 ? REW : p.reward_id;
     const int D = DC > 0 ? DC : p.obs_dim;
-    if (lane == 0 && pre != 3) {
+    if (lane == 0 && pre != 3)
         issue_page_loads(p, page, reinterpret_cast<T *>(wslots), &s_bar[warp][0], 3 & ~pre, pec, pref, eval_only, pol_keep, pol_stream);
-        if (next_issued)
-            issue_page_loads(p, next, reinterpret_cast<T *>(wslots + p.smem_per_slot), &s_bar[warp][1], 3 & ~pre, pec, pref, eval_only, pol_keep, pol_stream);
-    }
     __syncwarp();                                                  // barrier init visible to the waiting lanes
     unsigned parity = 0;                                           // bit b: phase of this warp's barrier b
     int buf = 0;
-    // Page assignment.  The first two pages of a warp are static: page `wid`, then one of the next `nwarps` pages dealt
-    // round-robin over the CTAs (so that every SM gets the same number of second pages).  No atomic sits in front of the
-    // first page: 2368 warps drawing from one counter at kernel entry cost each of them ~2 us (same-address atomics
+    // No atomic sits in front of the first two (static) pages: 2368 warps drawing from one counter at kernel entry cost each of them ~2 us (same-address atomics
     // serialise in L2), more than the page load they were meant to overlap.  From the third page on, work stealing: a warp
     // draws one ticket per processed page, half an iteration before it claims it (raw atom: the compiler's warp-aggregated
     // atomicAdd consumes its result at once), so the round trip to L2 hides behind the post-processing.  Launches with at
@@ -502,10 +443,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
     // long_sb on the ticket's consumer), so a launch that needs more draws than it has time for becomes atomic-bound.  The
     // chunk keeps >= 8 draws per warp for load balance.  A second counter of finished warps re-zeroes both.
     const bool stealing = my_pages > 2 * nwarps;
-#ifndef DSIM_CHUNK_DIV
-#define DSIM_CHUNK_DIV 8
-#endif
-    const int chunk = stealing ? max(1, min(16, (my_pages - 2 * nwarps) / (DSIM_CHUNK_DIV * nwarps))) : 1;
+    const int chunk = stealing ? max(1, min(16, (my_pages - 2 * nwarps) / (8 * nwarps))) : 1;
     int chunk_next = 0, chunk_end = 0;                             // pages of the current chunk still to be handed out
     auto draw = [&]() {
         unsigned tk = 0;
@@ -520,13 +458,6 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         }
         return chunk_next++;
     };
-#ifndef DSIM_DEFER
-#define DSIM_DEFER 0       // measured (tools/gpu_r2m.sh, C4 inputs-ready): holding the first page back 10.29 us, publishing it at once 9.32 us
-#endif
-    int held_page = -1;                                            // first page of an inputs-ready warp, waiting for the dependency wait
-    T *held_slot = nullptr;
-    T held_rew = T(0);
-    bool held_trunc = false;
     #pragma unroll 1
     while (page < p.npages) {
         const int i = page * kTile + lane;
@@ -536,17 +467,6 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         mbar_wait(&s_bar[warp][buf], (parity >> buf) & 1u);
         parity ^= 1u << buf;
         stamp();                                                   // [2], [4]: page landed
-#ifdef DSIM_DYN2
-        if (first_iter) {
-            first_iter = false;
-            unsigned tk = 0;
-            if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(tk) : "l"(p.ticket + 2));
-            const int cand = __reduce_max_sync(0xffffffffu, lane == 0 ? p.page0 + nwarps + (int)tk : 0);
-            const int second_pages = min(my_pages - nwarps, nwarps);
-            if (lane == 0 && (int)tk == nwarps - 1) p.ticket[2] = 0u;             // every warp draws exactly once: the last draw re-zeroes
-            next = ((int)(cand - p.page0 - nwarps) < second_pages) ? cand : p.npages;
-        }
-#endif
 
         // ---- physics
         T *col = s_rw + lane;
@@ -555,7 +475,7 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         EnvState<T> s = load_state(col);
         // ---- prefetch the next page into the other slot.  Its previous contents left with the bulk stores issued at the
         // end of the previous iteration; their shared-memory reads complete within a few hundred cycles.
-        if (lane == 0 && next < p.npages && !next_issued) {
+        if (lane == 0 && next < p.npages) {
             bulk_wait_read();
             issue_page_loads(p, next, reinterpret_cast<T *>(wslots + (size_t)(buf ^ 1) * p.smem_per_slot), &s_bar[warp][buf ^ 1], 7, pec, pref, eval_only, pol_keep, pol_stream);
         }
@@ -609,13 +529,6 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             ObsWriter<T, 1> w; w.base = s_obs + lane * D; w.stride = 1;
             emit_obs<T, PEND>(obs_id, s, ps, mk(p.start_t[0], p.start_t[1], p.start_t[2]), ref_off, prm, w);
         }
-        // Experiment (DSIM_DEFER, off): inputs-ready mode, launches with at most two pages per warp (both slots stay private):
-        // the FIRST page is not published when it is done - its reward / truncated flag ride in two registers, its rows stay
-        // in the slot - so that the second page's physics also runs ahead of the dependency wait and both pages leave after
-        // it.  Measured slower: the stores bunch up at the end of the grid and lengthen its straggler tail (last exit 15.9
-        // against 14.3 us after the first entry).  What did pay is the placement of the wait itself: as the very last thing
-        // before the first global store, after the statistics, the state write-back into the slot and the reset path.
-        const bool hold = DSIM_DEFER && !waited && !stealing && next < p.npages;
         if (!eval_only) {
             // would-be ground contact (the floor plane is out of reach in the BASELINE configs; detected, never ignored)
             if (active && p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(p.stats + 4, 1.0);
@@ -660,21 +573,18 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
                     if (p.obs_host) p.obs_host[(size_t)pg * kTile * D + e] = pobs[e];
                 }
         };
-        if (hold) {
-            held_page = page; held_slot = slot; held_rew = rew; held_trunc = trunc;
-        } else {
-            if (!waited) {                                          // inputs-ready mode: first store of this warp (warp-uniform)
-                waited = true;
-                asm volatile("griddepcontrol.wait;" ::: "memory");
-                asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-            }
-            if (held_page >= 0) { publish(held_page, held_slot, held_rew, held_trunc); held_page = -1; }
-            publish(page, slot, rew, trunc);
+        if (!waited) {
+            // inputs-ready mode: the dependency wait is the very LAST thing before this warp's first global store (warp-uniform),
+            // after the statistics, the write-back of the state into the slot and the reset path: 9.3 us per C4 step against
+            // 10.1 us with the wait in front of that tail work
+            waited = true;
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         }
-        stamp();                                                   // [3], [5]: page published (or held)
+        publish(page, slot, rew, trunc);
+        stamp();                                                   // [3], [5]: page published
         page = next;
         next = claim(drawn);
-        next_issued = false;
         buf ^= 1;
     }
     if (lane == 0) bulk_wait_read();                               // the slots must outlive the bulk reads
