@@ -750,6 +750,9 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": wl.get("traffic"),
                      "traffic_source": wl.get("traffic_src"),
+                     # the same launch against the same peak on the bytes it ACTUALLY moves (measured DRAM traffic): how close to the
+                     # HBM roof the kernel runs on its own page layout; `frac` above is on the algorithmic bytes
+                     "traffic_frac": (wl["traffic"] / (k_ms * 1e-3) / 1e9 / peak) if wl.get("traffic") else None,
                      # bytes the page layout moves per launch: read 24 of the 27 read-write rows (the sensordata rows are write-only) + the 19
                      # read-only rows when parameters are per env + 16 B of actions (+ 16 B setpoints); write 27 rows + the observation row + 5 B
                      "traffic_pages": n * ((96 + (76 if wl["cfg"].get("random_params", True) else 0) + 16 + (16 if wl["cfg"].get("per_env_reference") else 0))
