@@ -654,6 +654,7 @@ static int enqueue_host_pipeline(DsimHandle *h, const KParams<float> &base, cons
         CK(cudaStreamWaitEvent(root, h->ev_in[k], 0));
         KParams<float> kp = base;
         kp.page0 = p0; kp.npages = p1; kp.ticket = h->ticket + 4 * k;       // its own work-stealing counters
+        kp.early_in = 0;                                                    // chunks of one step: strict ordering (the action rows arrive through event-ordered copies)
         CK(launch_step<float>(h, kp, root));
         CK(cudaEventRecord(h->ev_k[k], root));
         CK(cudaStreamWaitEvent(s_out, h->ev_k[k], 0));
