@@ -26,7 +26,7 @@ def demangle(names):
 
 print("# nvcc " + " ".join(FLAGS) + "  (nvcc " + subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-2].strip() + ")")
 with tempfile.TemporaryDirectory() as td:
-    for src in ("dsim_kernels.cu", "dsim_policy_mlp.cu"):
+    for src in ("dsim_kernels.cu", "dsim_policy_mlp.cu", "dsim_policy_fp32.cu"):
         r = subprocess.run(["nvcc"] + FLAGS + [os.path.join(CSRC, src), "-o", os.path.join(td, "o.o")], capture_output=True, text=True)
         txt = r.stderr
         ents = re.findall(r"Compiling entry function '([^']+)' for 'sm_100a'\n.*?Function properties for [^\n]+\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers(?:, used (\d+) barriers)?(?:, (\d+) bytes smem)?", txt, re.S)
