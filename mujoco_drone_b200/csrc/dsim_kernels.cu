@@ -353,7 +353,7 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
     ALLOC(h->states33, (size_t)h->state_width * n * rs);
     ALLOC(h->actions_stage, 4 * (h->guard ? n : ld) * rs);
     ALLOC(h->params64, 6 * ld * sizeof(double));
-    ALLOC(h->stats, 8 * sizeof(double));
+    ALLOC(h->stats, (size_t)kStatReplicas * 8 * sizeof(double));
     ALLOC(h->center_hw, 12 * sizeof(double));
     ALLOC(h->trunc, h->guard ? n : ld);
     ALLOC(h->ticket, 256);
@@ -891,7 +891,7 @@ extern "C" int dsim_buffer(DsimHandle *h, int id, void **ptr, int64_t *rows, int
     case DSIM_BUF_RESET_COUNT: *ptr = rw + RW_RESET_COUNT * row_bytes; *rows = 1; *cols = n; *ld = L; *dtype = idt; *page_rows = RW_ROWS; break;
     case DSIM_BUF_STATES33: *ptr = h->states33; *rows = n; *cols = h->state_width; *ld = h->state_width; *dtype = rdt; break;
     case DSIM_BUF_SENSORDATA: *ptr = rw + S_ACC * row_bytes; *rows = 3; *cols = n; *ld = L; *dtype = rdt; *page_rows = RW_ROWS; break;
-    case DSIM_BUF_STATS: *ptr = h->stats; *rows = 1; *cols = 8; *ld = 8; *dtype = DSIM_DT_F64; break;
+    case DSIM_BUF_STATS: *ptr = h->stats; *rows = kStatReplicas; *cols = 8; *ld = 8; *dtype = DSIM_DT_F64; break;
     default: return fail(h, DSIM_EINVAL, "unknown buffer id%s", "");
     }
     return DSIM_OK;
@@ -901,8 +901,10 @@ extern "C" int dsim_stats(DsimHandle *h, double out[8], int reset) {
     if (!h || !out) return DSIM_EINVAL;
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(out, h->stats, 8 * sizeof(double), cudaMemcpyDeviceToHost));
-    if (reset) CK(cudaMemset(h->stats, 0, 8 * sizeof(double)));
+    double t[kStatReplicas * 8];
+    CK(cudaMemcpy(t, h->stats, sizeof t, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; k++) { out[k] = 0; for (int r = 0; r < kStatReplicas; r++) out[k] += t[r * 8 + k]; }
+    if (reset) CK(cudaMemset(h->stats, 0, sizeof t));
     return DSIM_OK;
 }
 

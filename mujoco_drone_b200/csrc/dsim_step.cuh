@@ -92,6 +92,13 @@ DSIM_DEV void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;"
 DSIM_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------ kernel parameter block (constant bank)
+// episode statistics are accumulated into kStatReplicas copies of the 8 counters (warp w adds to copy w % kStatReplicas,
+// dsim_stats sums them): every truncation costs three FP64 atomics, ~3400 per C4 step in the steady state, and atomics on
+// ONE address retire one after the other on the L2 slice that owns it
+#ifndef DSIM_STAT_REPLICAS
+#define DSIM_STAT_REPLICAS 64
+#endif
+constexpr int kStatReplicas = DSIM_STAT_REPLICAS;
 template <typename T> struct KParams {
     int n, npages;            // npages: one past the last page of this launch
     int page0;                // first page of this launch (0 unless the host entry point steps the batch in chunks)
@@ -100,7 +107,7 @@ template <typename T> struct KParams {
     T *refp;                  // [npages][REF_ROWS][32] (per-env setpoints) or nullptr
     T *obs, *reward;          // [n][obs_dim], [n]
     unsigned char *trunc;
-    double *stats;
+    double *stats;            // [kStatReplicas][8]
     const T *actions;         // [n][4]
     T uconst[C_ROWS];         // uniform-parameter fast path (random_params == False)
     T uparams[6];
@@ -531,11 +538,12 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
         }
         if (!eval_only) {
             // would-be ground contact (the floor plane is out of reach in the BASELINE configs; detected, never ignored)
-            if (active && p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(p.stats + 4, 1.0);
+            double *const st = p.stats + (wid & (kStatReplicas - 1)) * 8;
+            if (active && p.start_t[2] + s.pos.z < prm[4] + T(0.5)) atomicAdd(st + 4, 1.0);
             T ret = col[RW_EP_RETURN * kTile] + rew;
             if (trunc && active) {
-                atomicAdd(p.stats + 0, (double)ret); atomicAdd(p.stats + 1, (double)ns); atomicAdd(p.stats + 2, 1.0);
-                if (bad) atomicAdd(p.stats + 3, 1.0);
+                atomicAdd(st + 0, (double)ret); atomicAdd(st + 1, (double)ns); atomicAdd(st + 2, 1.0);
+                if (bad) atomicAdd(st + 3, 1.0);
             }
             col[RW_EP_RETURN * kTile] = trunc ? T(0) : ret;
             col[RW_NUM_STEPS * kTile] = int_to_slot<T>(ns);
