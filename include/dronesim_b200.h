@@ -81,7 +81,9 @@ typedef struct DsimConfig {
     int32_t round_precision;       /* 1: apply mjcf precision=5 ("%.5g") to every model attribute (env_gen.py:129) */
     double frequency;              /* config['frequency'] -> timestep = 1/frequency (env_gen.py:82) */
     int32_t obs_id, reward_id;     /* wrapper class / config['reward_fcn'] resolved by name */
-    int32_t reserved0;             /* must be 0 */
+    int32_t ground_contact;        /* 1: contacts of the drone's geoms with the floor plane z = 0 are simulated (env_gen.py:14-21,97:
+                                      plane vs box / cylinder / sphere, condim 3, pyramidal cone, MuJoCo's default solref / solimp);
+                                      0: the floor is out of reach and only would-be contacts are counted (n_near_ground) */
     int32_t per_env_reference;     /* 0: one reference shared by all drones (BaseDroneEnv.py:80) */
     int32_t auto_reset;            /* 1: truncated envs are re-sampled inside the step kernel (native loop) */
     int32_t random_start_pos, random_params;

@@ -32,7 +32,7 @@ class DsimConfig(C.Structure):
         ("struct_size", C.c_int32), ("abi_version", C.c_int32), ("num_envs", C.c_int32), ("precision", C.c_int32),
         ("env_id_offset", C.c_int64), ("seed", C.c_uint32), ("pendulum", C.c_int32), ("frame_skip", C.c_int32),
         ("round_precision", C.c_int32), ("frequency", C.c_double), ("obs_id", C.c_int32), ("reward_id", C.c_int32),
-        ("reserved0", C.c_int32), ("per_env_reference", C.c_int32), ("auto_reset", C.c_int32),
+        ("ground_contact", C.c_int32), ("per_env_reference", C.c_int32), ("auto_reset", C.c_int32),
         ("random_start_pos", C.c_int32), ("random_params", C.c_int32),
         ("reference", C.c_double * 4), ("start_pos", C.c_double * 4), ("max_distance", C.c_double),
         ("max_steps", C.c_int64), ("max_pos_offset", C.c_double),

@@ -229,8 +229,12 @@ template <typename T> DSIM_DEV V3<T> ldl3_solve(const Ldl3<T> &f, V3<T> b) {
 
 // ------------------------------------------------------------------ one mj_step (Euler, implicit hinge damping)
 // ADVANCE=false evaluates only the forward part (mj_forward: accelerometer refresh after set_state).
-template <typename T, bool PEND, bool ADVANCE>
-DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T h) {
+// GROUND: floor contacts (dsim_contact.cuh) for drones whose bounding sphere reaches the floor; `g` is only read then.
+template <typename T> struct GroundCtx;
+template <typename T> struct ContactIO;
+template <typename T> __device__ int contact_solve(ContactIO<T> &io, const EnvConsts<T> &c, const GroundCtx<T> &g);
+template <typename T, bool PEND, bool ADVANCE, bool GROUND = false>
+DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T h, const GroundCtx<T> *g = nullptr) {
     // -- kinematics (mj_kinematics normalises the free-joint quaternion)
     const T qn = s.qw * s.qw + s.qx * s.qx + s.qy * s.qy + s.qz * s.qz;
     const bool qok = qn >= T(1e-30);                                         // mju_normalize4: a (near-)zero quaternion becomes identity
@@ -346,8 +350,9 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
     const V3<T> ac0 = inv_m * F + cross(com, al0);
     V3<T> a_e = ac0, al_e = al0, a_i = ac0, al_i = al0;
     T hax_i = 0, hay_i = 0;
+    T hax_e = 0, hay_e = 0;
+    const T rx = f_x - bias_x, ry = f_y - bias_y;
     if (PEND) {
-        const T rx = f_x - bias_x, ry = f_y - bias_y;
         const V3<T> px = (-mu * cy) * yc, py = mu * xd;                      // linear momentum per unit hinge rate
         const V3<T> Lx = mk(IC + P + QmP * n.x * n.x, QmP * n.x * n.y, QmP * n.x * n.z) + mk(dl * px.y, -dl * px.x, T(0));
         const V3<T> Ly = P * yc + mk(dl * py.y, -dl * py.x, T(0));
@@ -362,6 +367,7 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
             const T hax = (Syy * r1 - Sxy * r2) * idet, hay = (Sxx * r2 - Sxy * r1) * idet;
             a_e = ac0 - hax * acx - hay * acy;
             al_e = al0 - hax * alx - hay * aly;
+            hax_e = hax; hay_e = hay;
         }
         if (ADVANCE) {  // implicit in joint damping (mj_EulerSkip): (M + h diag(B)) qacc = qfrc_smooth
             const T hb = h * T(kHingeDamping);
@@ -370,6 +376,26 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
             hax_i = (Syy2 * r1 - Sxy * r2) * idet; hay_i = (Sxx2 * r2 - Sxy * r1) * idet;
             a_i = ac0 - hax_i * acx - hay_i * acy;
             al_i = al0 - hax_i * alx - hay_i * aly;
+        }
+    }
+
+    if constexpr (GROUND) {
+        // -- mj_collision + mj_fwdConstraint for the few drones that can touch the floor (slow path, not inlined)
+        const T zo = g->start_z + s.pos.z;
+        if (zo < g->reach) {
+            ContactIO<T> io;
+            io.q[0] = F.x; io.q[1] = F.y; io.q[2] = F.z; io.q[3] = Tq.x; io.q[4] = Tq.y; io.q[5] = Tq.z; io.q[6] = rx; io.q[7] = ry;
+            io.v[0] = vb.x; io.v[1] = vb.y; io.v[2] = vb.z; io.v[3] = om.x; io.v[4] = om.y; io.v[5] = om.z; io.v[6] = PEND ? s.hvx : T(0); io.v[7] = PEND ? s.hvy : T(0);
+            io.x[0] = a_e.x; io.x[1] = a_e.y; io.x[2] = a_e.z; io.x[3] = al_e.x; io.x[4] = al_e.y; io.x[5] = al_e.z; io.x[6] = hax_e; io.x[7] = hay_e;
+            io.nb[0] = R.m[6]; io.nb[1] = R.m[7]; io.nb[2] = R.m[8];
+            io.t1[0] = R.m[3]; io.t1[1] = R.m[4]; io.t1[2] = R.m[5];
+            io.t2[0] = -R.m[0]; io.t2[1] = -R.m[1]; io.t2[2] = -R.m[2];
+            io.zo = zo; io.sx = sx; io.cx = cx; io.sy = sy; io.cy = cy; io.h = h;
+            if (contact_solve(io, c, *g) > 0) {
+                a_e = mk(io.x[0], io.x[1], io.x[2]); al_e = mk(io.x[3], io.x[4], io.x[5]);
+                a_i = mk(io.xi[0], io.xi[1], io.xi[2]); al_i = mk(io.xi[3], io.xi[4], io.xi[5]);
+                hax_i = io.xi[6]; hay_i = io.xi[7];
+            }
         }
     }
 

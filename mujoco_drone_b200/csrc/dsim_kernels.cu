@@ -16,6 +16,7 @@
 #include "dsim_device.cuh"
 #include "dsim_obs_reward.cuh"
 #include "dsim_params.cuh"
+#include "dsim_contact.cuh"
 #include "dsim_policy.cuh"
 
 using namespace dsim;
@@ -36,7 +37,10 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const KParams<T> p, int
     EnvState<T> s = load_state(col);
     const EnvConsts<T> c = load_consts(p, ro_col, p.per_env_consts != 0);
     const T ctrl[4] = {T(0), T(0), T(0), T(0)};
-    substep<T, PEND, false>(s, c, ctrl, p.h);
+    if (p.ground) {
+        const GroundCtx<T> g = make_ground_ctx<T>(p.start_t[2], p.params64, p.ld, i, p.round_precision, p.pendulum);
+        substep<T, PEND, false, true>(s, c, ctrl, p.h, &g);
+    } else substep<T, PEND, false>(s, c, ctrl, p.h);
     col[S_ACC * kTile] = s.acc.x; col[(S_ACC + 1) * kTile] = s.acc.y; col[(S_ACC + 2) * kTile] = s.acc.z;
     if (refresh_obs) {
         V3<T> ref_off; T ref_yaw; double ref64[3];
@@ -261,6 +265,7 @@ template <typename T> static KParams<T> make_params(const DsimHandle *h, const v
     p.timeline = h->timeline; p.ticket = h->ticket;
     p.early_ro = h->ro_dirty ? 0 : 1;
     p.early_in = h->inputs_ready ? 1 : 0;
+    p.params64 = h->params64; p.ld = h->ld; p.round_precision = c.round_precision; p.pendulum = c.pendulum; p.ground = c.ground_contact;
     return p;
 }
 
@@ -296,6 +301,7 @@ static int validate(const DsimConfig *c) {
         if (!(c->reward_id <= 2 || c->reward_id == 10))
             return fail(nullptr, DSIM_EUNSUPPORTED, "pendulum=False supports only rewards that do not index pendulum state%s", "");
     }
+    if (c->ground_contact != 0 && c->ground_contact != 1) return fail(nullptr, DSIM_EINVAL, "ground_contact must be 0 or 1%s", "");
     if (c->frame_skip < 1 || c->frequency <= 0) return fail(nullptr, DSIM_EINVAL, "frame_skip >= 1 and frequency > 0 required%s", "");
     return DSIM_OK;
 }
@@ -559,6 +565,10 @@ template <typename K> static cudaError_t launch_one(DsimHandle *h, K kernel, uns
 template <typename T> static cudaError_t launch_step(DsimHandle *h, const KParams<T> &kp, cudaStream_t st) {
     const unsigned smem = kp.smem_per_slot * kStages * kStepWarps;
     const int pages = kp.npages - kp.page0;
+    if (h->cfg.ground_contact) {                                           // generic instantiation + floor-contact slow path
+        if (!h->cfg.pendulum) return launch_one(h, step_kernel<T, false, -1, -1, -1, true>, smem, st, &kp, pages);
+        return launch_one(h, step_kernel<T, true, -1, -1, -1, true>, smem, st, &kp, pages);
+    }
     if (!h->cfg.pendulum) return launch_one(h, step_kernel<T, false, -1, -1>, smem, st, &kp, pages);
 #ifdef DSIM_TL_ALL
     if (std::is_same<T, float>::value && !kp.eval_only) {

@@ -128,6 +128,9 @@ template <typename T> struct KParams {
     // device-resident ones (posted PCIe writes from the same bulk stores; no copy-engine pass), or nullptr
     T *obs_host, *reward_host;
     unsigned char *trunc_host;
+    // floor contact (DsimConfig.ground_contact): raw FP64 drone_params [6][ld] the contact path rebuilds the geoms from
+    const double *params64;
+    int ld, round_precision, pendulum, ground;
 };
 
 // integer rows of the read-write page are stored in a lane-sized slot (int32 for float pages, int64 for double)
@@ -353,7 +356,8 @@ template <typename T> DSIM_DEV void issue_page_loads(const KParams<T> &p, int pa
 // and the next launch only starts grabbing once this grid has completed), so launches and CUDA-graph replays need no host reset.
 // CFG >= 0 (specialised instantiations): bit 0 per-env constants, bit 1 per-env setpoints, bit 2 frame_skip == 1 - the host
 // launches such an instantiation only when the handle's configuration matches; -1: everything is a run-time option
-template <typename T, bool PEND, int OBS, int REW, int CFG = -1>
+// GROUND: the generic instantiation with the floor-contact slow path compiled in (DsimConfig.ground_contact)
+template <typename T, bool PEND, int OBS, int REW, int CFG = -1, bool GROUND = false>
 __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[kStepWarps][kStages];
@@ -494,7 +498,14 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             #pragma unroll
             for (int k = 0; k < 4; k++) ctrl[k] = clamp_(T(0.1) + T(0.9) * a[k], T(0), T(1));   // :269 + ctrlrange (0,1) clamp of mj_fwdActuation
             #pragma unroll 1
-            for (int f = 0; f < frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
+            if constexpr (GROUND) {
+                const GroundCtx<T> g = make_ground_ctx<T>(p.start_t[2], p.params64, p.ld, active ? i : 0, p.round_precision, p.pendulum);
+                #pragma unroll 1
+                for (int f = 0; f < frame_skip; f++) substep<T, PEND, true, true>(s, c, ctrl, p.h, &g);
+            } else {
+                #pragma unroll 1
+                for (int f = 0; f < frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);
+            }
         }
         const unsigned drawn = draw();                             // for the page after `next`; claimed at the end of the iteration
         // ---- counters, termination, reward, observation

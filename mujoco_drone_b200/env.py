@@ -122,6 +122,9 @@ class BaseDroneEnv(_VectorEnv):
         self.env_id_offset = int(g('env_id_offset', 0))
         self.round_precision = bool(g('round_precision', True))
         self._inputs_ready = bool(g('inputs_ready', False))
+        # floor contact (env_gen.py:14-21,97): off by default - the floor is out of reach in the training configs (z = 15 m,
+        # truncation at 4 m) and would-be contacts are only counted (episode_stats()['n_near_ground']); on: simulated
+        self.ground_contact = bool(g('ground_contact', False))
         self._regen_epoch = 0
         # seed: reference uses config.get('worker_index', -1) + 1 + seed (BaseDroneEnv.py:113, Q5)
         self.seed_value = int(g('worker_index', -1) + 1 + g('seed', 1))
@@ -147,6 +150,7 @@ class BaseDroneEnv(_VectorEnv):
         cfg.obs_id = int(self.OBS_ID)
         cfg.reward_id = int(self.reward_id)
         cfg.per_env_reference = int(self.per_env_reference)
+        cfg.ground_contact = int(self.ground_contact)
         cfg.auto_reset = int(self.auto_reset)
         cfg.random_start_pos = int(bool(self.random_start_pos))
         cfg.random_params = int(bool(self.random_params))

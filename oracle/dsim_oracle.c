@@ -191,6 +191,13 @@ static void body_from_geoms(const OGeom *g, int ng, double *mass, double ipos[3]
     *mass = M; v3_copy(ipos, com);
 }
 
+static void add_geom(OrcModel *m, int body, const OGeom *g) {
+    OrcGeom *o = &m->geom[m->ngeom++];
+    o->body = body; o->type = g->type; o->yaw = g->yaw;
+    memcpy(o->size, g->size, sizeof o->size); memcpy(o->pos, g->pos, sizeof o->pos);
+}
+static void set_invweight0(OrcModel *m);
+
 void orc_compile(const double params[6], int pendulum_enabled, double frequency, int rp, OrcModel *m) {
     memset(m, 0, sizeof *m);
     memcpy(m->params, params, 6 * sizeof(double));
@@ -229,12 +236,27 @@ void orc_compile(const double params[6], int pendulum_enabled, double frequency,
     }
     m->site_pos[4][2] = rnd(-hb / 4, rp);                                   /* 'sense' site, env_gen.py:48 */
     body_from_geoms(g, ng, &m->mass[2], m->ipos[2], m->iquat[2], m->inertia[2]);
+    /* collision geoms of core_body: the 9 above, the massless 'front' box (:47) and the four propeller discs (:60) */
+    for (int i = 0; i < ng; i++) add_geom(m, 2, &g[i]);
+    {
+        OGeom f; memset(&f, 0, sizeof f);
+        f.type = 0; f.size[0] = rnd(hb / 3, rp); f.size[1] = rnd(0.15 * hb, rp); f.size[2] = rnd(0.15 * hb, rp); f.pos[0] = rnd(hb + hb / 3, rp);
+        add_geom(m, 2, &f);
+        for (int i = 0; i < 4; i++) {
+            double theta = i * PI / 2 - PI / 4, rr = sqrt(2.0) * hb + arm_len;
+            OGeom q; memset(&q, 0, sizeof q);
+            q.type = 1; q.size[0] = rnd(arm_len / 1.5, rp); q.size[1] = 0.0025;
+            q.pos[0] = rnd(rr * cos(theta) + 0.0, rp); q.pos[1] = rnd(rr * sin(theta) + 0.0, rp); q.pos[2] = rnd(0.0 + 0.025, rp);
+            add_geom(m, 2, &q);
+        }
+    }
     if (pendulum) {
         /* body 3 = link: hinge x, sphere r=.02 m=.01 (env_gen.py:66-68) */
         m->pos[3][2] = rnd(-hb / 2, rp);
         m->jnt_type[3] = 2; m->jnt_axis[3][0] = 1; m->dofadr[3] = 6; m->qposadr[3] = 7; m->dof_body[6] = 3; m->damping[6] = 0.15;
         OGeom s; memset(&s, 0, sizeof s); s.type = 2; s.size[0] = 0.02; s.mass = 0.01;
         body_from_geoms(&s, 1, &m->mass[3], m->ipos[3], m->iquat[3], m->inertia[3]);
+        add_geom(m, 3, &s);
         /* body 4 = pendulum: hinge y, pole cylinder + weight box (env_gen.py:69-72) */
         m->jnt_type[4] = 2; m->jnt_axis[4][1] = 1; m->dofadr[4] = 7; m->qposadr[4] = 8; m->dof_body[7] = 4; m->damping[7] = 0.15;
         OGeom p[2]; memset(p, 0, sizeof p);
@@ -242,7 +264,9 @@ void orc_compile(const double params[6], int pendulum_enabled, double frequency,
         double sz = rnd(0.1 * cbrt(weight_mass), rp);
         p[1].type = 0; p[1].size[0] = p[1].size[1] = p[1].size[2] = sz; p[1].pos[2] = rnd(-pend_len, rp); p[1].mass = rnd(weight_mass, rp);
         body_from_geoms(p, 2, &m->mass[4], m->ipos[4], m->iquat[4], m->inertia[4]);
+        add_geom(m, 4, &p[0]); add_geom(m, 4, &p[1]);
     }
+    set_invweight0(m);
 }
 
 /* ------------------------------------------------------------------ dynamics (generic, MuJoCo layout) */
@@ -258,6 +282,8 @@ typedef struct {
     double M[ORC_MAXNV * ORC_MAXNV];
     double qfrc_bias[ORC_MAXNV], qfrc_passive[ORC_MAXNV], qfrc_actuator[ORC_MAXNV], qfrc_smooth[ORC_MAXNV];
     double site_xpos[5][3];
+    double qfrc_constraint[ORC_MAXNV];
+    int ncon;
 } OData;
 
 static void inert_mulvec(double *res, const double *I, const double *v) {
@@ -464,6 +490,223 @@ static void solve_dense(int n, const double *A, const double *b, double *x) {
     }
 }
 
+
+/* ------------------------------------------------------------------ floor contact (models with `ground` set)
+ * env_gen.py:14-21: every drone geom has contype 1 / conaffinity 0, condim 3, friction (1, .5, .5), margin 0; the floor
+ * (:97) is a default plane geom (contype = conaffinity = 1, friction (1, .005, .0001)) at z = 0.  Drone geoms therefore
+ * collide with the floor and with nothing else.  Contact parameters are MuJoCo's defaults on both sides: solref (0.02, 1),
+ * solimp (0.9, 0.95, 0.001, 0.5, 2), friction = element-wise max -> mu = 1, condim 3, pyramidal cone, impratio 1.
+ * [MuJoCo's algorithm restated from its documentation / engine_collision_primitive.c / engine_core_constraint.c; unpinned.] */
+static void geom_pose(const OData *d, const OrcGeom *g, double gp[3], double gm[9]) {
+    double t[3]; m3_mulv(t, d->xmat[g->body], g->pos); v3_add(gp, d->xpos[g->body], t);
+    double c = cos(g->yaw), s = sin(g->yaw), Rz[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
+    m3_mul(gm, d->xmat[g->body], Rz);
+}
+static int add_con(OrcContact *con, int n, const double p[3], double dist, int body, int geom) {
+    if (n >= ORC_MAXCON) return n;
+    /* contact position: half-way between the geom's point and the plane surface */
+    con[n].pos[0] = p[0]; con[n].pos[1] = p[1]; con[n].pos[2] = p[2] - 0.5 * dist;
+    con[n].dist = dist; con[n].body = body; con[n].geom = geom;
+    return n + 1;
+}
+static int collide_floor(const OrcModel *m, const OData *d, OrcContact *con) {
+    const double margin = 0.0;
+    int n = 0;
+    for (int gi = 0; gi < m->ngeom; gi++) {
+        const OrcGeom *g = &m->geom[gi];
+        double gp[3], gm[9];
+        geom_pose(d, g, gp, gm);
+        const double dist0 = gp[2];                                   /* plane through the origin, normal +z */
+        if (g->type == 2) {                                           /* mjc_PlaneSphere */
+            double dist = dist0 - g->size[0];
+            if (dist > margin) continue;
+            double p[3] = {gp[0], gp[1], gp[2] - g->size[0]};
+            n = add_con(con, n, p, dist, g->body, gi);
+        } else if (g->type == 0) {                                    /* mjc_PlaneBox: corners below the plane that point down, at most 4 */
+            int cnt = 0;
+            for (int i = 0; i < 8 && cnt < 4; i++) {
+                double v[3] = {(i & 1 ? 1 : -1) * g->size[0], (i & 2 ? 1 : -1) * g->size[1], (i & 4 ? 1 : -1) * g->size[2]}, c[3];
+                m3_mulv(c, gm, v);
+                double ldist = c[2];
+                if (dist0 + ldist > margin || ldist > 0) continue;
+                double p[3] = {gp[0] + c[0], gp[1] + c[1], gp[2] + c[2]};
+                n = add_con(con, n, p, dist0 + ldist, g->body, gi); cnt++;
+            }
+        } else {                                                      /* mjc_PlaneCylinder */
+            double axis[3] = {gm[2], gm[5], gm[8]};
+            double prjaxis = axis[2];
+            if (prjaxis > 0) { v3_scl(axis, axis, -1.0); prjaxis = -prjaxis; }
+            /* direction inside the disc plane that points most steeply towards the floor: -z projected */
+            double vec[3] = {axis[0] * prjaxis, axis[1] * prjaxis, axis[2] * prjaxis - 1.0};
+            double len = sqrt(v3_dot(vec, vec));
+            if (len < 1e-12) { vec[0] = gm[0] * g->size[0]; vec[1] = gm[3] * g->size[0]; vec[2] = gm[6] * g->size[0]; }   /* disc parallel to the floor */
+            else v3_scl(vec, vec, g->size[0] / len);
+            double prjvec = vec[2];
+            v3_scl(axis, axis, g->size[1]); prjaxis *= g->size[1];
+            if (dist0 + prjaxis + prjvec > margin) continue;
+            double p[3];
+            for (int k = 0; k < 3; k++) p[k] = gp[k] + axis[k] + vec[k];
+            n = add_con(con, n, p, dist0 + prjaxis + prjvec, g->body, gi);
+            if (dist0 - prjaxis + prjvec <= margin) {                 /* same direction on the far cap */
+                for (int k = 0; k < 3; k++) p[k] = gp[k] - axis[k] + vec[k];
+                n = add_con(con, n, p, dist0 - prjaxis + prjvec, g->body, gi);
+            }
+            double prjvec1 = -0.5 * prjvec;                           /* two more points of the near rim, 120 degrees away */
+            if (dist0 + prjaxis + prjvec1 <= margin) {
+                double side[3]; v3_cross(side, vec, axis);
+                double sl = sqrt(v3_dot(side, side));
+                v3_scl(side, side, g->size[0] * sqrt(3.0) / 2 / (sl > 1e-300 ? sl : 1e-300));
+                for (int sg = -1; sg <= 1; sg += 2) {
+                    for (int k = 0; k < 3; k++) p[k] = gp[k] + axis[k] - 0.5 * vec[k] + sg * side[k];
+                    n = add_con(con, n, p, dist0 + prjaxis + prjvec1, g->body, gi);
+                }
+            }
+        }
+    }
+    return n;
+}
+
+/* translational Jacobian of world point `point` moving with `body`: jp[k] for every dof k (mj_jac) */
+static void jac_point(const OrcModel *m, const OData *d, const double *point, int body, double jp[][3]) {
+    double off[3]; v3_sub(off, point, d->com);
+    for (int k = 0; k < m->nv; k++) {
+        if (m->dof_body[k] > body) { v3_zero(jp[k]); continue; }
+        double tmp[3]; v3_cross(tmp, d->cdof[k], off); v3_add(jp[k], d->cdof[k] + 3, tmp);
+    }
+}
+
+/* mjModel.body_invweight0 (engine_setconst.c, set0): at qpos0, A = J M^-1 J^T with the 6 x nv Jacobian of the body at its
+ * COM; translation weight = mean of the first three diagonal entries, rotation weight = mean of the last three */
+static void set_invweight0(OrcModel *m) {
+    double qpos0[ORC_MAXNQ] = {0, 0, 0, 1, 0, 0, 0, 0, 0};
+    OData d;
+    kin_com(m, qpos0, &d); crb(m, &d);
+    int nv = m->nv;
+    for (int b = 2; b < m->nbody; b++) {
+        double jp[ORC_MAXNV][3], tr = 0, rot = 0;
+        jac_point(m, &d, d.xipos[b], b, jp);
+        for (int a = 0; a < 3; a++) {
+            double col[ORC_MAXNV], x[ORC_MAXNV];
+            for (int k = 0; k < nv; k++) col[k] = jp[k][a];
+            solve_dense(nv, d.M, col, x);
+            for (int k = 0; k < nv; k++) tr += col[k] * x[k];
+            for (int k = 0; k < nv; k++) col[k] = m->dof_body[k] > b ? 0.0 : d.cdof[k][a];
+            solve_dense(nv, d.M, col, x);
+            for (int k = 0; k < nv; k++) rot += col[k] * x[k];
+        }
+        m->invweight0[b][0] = fmax(MJMINVAL, tr / 3); m->invweight0[b][1] = fmax(MJMINVAL, rot / 3);
+    }
+}
+
+/* mj_makeConstraint + mj_makeImpedance for the contacts, then the convex problem of mj_fwdConstraint:
+ *   qacc = argmin_x  1/2 (x - qacc_smooth)^T M (x - qacc_smooth) + sum_rows 1/2 D_r min(0, J_r x - aref_r)^2
+ * (primal form, pyramidal cone: every row is a one-sided soft constraint).  The minimiser is unique (M > 0), so any solver
+ * that converges reproduces MuJoCo's Newton solver up to its tolerance; this one is Newton with an exact line search. */
+static void fwd_constraint(const OrcModel *m, const double *qvel, OData *d, double *qacc) {
+    static const double solref[2] = {0.02, 1.0}, solimp[5] = {0.9, 0.95, 0.001, 0.5, 2.0};
+    const int nv = m->nv;
+    OrcContact con[ORC_MAXCON];
+    memset(d->qfrc_constraint, 0, sizeof d->qfrc_constraint);
+    const int ncon = collide_floor(m, d, con);
+    d->ncon = ncon;
+    if (!ncon) return;
+    const int nrow = 4 * ncon;
+    static __thread double J[4 * ORC_MAXCON][ORC_MAXNV], aref[4 * ORC_MAXCON], Dv[4 * ORC_MAXCON], jar[4 * ORC_MAXCON], jd[4 * ORC_MAXCON];
+    /* reference acceleration parameters (mj_makeImpedance: getsolparam), refsafe: timeconst >= 2 timestep */
+    const double tc = fmax(solref[0], 2 * m->timestep), dr = solref[1], dmax = solimp[1];
+    const double K = 1.0 / fmax(MJMINVAL, dmax * dmax * tc * tc * dr * dr), B = 2.0 / fmax(MJMINVAL, dmax * tc);
+    const double mu = 1.0;                                           /* max(1, 1) / sqrt(impratio = 1) */
+    for (int c = 0; c < ncon; c++) {
+        double jp[ORC_MAXNV][3];
+        jac_point(m, d, con[c].pos, con[c].body, jp);
+        /* impedance d(r): smooth step of |r| / width between solimp[0] and solimp[1] (midpoint, power) */
+        double x = fabs(con[c].dist) / solimp[2], y;
+        if (x >= 1) y = 1;
+        else if (x <= solimp[3]) y = pow(x, solimp[4]) / pow(solimp[3], solimp[4] - 1);
+        else y = 1 - pow(1 - x, solimp[4]) / pow(1 - solimp[3], solimp[4] - 1);
+        const double imp = solimp[0] + y * (solimp[1] - solimp[0]);
+        /* mj_diagApprox, pyramidal rows: tran + mu^2 tran with tran = invweight0 of the two bodies (the world's is 0);
+         * R = (1 - imp) / imp * diagApprox, then all rows of the contact get Rpy = 2 mu^2 R */
+        const double tran = m->invweight0[con[c].body][0];
+        const double R = 2 * mu * mu * fmax(MJMINVAL, (1 - imp) / imp * (tran + mu * mu * tran));
+        /* contact frame of a +z normal (mju_makeFrame): t1 = +y, t2 = -x; rows n + mu t1, n - mu t1, n + mu t2, n - mu t2 */
+        static const double dirs[4][3] = {{0, 1, 1}, {0, -1, 1}, {-1, 0, 1}, {1, 0, 1}};
+        for (int r = 0; r < 4; r++) {
+            const int i = 4 * c + r;
+            double vel = 0;
+            for (int k = 0; k < nv; k++) { J[i][k] = mu * (dirs[r][0] * jp[k][0] + dirs[r][1] * jp[k][1]) + jp[k][2]; vel += J[i][k] * qvel[k]; }
+            Dv[i] = 1.0 / R;
+            aref[i] = -B * vel - K * imp * con[c].dist;
+        }
+    }
+    /* Newton */
+    double x[ORC_MAXNV], g[ORC_MAXNV], H[ORC_MAXNV * ORC_MAXNV], dx[ORC_MAXNV], Mx[ORC_MAXNV] = {0};
+    memcpy(x, qacc, nv * sizeof(double));
+    double scale = 0;
+    for (int k = 0; k < nv; k++) scale += d->M[k * nv + k];
+    scale = 1.0 / (scale / nv * nv);                                  /* 1 / (meaninertia * nv), as MuJoCo scales its tolerance */
+    for (int it = 0; it < 100; it++) {
+        for (int k = 0; k < nv; k++) { Mx[k] = -d->qfrc_smooth[k]; for (int j = 0; j < nv; j++) Mx[k] += d->M[k * nv + j] * x[j]; }
+        memcpy(g, Mx, nv * sizeof(double)); memcpy(H, d->M, nv * nv * sizeof(double));
+        for (int i = 0; i < nrow; i++) {
+            double v = -aref[i];
+            for (int k = 0; k < nv; k++) v += J[i][k] * x[k];
+            jar[i] = v;
+            if (v >= 0) continue;
+            for (int k = 0; k < nv; k++) {
+                g[k] += Dv[i] * v * J[i][k];
+                for (int j = 0; j < nv; j++) H[k * nv + j] += Dv[i] * J[i][k] * J[i][j];
+            }
+        }
+        double gn = 0;
+        for (int k = 0; k < nv; k++) gn += g[k] * g[k];
+        if (sqrt(gn) * scale < 1e-13) break;
+        for (int k = 0; k < nv; k++) g[k] = -g[k];
+        solve_dense(nv, H, g, dx);
+        /* exact line search on phi'(a) = p0 + a p2 + sum_r D_r jd_r min(0, jar_r + a jd_r): increasing, piecewise linear */
+        double p0 = 0, p2 = 0;
+        for (int k = 0; k < nv; k++) { p0 += Mx[k] * dx[k]; for (int j = 0; j < nv; j++) p2 += dx[k] * d->M[k * nv + j] * dx[j]; }
+        for (int i = 0; i < nrow; i++) { double v = 0; for (int k = 0; k < nv; k++) v += J[i][k] * dx[k]; jd[i] = v; }
+        double a = 0;
+        for (int ls = 0; ls < 64; ls++) {
+            double f1 = p0 + a * p2, f2 = p2, nxt = 1e300;            /* value, slope, next breakpoint beyond a */
+            for (int i = 0; i < nrow; i++) {
+                /* row i is active (J x - aref < 0) just to the right of a: decided from its breakpoint, not from a rounded residual */
+                int act;
+                if (jd[i] != 0) {
+                    double bp = -jar[i] / jd[i];
+                    act = jd[i] < 0 ? (a >= bp) : (a < bp);
+                    if (bp > a && bp < nxt) nxt = bp;
+                } else act = jar[i] < 0;
+                if (act) { double v = jar[i] + a * jd[i]; f1 += Dv[i] * jd[i] * v; f2 += Dv[i] * jd[i] * jd[i]; }
+            }
+            if (f1 >= 0) break;                                       /* (only by rounding: phi' is negative left of the root) */
+            double root = a - f1 / f2;
+            if (root <= nxt) { a = root; break; }
+            a = nxt;
+        }
+        double big = 0;
+        for (int k = 0; k < nv; k++) { x[k] += a * dx[k]; big = fmax(big, fabs(a * dx[k]) / (1 + fabs(x[k]))); }
+        if (big < 1e-15) break;
+    }
+    memcpy(qacc, x, nv * sizeof(double));
+    for (int k = 0; k < nv; k++) {
+        double f = 0;
+        for (int i = 0; i < nrow; i++) {
+            double v = -aref[i];
+            for (int j = 0; j < nv; j++) v += J[i][j] * x[j];
+            if (v < 0) f -= Dv[i] * v * J[i][k];
+        }
+        d->qfrc_constraint[k] = f;
+    }
+}
+
+int orc_collide(const OrcModel *m, const double *qpos, OrcContact *con) {
+    OData d;
+    kin_com(m, qpos, &d);
+    return collide_floor(m, &d, con);
+}
+
 static void forward_core(const OrcModel *m, const double *qpos, const double *qvel, const double *act,
                          const double *ctrl, OData *d, double *qacc, double *act_dot, double *sensordata) {
     int nv = m->nv;
@@ -484,7 +727,8 @@ static void forward_core(const OrcModel *m, const double *qpos, const double *qv
         apply_ft(m, d, fw, tw, d->site_xpos[k], 2, d->qfrc_actuator);
     }
     for (int k = 0; k < nv; k++) d->qfrc_smooth[k] = d->qfrc_passive[k] - d->qfrc_bias[k] + d->qfrc_actuator[k];
-    solve_dense(nv, d->M, d->qfrc_smooth, qacc);       /* no contacts: qacc = qacc_smooth */
+    solve_dense(nv, d->M, d->qfrc_smooth, qacc);       /* qacc_smooth; stays the answer when no contact is active */
+    if (m->ground) fwd_constraint(m, qvel, d, qacc);
     /* accelerometer (mj_sensorAcc): site 'sense' on body 2 */
     double cacc[ORC_MAXBODY][6];
     rne(m, qvel, qacc, d, NULL, cacc);
@@ -507,6 +751,15 @@ void orc_forward(const OrcModel *m, const double *qpos, const double *qvel, cons
     if (qfrc_smooth_out) memcpy(qfrc_smooth_out, d.qfrc_smooth, m->nv * sizeof(double));
 }
 
+int orc_forward_contact(const OrcModel *m, const double *qpos, const double *qvel, const double *act, const double *ctrl,
+                        double *qacc, double *qfrc_constraint, double *sensordata) {
+    OData d;
+    double act_dot[4];
+    forward_core(m, qpos, qvel, act, ctrl, &d, qacc, act_dot, sensordata);
+    if (qfrc_constraint) memcpy(qfrc_constraint, d.qfrc_constraint, m->nv * sizeof(double));
+    return m->ground ? d.ncon : 0;
+}
+
 void orc_step(const OrcModel *m, double *qpos, double *qvel, double *act, const double *ctrl,
               double *sensordata, int nstep) {
     int nv = m->nv;
@@ -522,7 +775,9 @@ void orc_step(const OrcModel *m, double *qpos, double *qvel, double *act, const 
             double H[ORC_MAXNV * ORC_MAXNV];
             memcpy(H, d.M, nv * nv * sizeof(double));
             for (int k = 0; k < nv; k++) H[k * nv + k] += h * m->damping[k];
-            solve_dense(nv, H, d.qfrc_smooth, qacc_i);
+            double f[ORC_MAXNV];
+            for (int k = 0; k < nv; k++) f[k] = d.qfrc_smooth[k] + d.qfrc_constraint[k];
+            solve_dense(nv, H, f, qacc_i);
         } else memcpy(qacc_i, qacc, nv * sizeof(double));
         /* mj_advance */
         for (int k = 0; k < 4; k++) act[k] += h * act_dot[k];

@@ -17,6 +17,17 @@ _SO = os.path.join(_HERE, "libdsim_oracle.so")
 MAXBODY, MAXNV = 5, 8
 
 
+MAXGEOM, MAXCON = 21, 84
+
+
+class OrcGeom(C.Structure):
+    _fields_ = [("body", C.c_int), ("type", C.c_int), ("size", C.c_double * 3), ("pos", C.c_double * 3), ("yaw", C.c_double)]
+
+
+class OrcContact(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("dist", C.c_double), ("body", C.c_int), ("geom", C.c_int)]
+
+
 class OrcModel(C.Structure):
     _fields_ = [
         ("nbody", C.c_int), ("nv", C.c_int), ("nq", C.c_int), ("pendulum", C.c_int),
@@ -39,6 +50,9 @@ class OrcModel(C.Structure):
         ("timestep", C.c_double), ("density", C.c_double), ("viscosity", C.c_double),
         ("gravity", C.c_double * 3),
         ("params", C.c_double * 6),
+        ("ground", C.c_int), ("ngeom", C.c_int),
+        ("geom", OrcGeom * MAXGEOM),
+        ("invweight0", (C.c_double * 2) * MAXBODY),
     ]
 
 
@@ -102,6 +116,10 @@ def lib():
         L.orc_compile.argtypes = [dp, C.c_int, C.c_double, C.c_int, C.POINTER(OrcModel)]
         L.orc_forward.argtypes = [C.POINTER(OrcModel)] + [dp] * 9
         L.orc_step.argtypes = [C.POINTER(OrcModel), dp, dp, dp, dp, dp, C.c_int]
+        L.orc_collide.argtypes = [C.POINTER(OrcModel), dp, C.POINTER(OrcContact)]
+        L.orc_collide.restype = C.c_int
+        L.orc_forward_contact.argtypes = [C.POINTER(OrcModel)] + [dp] * 7
+        L.orc_forward_contact.restype = C.c_int
         L.orc_energy.argtypes = [C.POINTER(OrcModel), dp, dp, dp, dp]
         for f in (L.orc_quat2rpy, L.orc_rpy2quat, L.orc_quat2dcm, L.orc_pendulumrp2quat):
             f.argtypes = [dp, dp]
@@ -153,12 +171,27 @@ def round_prec5(x):
     return lib().orc_round_prec5(float(x))
 
 
-def compile_model(params, pendulum=True, frequency=100.0, round_precision=True):
-    """params: mass, arm_len, motor_force, motor_tau, pendulum_len, weight_mass."""
+def compile_model(params, pendulum=True, frequency=100.0, round_precision=True, ground=False):
+    """params: mass, arm_len, motor_force, motor_tau, pendulum_len, weight_mass.  ground: simulate floor contacts."""
     m = OrcModel()
     p = _arr(params, 6)
     lib().orc_compile(_dp(p), int(pendulum), float(frequency), int(round_precision), C.byref(m))
+    m.ground = int(ground)
     return m
+
+
+def collide(m, qpos):
+    """Floor contacts of configuration qpos: list of dicts (pos, dist, body, geom)."""
+    con = (OrcContact * MAXCON)()
+    n = lib().orc_collide(C.byref(m), _dp(_arr(qpos)), con)
+    return [dict(pos=np.array(con[i].pos[:]), dist=con[i].dist, body=con[i].body, geom=con[i].geom) for i in range(n)]
+
+
+def forward_contact(m, qpos, qvel, act, ctrl):
+    qpos, qvel, act, ctrl = _arr(qpos), _arr(qvel), _arr(act, 4), _arr(ctrl, 4)
+    qacc, qc, sens = np.zeros(m.nv), np.zeros(m.nv), np.zeros(3)
+    n = lib().orc_forward_contact(C.byref(m), _dp(qpos), _dp(qvel), _dp(act), _dp(ctrl), _dp(qacc), _dp(qc), _dp(sens))
+    return dict(qacc=qacc, qfrc_constraint=qc, sensordata=sens, ncon=n)
 
 
 def forward(m, qpos, qvel, act, ctrl):
@@ -281,7 +314,7 @@ class CpuVecEnv:
     """Batched CPU vec-env on the oracle (OpenMP over envs) — the timed CPU baseline and the parity
     checker for whole vector_step calls.  State arrays use the reference's drone-major layout."""
 
-    def __init__(self, params, pendulum=True, frequency=100.0, frame_skip=1, round_precision=True):
+    def __init__(self, params, pendulum=True, frequency=100.0, frame_skip=1, round_precision=True, ground=False):
         params = np.atleast_2d(np.asarray(params, dtype=np.float64))
         self.n = params.shape[0]
         self.models = (OrcModel * self.n)()
@@ -289,6 +322,7 @@ class CpuVecEnv:
         for i in range(self.n):
             p = np.ascontiguousarray(params[i])
             L.orc_compile(_dp(p), int(pendulum), float(frequency), int(round_precision), C.byref(self.models[i]))
+            self.models[i].ground = int(ground)
         self.nq, self.nv = self.models[0].nq, self.models[0].nv
         self.frame_skip = frame_skip
         self.qpos = np.zeros((self.n, self.nq))

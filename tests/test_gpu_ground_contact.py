@@ -1,0 +1,168 @@
+"""Floor contact (env_gen.py:14-21,97) - the CUDA slow path (csrc/dsim_contact.cuh, body-frame coordinates,
+dense 8 x 8 Newton) against the oracle's MuJoCo-layout restatement (oracle/dsim_oracle.c: world-frame Jacobians from cdof).
+Both restate MuJoCo's contact model from its documentation; like the rest of the physics it is UNPINNED against MuJoCo itself
+(tests/test_mujoco_pin.py switches on when `import mujoco` works), so what is asserted here is CUDA == oracle plus the
+invariants a contact model must have (tests/test_ground_contact.py holds the oracle-side ones)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NOMINAL = np.array([1, 0.17, 7, 0.01, 1.2, 0.3])
+KEYS = ("mass", "arm_len", "motor_force", "motor_tau", "pendulum_len", "weight_mass")
+
+
+def _mk(**over):
+    import mujoco_drone_b200 as M
+    cfg = dict(M.base_config)
+    cfg.update(dict(start_pos=[0, 0, 1.0, 0], reference=[0, 0, 1.0, 0], max_distance=100, random_params=False, ground_contact=True))
+    cfg.update(over)
+    return M.BaseDroneEnv(cfg)
+
+
+def _near_floor(rng, n, pend, zmax=1.5):
+    """random attitudes (any, incl. upside down), heights from 'core body in the floor' to 'pendulum tip just above it'"""
+    q = rng.normal(size=(n, 4))
+    q[: n // 4] = [1, 0, 0, 0] + 0.05 * rng.normal(size=(n // 4, 4))          # a quarter almost level
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    pos = np.stack([rng.normal(size=n), rng.normal(size=n), rng.uniform(0.0, zmax, size=n)], axis=1)
+    qpos = np.concatenate([pos, q] + ([rng.normal(size=(n, 2)) * 0.5] if pend else []), axis=1)
+    qvel = rng.normal(size=(n, 8 if pend else 6)) * 0.5
+    act = rng.uniform(0, 1, size=(n, 4))
+    actions = rng.uniform(0, 1, size=(n, 4))
+    params = NOMINAL * rng.uniform(0.85, 1.15, size=(n, 6))
+    if not pend:
+        params[:, 4:] = 0
+    return qpos, qvel, act, actions, params
+
+
+def _set(env, qpos, qvel, act, params):
+    env.drone_params = [dict(zip(KEYS, p)) for p in params]
+    env.set_state(qpos, qvel, act, None)
+
+
+@pytest.mark.parametrize("precision,frame_skip,pend", [("fp64", 1, True), ("fp64", 2, False), ("fp32", 1, True), ("fp32", 1, False)])
+def test_contact_step_matches_oracle(oracle, precision, frame_skip, pend):
+    import torch
+    rng = np.random.default_rng(11)
+    n = 256
+    qpos, qvel, act, actions, params = _near_floor(rng, n, pend, zmax=1.5 if pend else 0.3)
+    env = _mk(num_drones=n, precision=precision, skip_steps=frame_skip, pendulum=pend)
+    _set(env, qpos, qvel, act, params)
+    qpos_d, qvel_d, act_d, _, _ = env.get_state()
+    env.step_tensor(torch.as_tensor(actions, device="cuda"))
+    qp, qv, ac, sens, ns = env.get_state()
+    a_in = actions.astype(np.float32).astype(np.float64) if precision == "fp32" else actions
+    prm = env.drone_params
+    # FP32: a contact force is K d(r) r / R with r the penetration (~1e-4 .. 1e-2 m) computed from a height of ~1 m: its
+    # relative error is eps * 1 m / r, i.e. up to 1e-3 where the penetration is shallow, times h / m on the velocity
+    # measured (B200, this seed): FP64 2e-14 / 1e-12 / 7e-13; FP32 3e-6 (hinge angles) / 3.3e-5 / 1.1e-4
+    tol = dict(pos=1e-11, vel=1e-9, acc=1e-7) if precision == "fp64" else dict(pos=1e-5, vel=2e-4, acc=1e-3)
+    touching = 0
+    worst = dict(pos=0.0, vel=0.0, acc=0.0)
+    for i in range(n):
+        p = np.array(list(prm[i].values()))
+        m = oracle.compile_model(p, pend, 100, True, ground=True)
+        ncon = len(oracle.collide(m, qpos_d[i]))
+        touching += ncon > 0
+        oqp, oqv, oact, osens = oracle.step(m, qpos_d[i], qvel_d[i], act_d[i], 0.1 + 0.9 * a_in[i], frame_skip)
+        worst["pos"] = max(worst["pos"], np.abs(qp[i] - oqp).max())
+        worst["vel"] = max(worst["vel"], (np.abs(qv[i] - oqv) / (1 + np.abs(oqv))).max())
+        worst["acc"] = max(worst["acc"], (np.abs(sens[i] - osens) / (1 + np.abs(osens))).max())
+    print(precision, frame_skip, pend, "touching", touching, "of", n, worst)
+    assert touching > n // 4                                      # the scenario does exercise the contact path
+    for k in worst:
+        assert worst[k] <= tol[k] * frame_skip, (k, worst[k])
+    env.close()
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_drop_and_settle_matches_oracle(oracle, precision):
+    """400 steps from 0.3 m above the floor: free fall, impact, bounce, rest.  FP64: the whole trajectory; FP32: the resting pose
+    (a chaotic bounce amplifies rounding, the rest state is an attractor)."""
+    import torch
+    rng = np.random.default_rng(5)
+    n = 64
+    params = NOMINAL * rng.uniform(0.85, 1.15, size=(n, 6))
+    params[:, 4:] = 0
+    qpos = np.zeros((n, 7)); qpos[:, 2] = 0.3; qpos[:, 3] = 1
+    tilt = rng.normal(size=(n, 3)) * 0.1
+    qpos[:, 4:7] = tilt; qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+    qvel = np.zeros((n, 6)); act = np.zeros((n, 4))
+    env = _mk(num_drones=n, precision=precision, pendulum=False, max_steps=100000)
+    _set(env, qpos, qvel, act, params)
+    qpos_d, qvel_d, act_d, _, _ = env.get_state()
+    zero = torch.full((n, 4), -1.0, device="cuda", dtype=torch.float64 if precision == "fp64" else torch.float32)   # ctrl = clamp(0.1 - 0.9) = 0
+    T = 400
+    for _ in range(T):
+        env.step_tensor(zero)
+    qp, qv, ac, sens, ns = env.get_state()
+    assert np.isfinite(qp).all() and np.isfinite(qv).all()
+    prm = env.drone_params
+    for i in range(n):
+        m = oracle.compile_model(np.array(list(prm[i].values())), False, 100, True, ground=True)
+        oqp, oqv, oact, osens = oracle.step(m, qpos_d[i], qvel_d[i], act_d[i], np.zeros(4), T)
+        if precision == "fp64":
+            assert np.abs(qp[i] - oqp).max() < 1e-7 and np.abs(qv[i] - oqv).max() < 1e-6
+        else:
+            assert abs(qp[i, 2] - oqp[2]) < 2e-5                              # rest height: core box half height - penetration
+            assert np.abs(qv[i]).max() < 5e-3 and np.abs(oqv).max() < 1e-3   # at rest
+            assert np.abs(sens[i] - [0, 0, 9.81]).max() < 0.05               # the floor carries the weight
+    env.close()
+
+
+def test_far_from_the_floor_ground_contact_changes_nothing():
+    """ground_contact=True with every drone out of reach of the floor: the instantiation with the slow path compiled in takes none
+    of it and reproduces ground_contact=False bit for bit (frame_skip 2: both runs take a generic instantiation)."""
+    import torch
+    n = 4128
+    outs = []
+    for ground in (False, True):
+        import mujoco_drone_b200 as M
+        cfg = dict(M.base_config)
+        cfg.update(dict(num_drones=n, random_params=True, ground_contact=ground, seed=3, skip_steps=2))
+        env = M.BaseDroneEnv(cfg)
+        env.reset_tensor()
+        g = torch.Generator(device="cuda"); g.manual_seed(1)
+        for _ in range(20):
+            obs, rew, trunc = env.step_tensor(torch.rand((n, 4), device="cuda", generator=g))
+        outs.append((obs.clone(), rew.clone(), trunc.clone(), env.get_state()))
+        env.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    for a, b in zip(outs[0][3], outs[1][3]):
+        assert np.array_equal(a, b)
+
+
+def test_many_drones_land_and_stay_on_the_floor():
+    """Size-independent properties at a full batch: random drops, every drone ends up resting on the floor - finite, no
+    geom deeper than the soft-contact penetration allows, velocities gone, accelerometer reads |g|."""
+    import torch
+    import mujoco_drone_b200 as M
+    n = 32768
+    cfg = dict(M.base_config)
+    cfg.update(dict(num_drones=n, start_pos=[0, 0, 1.6, 0], reference=[0, 0, 1.6, 0], max_distance=1000, max_steps=10**6, random_params=True,
+                    ground_contact=True, angle_variance=[0.5, 0.5], vel_variance=[0.5, 0.5, 0.5], ang_vel_variance=[1, 1, 1],
+                    pendulum_rp_variance=[0.3, 0.3], max_random_offset=0.3, seed=9))
+    env = M.BaseDroneEnv(cfg)
+    env.reset_tensor()
+    off = torch.full((n, 4), -1.0, device="cuda")
+    for _ in range(1200):
+        obs, rew, trunc = env.step_tensor(off)
+    qp, qv, ac, sens, ns = env.get_state()
+    assert np.isfinite(qp).all() and np.isfinite(qv).all() and np.isfinite(sens).all()
+    assert not trunc.any().item()
+    # body origin: not under the floor, and either down on it or - a real, statically stable outcome of ~1.5 % of these drops - hanging
+    # upside down from the top of the pole, which stands on its flat weight box (hinge angles at +-pi)
+    assert (qp[:, 2] > -0.01).all() and (qp[:, 2] < 1.2 * 1.1 + 0.2).all()
+    perched = qp[:, 2] > 0.5
+    assert perched.mean() < 0.05 and (np.abs(np.abs(qp[perched, 7:9]).max(axis=1) - np.pi) < 0.05).all()
+    moving = np.abs(qv).max(axis=1) > 0.05
+    assert moving.mean() < 0.01, moving.mean()                              # (a few may still be rocking)
+    settled = np.abs(qv).max(axis=1) < 1e-3
+    g = np.linalg.norm(sens, axis=1)
+    print("settled", settled.mean(), "perched", perched.mean(), "max | |acc| - g | of the settled", np.abs(g[settled] - 9.81).max())
+    assert settled.mean() > 0.9
+    assert np.percentile(np.abs(g[settled] - 9.81), 99.9) < 0.05            # the floor carries the weight
+    st = env.episode_stats()
+    assert st["n_nonfinite"] == 0
+    env.close()
