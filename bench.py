@@ -230,6 +230,8 @@ def make_env(wl, n, rank_offset, device, auto_reset=True):
     cfg = dict(M.base_config)
     cfg.update(wl["cfg"])
     cfg.update(num_drones=n, reward_fcn=getattr(M.rewards, wl["reward"]), env_id_offset=rank_offset, device=device, auto_reset=auto_reset)
+    if os.environ.get("DSIM_BENCH_GROUND"):       # diagnostics only: the generic instantiation with the floor-contact slow path compiled in
+        cfg.update(ground_contact=True)
     if os.environ.get("DSIM_BENCH_NORESET"):      # diagnostics only: episodes never end (isolates the cost of the in-kernel reset path)
         cfg.update(max_distance=1e9, max_steps=10 ** 9)
     return cls(cfg)

@@ -53,7 +53,8 @@ enum {
     DSIM_BUF_STATES33 = 9,   /* real  [N][33|29] get_drone_states() rows, filled by dsim_compute_states */
     DSIM_BUF_EP_RETURN = 10, /* real  PAGED 1 row: running return of the current episode */
     DSIM_BUF_STATS = 11,     /* double[64][8] partial sums (dsim_stats adds the 64 rows): sum_return, sum_length, n_episodes, n_nonfinite, n_near_ground, 0,0,0 */
-    DSIM_BUF_SENSORDATA = 12 /* real  PAGED 3 rows of the read-write page        data.sensordata (accelerometer) */
+    DSIM_BUF_SENSORDATA = 12, /* real PAGED 3 rows of the read-write page        data.sensordata (accelerometer) */
+    DSIM_BUF_GEOMETRY = 13   /* real  [39][ld]  collision geometry of every drone (handles created with ground_contact; csrc/dsim_contact.cuh GeoRow) */
 };
 enum { DSIM_DT_F32 = 0, DSIM_DT_F64 = 1, DSIM_DT_I32 = 2, DSIM_DT_U8 = 3, DSIM_DT_U32 = 4, DSIM_DT_I64 = 5 };
 

@@ -15,7 +15,7 @@ ABI_VERSION = 3
 TRAJ_CIRCLE, TRAJ_STEP, TRAJ_RAMP = 0, 1, 2
 TILE = 32                     # envs per page (include/dronesim_b200.h: PAGED buffers)
 (BUF_STATE, BUF_NUM_STEPS, BUF_OBS, BUF_REWARD, BUF_TRUNCATED, BUF_PARAMS, BUF_CONSTS, BUF_REFERENCE,
- BUF_RESET_COUNT, BUF_STATES33, BUF_EP_RETURN, BUF_STATS, BUF_SENSORDATA) = range(13)
+ BUF_RESET_COUNT, BUF_STATES33, BUF_EP_RETURN, BUF_STATS, BUF_SENSORDATA, BUF_GEOMETRY) = range(14)
 DT_F32, DT_F64, DT_I32, DT_U8, DT_U32, DT_I64 = range(6)
 
 EXPORTS = [

@@ -16,7 +16,7 @@
 // the kernel's own generalized coordinates x = (origin acceleration in body axes, angular acceleration in body axes, hinge x,
 // hinge y) - a rotation of MuJoCo's, under which the convex problem is invariant - on a dense 8 x 8 mass matrix, with every
 // geometric quantity expressed in the body frame (floor normal n_b = R^T z, height of a body point p: z_o + n_b . p).
-// The geometry is rebuilt from the FP64 drone_params with the same "%.5g" rounding the model compiler applies.
+// The geometry comes from a per-env table the model compile fills in FP64 with the compiler's "%.5g" rounding (geometry_kernel).
 #pragma once
 #include "dsim_device.cuh"
 #include "dsim_params.cuh"
@@ -25,20 +25,58 @@ namespace dsim {
 
 constexpr int kMaxContacts = 68;          // 7 boxes x 4 + 9 cylinders x 4 + 1 sphere = 65
 
+// Per-env collision geometry, written by geometry_kernel next to the model compile (FP64, "%.5g" rounding like the compiler)
+enum GeoRow : int {
+    G_CORE_XY = 0, G_CORE_Z,              // core box half sizes
+    G_FRONT_X, G_FRONT_SX, G_FRONT_SYZ,   // 'front' marker box: centre x, half sizes
+    G_ARM_SX, G_ARM_SYZ,                  // arm boxes: half length, half thickness
+    G_PROP_R,                             // propeller disc radius
+    G_MOTOR_Z, G_PROP_Z,                  // heights of the motor / propeller cylinders
+    G_ARM_X0,                             // [4] arm centre x      (per arm i: +i)
+    G_ARM_Y0 = G_ARM_X0 + 4,              // [4] arm centre y
+    G_ROT_X0 = G_ARM_Y0 + 4,              // [4] motor / propeller centre x
+    G_ROT_Y0 = G_ROT_X0 + 4,              // [4] motor / propeller centre y
+    G_YAW_C0 = G_ROT_Y0 + 4,              // [4] cos of the arm's rounded yaw
+    G_YAW_S0 = G_YAW_C0 + 4,              // [4] sin
+    G_PEND = G_YAW_S0 + 4,                // 1: this drone has a pendulum (env_gen.py:33-36)
+    G_POLE_HH, G_POLE_Z, G_WEIGHT_S, G_WEIGHT_Z,
+    GEO_ROWS
+};
+DSIM_HD void contact_geometry(const double p[6], bool pendulum_enabled, bool rounding, double out[GEO_ROWS]) {
+#define RND(v) (rounding ? round_prec5(v) : (v))
+    const double hb = 0.05, arm = p[1], r2 = sqrt(2.0);
+    out[G_CORE_XY] = RND(hb); out[G_CORE_Z] = RND(hb / 3);
+    out[G_FRONT_X] = RND(hb + hb / 3); out[G_FRONT_SX] = RND(hb / 3); out[G_FRONT_SYZ] = RND(0.15 * hb);
+    out[G_ARM_SX] = RND(arm / 2); out[G_ARM_SYZ] = RND(arm / 20);
+    out[G_PROP_R] = RND(arm / 1.5);
+    out[G_MOTOR_Z] = RND(0.0 + 0.015); out[G_PROP_Z] = RND(0.0 + 0.025);
+    for (int i = 0; i < 4; i++) {
+        const double th = i * kPi / 2 - kPi / 4, ct = cos(th), st = sin(th), yaw = RND(th);
+        const double ra = r2 * hb + 0.5 * arm, rr = r2 * hb + arm;
+        out[G_ARM_X0 + i] = RND(ra * ct); out[G_ARM_Y0 + i] = RND(ra * st);
+        out[G_ROT_X0 + i] = RND(rr * ct + 0.0); out[G_ROT_Y0 + i] = RND(rr * st + 0.0);
+        out[G_YAW_C0 + i] = cos(yaw); out[G_YAW_S0 + i] = sin(yaw);
+    }
+    const bool pend = pendulum_enabled && p[4] > 0 && p[5] > 0;
+    out[G_PEND] = pend ? 1.0 : 0.0;
+    out[G_POLE_HH] = pend ? RND(p[4] / 2) : 0.0; out[G_POLE_Z] = pend ? RND(-p[4] / 2) : 0.0;
+    out[G_WEIGHT_S] = pend ? RND(0.1 * cbrt(p[5])) : 0.0; out[G_WEIGHT_Z] = pend ? RND(-p[4]) : 0.0;
+#undef RND
+}
+
 template <typename T> struct GroundCtx {
     T start_z;                            // world z of the origin the state's position offset refers to
     T reach;                              // radius of a sphere about the body origin that holds every geom (conservative)
-    const double *params64;               // [6][ld] raw drone_params
-    int ld, env, rounding, pendulum;
+    const T *geo;                         // (row 0, this env) of the geometry table [GEO_ROWS][ld]
+    int ld;
 };
 
 // bounding radius from the raw parameters: propeller rim (0.0982 + 1.667 arm_len) / far corner of the weight (0.025 + l + 0.1733 cbrt(m))
-template <typename T> DSIM_DEV GroundCtx<T> make_ground_ctx(T start_z, const double *params64, int ld, int env, int rounding, int pendulum) {
+template <typename T> DSIM_DEV GroundCtx<T> make_ground_ctx(T start_z, const T *prm, const T *geo, int ld, int env, int pendulum) {
     GroundCtx<T> g;
-    g.start_z = start_z; g.params64 = params64; g.ld = ld; g.env = env; g.rounding = rounding; g.pendulum = pendulum;
-    const double arm = params64[(size_t)1 * ld + env], plen = params64[(size_t)4 * ld + env], wm = params64[(size_t)5 * ld + env];
-    const double rb = 0.1 + 1.7 * arm, rp = pendulum ? 0.03 + plen + 0.18 * fmax(1.0, wm) : 0.0;
-    g.reach = T(fmax(rb, rp) * 1.001);
+    g.start_z = start_z; g.geo = geo + env; g.ld = ld;
+    const T rb = T(0.1) + T(1.7) * prm[1], rp = pendulum ? T(0.03) + prm[4] + T(0.18) * max_(T(1), prm[5]) : T(0);
+    g.reach = max_(rb, rp) * T(1.001);
     return g;
 }
 
@@ -170,43 +208,35 @@ template <typename T> DSIM_DEV void contact_row(V3<T> d, V3<T> p, int body, V3<T
 
 // Returns the number of contacts; with none, io.x / io.xi are left alone.
 template <typename T>
-__device__ __noinline__ int contact_solve(ContactIO<T> &io, const EnvConsts<T> &c, const GroundCtx<T> &g) {
+__device__ DSIM_CONTACT_CALL int contact_solve(ContactIO<T> &io, const EnvConsts<T> &c, const GroundCtx<T> &g) {
     ContactSet<T> cs;
     cs.n = 0;
     const V3<T> nb = mk(io.nb[0], io.nb[1], io.nb[2]);
     const T zo = io.zo;
     const V3<T> X = mk(T(1), T(0), T(0)), Y = mk(T(0), T(1), T(0)), Z = mk(T(0), T(0), T(1)), O = mk(T(0), T(0), T(0));
-    double prm[6];
-    for (int k = 0; k < 6; k++) prm[k] = g.params64[(size_t)k * g.ld + g.env];
-    const bool rounding = g.rounding != 0;
-    const bool pend = g.pendulum && prm[4] > 0 && prm[5] > 0;
-#define RND(v) (rounding ? round_prec5(v) : (v))
+    auto G = [&](int row) { return g.geo[(size_t)row * g.ld]; };
+    const bool pend = G(G_PEND) != T(0);
     {   // ---- core body (env_gen.py:45-61)
-        const double hb = 0.05, arm = prm[1], r2 = sqrt(2.0);
-        collide_box(cs, nb, zo, O, X, Y, Z, T(RND(hb)), T(RND(hb)), T(RND(hb / 3)), 0);
-        collide_box(cs, nb, zo, mk(T(RND(hb + hb / 3)), T(0), T(0)), X, Y, Z, T(RND(hb / 3)), T(RND(0.15 * hb)), T(RND(0.15 * hb)), 0);
+        collide_box(cs, nb, zo, O, X, Y, Z, G(G_CORE_XY), G(G_CORE_XY), G(G_CORE_Z), 0);
+        collide_box(cs, nb, zo, mk(G(G_FRONT_X), T(0), T(0)), X, Y, Z, G(G_FRONT_SX), G(G_FRONT_SYZ), G(G_FRONT_SYZ), 0);
+        const T asx = G(G_ARM_SX), asyz = G(G_ARM_SYZ), pr = G(G_PROP_R), mz = G(G_MOTOR_Z), pz = G(G_PROP_Z);
         #pragma unroll 1
         for (int i = 0; i < 4; i++) {
-            const double th = i * kPi / 2 - kPi / 4, ct = cos(th), st = sin(th), yaw = RND(th);
-            const double ra = r2 * hb + 0.5 * arm, rr = r2 * hb + arm;
-            const T cyw = T(cos(yaw)), syw = T(sin(yaw));
-            collide_box(cs, nb, zo, mk(T(RND(ra * ct)), T(RND(ra * st)), T(0)), mk(cyw, syw, T(0)), mk(-syw, cyw, T(0)), Z,
-                        T(RND(arm / 2)), T(RND(arm / 20)), T(RND(arm / 20)), 0);
-            const T mx = T(RND(rr * ct + 0.0)), my = T(RND(rr * st + 0.0));
-            collide_cylinder(cs, nb, zo, mk(mx, my, T(RND(0.015))), X, Z, T(0.01), T(0.01), 0);
-            collide_cylinder(cs, nb, zo, mk(mx, my, T(RND(0.025))), X, Z, T(RND(arm / 1.5)), T(0.0025), 0);
+            const T cyw = G(G_YAW_C0 + i), syw = G(G_YAW_S0 + i);
+            collide_box(cs, nb, zo, mk(G(G_ARM_X0 + i), G(G_ARM_Y0 + i), T(0)), mk(cyw, syw, T(0)), mk(-syw, cyw, T(0)), Z, asx, asyz, asyz, 0);
+            const T mx = G(G_ROT_X0 + i), my = G(G_ROT_Y0 + i);
+            collide_cylinder(cs, nb, zo, mk(mx, my, mz), X, Z, T(0.01), T(0.01), 0);
+            collide_cylinder(cs, nb, zo, mk(mx, my, pz), X, Z, pr, T(0.0025), 0);
         }
     }
     const V3<T> yc = mk(T(0), io.cx, io.sx), n = mk(io.sy, -io.sx * io.cy, io.cx * io.cy), xd = mk(io.cy, io.sx * io.sy, -io.cx * io.sy);
     const V3<T> hp = mk(T(0), T(0), T(-kLinkDrop));
     if (pend) {   // ---- link sphere, pole, weight (env_gen.py:66-72)
-        const double plen = prm[4], wm = prm[5];
         collide_sphere(cs, nb, zo, hp, T(0.02), 1);
-        collide_cylinder(cs, nb, zo, hp + T(RND(-plen / 2)) * n, xd, n, T(0.005), T(RND(plen / 2)), 2);
-        const T sw = T(RND(0.1 * cbrt(wm)));
-        collide_box(cs, nb, zo, hp + T(RND(-plen)) * n, xd, yc, n, sw, sw, sw, 2);
+        collide_cylinder(cs, nb, zo, hp + G(G_POLE_Z) * n, xd, n, T(0.005), G(G_POLE_HH), 2);
+        const T sw = G(G_WEIGHT_S);
+        collide_box(cs, nb, zo, hp + G(G_WEIGHT_Z) * n, xd, yc, n, sw, sw, sw, 2);
     }
-#undef RND
     if (cs.n == 0) return 0;
 
     // ---- mj_makeImpedance: body_invweight0 at qpos0 (identity attitude, hinges at 0), then K, B, d(r), R per contact
@@ -253,13 +283,18 @@ __device__ __noinline__ int contact_solve(ContactIO<T> &io, const EnvConsts<T> &
         return -B * vel - cs.kr[i];
     };
     T x[8], gq[8], grad[8], dx[8];
+    T jar_[4 * kMaxContacts], jd_[4 * kMaxContacts];                          // per row: J x - aref at x, J dx (the line search reads only these)
     for (int k = 0; k < 8; k++) x[k] = io.x[k];
+    // Newton converges quadratically once the active set is right: the iteration whose step falls below the precision's
+    // resolution of x was the last useful one.  FP32: the gradient carries ~1e-6 of rounding noise per newton of force, so the
+    // tolerances sit just above that floor and the iteration cap does the rest (measured: a cap of 16 costs nothing - the
+    // slow path is bound by the latency of its local-memory arrays, the L1 being almost entirely carved out as shared memory)
     T trace = T(0);
     for (int k = 0; k < 8; k++) trace += M[k * 8 + k];
     const bool f32 = sizeof(T) == 4;
-    const T tol = (f32 ? T(1e-6) : T(1e-13)) * trace;
+    const T tol = (f32 ? T(2e-6) : T(1e-13)) * trace;
     #pragma unroll 1
-    for (int it = 0; it < 40; it++) {
+    for (int it = 0; it < (f32 ? 16 : 40); it++) {
         for (int k = 0; k < 8; k++) { T s = -io.q[k]; for (int j = 0; j < 8; j++) s += M[k * 8 + j] * x[j]; gq[k] = s; grad[k] = s; }
         for (int k = 0; k < 64; k++) L[k] = M[k];
         #pragma unroll 1
@@ -270,6 +305,7 @@ __device__ __noinline__ int contact_solve(ContactIO<T> &io, const EnvConsts<T> &
                 const T aref = row(i, r, J);
                 T jar = -aref;
                 for (int k = 0; k < 8; k++) jar += J[k] * x[k];
+                jar_[4 * i + r] = jar;
                 if (jar >= T(0)) continue;
                 const T D = cs.D[i];
                 for (int k = 0; k < 8; k++) {
@@ -286,26 +322,31 @@ __device__ __noinline__ int contact_solve(ContactIO<T> &io, const EnvConsts<T> &
         // phi'(a) = p0 + a p2 + sum_rows D jd min(0, jar + a jd): increasing and piecewise linear; walk its breakpoints
         T p0 = T(0), p2 = T(0);
         for (int k = 0; k < 8; k++) { p0 += gq[k] * dx[k]; T s = T(0); for (int j = 0; j < 8; j++) s += M[k * 8 + j] * dx[j]; p2 += dx[k] * s; }
+        #pragma unroll 1
+        for (int i = 0; i < cs.n; i++)
+            #pragma unroll 1
+            for (int r = 0; r < 4; r++) {
+                T J[8];
+                row(i, r, J);
+                T jd = T(0);
+                for (int k = 0; k < 8; k++) jd += J[k] * dx[k];
+                jd_[4 * i + r] = jd;
+            }
         T a = T(0);
         #pragma unroll 1
-        for (int ls = 0; ls < 48; ls++) {
+        for (int ls = 0; ls < 64; ls++) {
             T f1 = p0 + a * p2, f2 = p2, nxt = T(1e30);
             #pragma unroll 1
-            for (int i = 0; i < cs.n; i++)
-                #pragma unroll 1
-                for (int r = 0; r < 4; r++) {
-                    T J[8];
-                    const T aref = row(i, r, J);
-                    T jar = -aref, jd = T(0);
-                    for (int k = 0; k < 8; k++) { jar += J[k] * x[k]; jd += J[k] * dx[k]; }
-                    bool act;
-                    if (jd != T(0)) {
-                        const T bp = -jar / jd;
-                        act = jd < T(0) ? (a >= bp) : (a < bp);
-                        if (bp > a && bp < nxt) nxt = bp;
-                    } else act = jar < T(0);
-                    if (act) { f1 += cs.D[i] * jd * (jar + a * jd); f2 += cs.D[i] * jd * jd; }
-                }
+            for (int i = 0; i < 4 * cs.n; i++) {
+                const T jar = jar_[i], jd = jd_[i], D = cs.D[i >> 2];
+                bool act;
+                if (jd != T(0)) {
+                    const T bp = -jar / jd;
+                    act = jd < T(0) ? (a >= bp) : (a < bp);
+                    if (bp > a && bp < nxt) nxt = bp;
+                } else act = jar < T(0);
+                if (act) { f1 += D * jd * (jar + a * jd); f2 += D * jd * jd; }
+            }
             if (f1 >= T(0)) break;
             const T root = a - f1 / f2;
             if (root <= nxt) { a = root; break; }
@@ -313,7 +354,7 @@ __device__ __noinline__ int contact_solve(ContactIO<T> &io, const EnvConsts<T> &
         }
         T big = T(0);
         for (int k = 0; k < 8; k++) { x[k] += a * dx[k]; big = max_(big, abs_(a * dx[k]) / (T(1) + abs_(x[k]))); }
-        if (big < (f32 ? T(1e-7) : T(1e-15))) break;
+        if (big < (f32 ? T(2e-6) : T(1e-15))) break;
     }
     for (int k = 0; k < 8; k++) io.x[k] = x[k];
     // ---- mj_EulerSkip with the constraint force: (M + h B) xi = qfrc_smooth + qfrc_constraint = M x  ->  xi = x - (M + h B)^-1 h B x
@@ -327,6 +368,13 @@ __device__ __noinline__ int contact_solve(ContactIO<T> &io, const EnvConsts<T> &
         for (int k = 0; k < 8; k++) io.xi[k] = x[k] - y[k];
     }
     return cs.n;
+}
+
+// One mj_step of a drone that may touch the floor, as ONE out-of-line call: the step kernel's in-air path stays exactly the
+// code of the kernels without floor contact (no struct in local memory, no registers saved around a call).
+template <typename T, bool PEND>
+__device__ __noinline__ void ground_substep(EnvState<T> &s, const EnvConsts<T> &c, const T *ctrl, T h, const GroundCtx<T> &g) {
+    substep<T, PEND, true, true>(s, c, ctrl, h, &g);
 }
 
 }  // namespace dsim

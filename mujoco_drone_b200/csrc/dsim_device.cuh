@@ -230,9 +230,12 @@ template <typename T> DSIM_DEV V3<T> ldl3_solve(const Ldl3<T> &f, V3<T> b) {
 // ------------------------------------------------------------------ one mj_step (Euler, implicit hinge damping)
 // ADVANCE=false evaluates only the forward part (mj_forward: accelerometer refresh after set_state).
 // GROUND: floor contacts (dsim_contact.cuh) for drones whose bounding sphere reaches the floor; `g` is only read then.
+#ifndef DSIM_CONTACT_CALL
+#define DSIM_CONTACT_CALL __noinline__
+#endif
 template <typename T> struct GroundCtx;
 template <typename T> struct ContactIO;
-template <typename T> __device__ int contact_solve(ContactIO<T> &io, const EnvConsts<T> &c, const GroundCtx<T> &g);
+template <typename T> __device__ DSIM_CONTACT_CALL int contact_solve(ContactIO<T> &io, const EnvConsts<T> &c, const GroundCtx<T> &g);
 template <typename T, bool PEND, bool ADVANCE, bool GROUND = false>
 DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T h, const GroundCtx<T> *g = nullptr) {
     // -- kinematics (mj_kinematics normalises the free-joint quaternion)

@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const KParams<T> p, int
     const EnvConsts<T> c = load_consts(p, ro_col, p.per_env_consts != 0);
     const T ctrl[4] = {T(0), T(0), T(0), T(0)};
     if (p.ground) {
-        const GroundCtx<T> g = make_ground_ctx<T>(p.start_t[2], p.params64, p.ld, i, p.round_precision, p.pendulum);
+        T gprm[6];
+        load_params(p, ro_col, gprm, p.per_env_consts != 0);
+        const GroundCtx<T> g = make_ground_ctx<T>(p.start_t[2], gprm, p.geo, p.ld, i, p.pendulum);
         substep<T, PEND, false, true>(s, c, ctrl, p.h, &g);
     } else substep<T, PEND, false>(s, c, ctrl, p.h);
     col[S_ACC * kTile] = s.acc.x; col[(S_ACC + 1) * kTile] = s.acc.y; col[(S_ACC + 2) * kTile] = s.acc.z;
@@ -112,6 +114,16 @@ __global__ void compile_kernel(int n, int ld, const double *params64, T *ro, int
     for (int k = 0; k < C_ROWS; k++) col[(RO_CONSTS + k) * kTile] = (T)c[k];
     for (int k = 0; k < 6; k++) col[(RO_PARAMS + k) * kTile] = (T)p[k];
 }
+// collision geometry of every drone for the floor-contact path (DsimConfig.ground_contact), same FP64 + "%.5g" stage as the compile
+template <typename T>
+__global__ void geometry_kernel(int n, int ld, const double *params64, T *geo, int pendulum, int rounding) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[6], g[GEO_ROWS];
+    for (int k = 0; k < 6; k++) p[k] = params64[(size_t)k * ld + i];
+    contact_geometry(p, pendulum != 0, rounding != 0, g);
+    for (int k = 0; k < GEO_ROWS; k++) geo[(size_t)k * ld + i] = (T)g[k];
+}
 // control_reference (:151-172) per env: axes [4][ld] are the already sign-flipped joystick values (x, -y, -z, -yaw).
 // The dead-zone DECISIONS (:160-161) are index logic and are taken in FP64 whatever the page precision: an axis value that is
 // a 2-decimal number which went through FP32 (joystick.py:36 rounds to 2 decimals; 0.12f != 0.12) is restored to the double
@@ -182,6 +194,7 @@ struct DsimHandle {
     size_t rs;                        // sizeof(real)
     void *rw, *ro, *refp, *obs, *reward, *states33, *actions_stage;
     double *params64, *stats, *center_hw;
+    void *geo;                       // floor contact: [GEO_ROWS][ld] per-env collision geometry, or nullptr
     unsigned long long *timeline;
     unsigned *ticket;
     unsigned char *trunc;
@@ -265,7 +278,7 @@ template <typename T> static KParams<T> make_params(const DsimHandle *h, const v
     p.timeline = h->timeline; p.ticket = h->ticket;
     p.early_ro = h->ro_dirty ? 0 : 1;
     p.early_in = h->inputs_ready ? 1 : 0;
-    p.params64 = h->params64; p.ld = h->ld; p.round_precision = c.round_precision; p.pendulum = c.pendulum; p.ground = c.ground_contact;
+    p.geo = (const T *)h->geo; p.ld = h->ld; p.pendulum = c.pendulum; p.ground = c.ground_contact;
     return p;
 }
 
@@ -359,6 +372,7 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
     ALLOC(h->states33, (size_t)h->state_width * n * rs);
     ALLOC(h->actions_stage, 4 * (h->guard ? n : ld) * rs);
     ALLOC(h->params64, 6 * ld * sizeof(double));
+    if (cfg->ground_contact) ALLOC(h->geo, (size_t)GEO_ROWS * ld * rs);
     ALLOC(h->stats, (size_t)kStatReplicas * 8 * sizeof(double));
     ALLOC(h->center_hw, 12 * sizeof(double));
     ALLOC(h->trunc, h->guard ? n : ld);
@@ -393,7 +407,7 @@ extern "C" void dsim_destroy(DsimHandle *h) {
         cudaEventDestroy(h->ev_a); cudaEventDestroy(h->ev_b); cudaEventDestroy(h->ev_c);
     }
     void *ptrs[] = {h->rw, h->ro, h->refp, h->obs, h->reward, h->states33, h->actions_stage,
-                    h->params64, h->stats, h->center_hw, h->trunc, h->timeline, h->ticket};
+                    h->params64, h->stats, h->center_hw, h->trunc, h->timeline, h->ticket, h->geo};
     for (void *p : ptrs) if (p) cudaFree(h->guard ? (char *)p - kGuardBytes : (char *)p);
     delete h;
 }
@@ -404,6 +418,11 @@ static int compile_on_device(DsimHandle *h, cudaStream_t st) {
     if (h->rs == 4) compile_kernel<float><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (float *)h->ro, h->cfg.pendulum, h->cfg.round_precision);
     else compile_kernel<double><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (double *)h->ro, h->cfg.pendulum, h->cfg.round_precision);
     h->launches++;
+    if (h->geo) {
+        if (h->rs == 4) geometry_kernel<float><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (float *)h->geo, h->cfg.pendulum, h->cfg.round_precision);
+        else geometry_kernel<double><<<grid, 128, 0, st>>>(h->n, h->ld, h->params64, (double *)h->geo, h->cfg.pendulum, h->cfg.round_precision);
+        h->launches++;
+    }
     CK(cudaGetLastError());
     return DSIM_OK;
 }
@@ -901,6 +920,9 @@ extern "C" int dsim_buffer(DsimHandle *h, int id, void **ptr, int64_t *rows, int
     case DSIM_BUF_RESET_COUNT: *ptr = rw + RW_RESET_COUNT * row_bytes; *rows = 1; *cols = n; *ld = L; *dtype = idt; *page_rows = RW_ROWS; break;
     case DSIM_BUF_STATES33: *ptr = h->states33; *rows = n; *cols = h->state_width; *ld = h->state_width; *dtype = rdt; break;
     case DSIM_BUF_SENSORDATA: *ptr = rw + S_ACC * row_bytes; *rows = 3; *cols = n; *ld = L; *dtype = rdt; *page_rows = RW_ROWS; break;
+    case DSIM_BUF_GEOMETRY:
+        if (!h->geo) return fail(h, DSIM_EINVAL, "no collision geometry: the handle was created without ground_contact%s", "");
+        *ptr = h->geo; *rows = GEO_ROWS; *cols = n; *ld = L; *dtype = rdt; break;
     case DSIM_BUF_STATS: *ptr = h->stats; *rows = kStatReplicas; *cols = 8; *ld = 8; *dtype = DSIM_DT_F64; break;
     default: return fail(h, DSIM_EINVAL, "unknown buffer id%s", "");
     }

@@ -9,11 +9,15 @@
 
 namespace dsim {
 
+// v * 10^p for |p| <= 22 (clamped): every power of ten up to 1e22 is an exact double, and so is each partial product below.
+// (No lookup table: a local `const double P10[23]` inlined into a caller that keeps its own local array was seen to share
+// that array's stack slots on the device - geometry_kernel, nvcc 12.9 - and overwrite it.)
 DSIM_HD double scale10(double v, int p) {
-    const double P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
-                            1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
-    if (p >= 0) return v * P10[p > 22 ? 22 : p];
-    return v / P10[-p > 22 ? 22 : -p];
+    int k = p < 0 ? -p : p;
+    if (k > 22) k = 22;
+    double t = 1.0;
+    for (int j = 0; j < k; j++) t *= 10.0;
+    return p >= 0 ? v * t : v / t;
 }
 // dm_control writes every float attribute with "%.5g" (to_xml_string(precision=5), env_gen.py:129) and MuJoCo
 // parses the decimal back: value -> nearest 5-significant-digit decimal -> nearest double.  k / 10^j with both

@@ -128,9 +128,9 @@ template <typename T> struct KParams {
     // device-resident ones (posted PCIe writes from the same bulk stores; no copy-engine pass), or nullptr
     T *obs_host, *reward_host;
     unsigned char *trunc_host;
-    // floor contact (DsimConfig.ground_contact): raw FP64 drone_params [6][ld] the contact path rebuilds the geoms from
-    const double *params64;
-    int ld, round_precision, pendulum, ground;
+    // floor contact (DsimConfig.ground_contact): per-env collision geometry [GEO_ROWS][ld] (geometry_kernel)
+    const T *geo;
+    int ld, pendulum, ground;
 };
 
 // integer rows of the read-write page are stored in a lane-sized slot (int32 for float pages, int64 for double)
@@ -499,9 +499,22 @@ __global__ void __launch_bounds__(kStepBlock, min_blocks<T>()) step_kernel(const
             for (int k = 0; k < 4; k++) ctrl[k] = clamp_(T(0.1) + T(0.9) * a[k], T(0), T(1));   // :269 + ctrlrange (0,1) clamp of mj_fwdActuation
             #pragma unroll 1
             if constexpr (GROUND) {
-                const GroundCtx<T> g = make_ground_ctx<T>(p.start_t[2], p.params64, p.ld, active ? i : 0, p.round_precision, p.pendulum);
+                T gprm[6];
+                load_params(p, ro_col, gprm, pec);
+                const GroundCtx<T> g = make_ground_ctx<T>(p.start_t[2], gprm, p.geo, p.ld, active ? i : 0, p.pendulum);
                 #pragma unroll 1
-                for (int f = 0; f < frame_skip; f++) substep<T, PEND, true, true>(s, c, ctrl, p.h, &g);
+                for (int f = 0; f < frame_skip; f++) {
+                    if (g.start_z + s.pos.z < g.reach) {
+                        // rare, out of line.  Through COPIES: a variable whose address reaches a call lives in local memory for
+                        // its whole lifetime, and the in-air path must keep its state in registers
+                        EnvState<T> s2 = s;
+                        const EnvConsts<T> c2 = c;
+                        const GroundCtx<T> g2 = g;
+                        const T ctrl2[4] = {ctrl[0], ctrl[1], ctrl[2], ctrl[3]};
+                        ground_substep<T, PEND>(s2, c2, ctrl2, p.h, g2);
+                        s = s2;
+                    } else substep<T, PEND, true>(s, c, ctrl, p.h);
+                }
             } else {
                 #pragma unroll 1
                 for (int f = 0; f < frame_skip; f++) substep<T, PEND, true>(s, c, ctrl, p.h);

@@ -9,6 +9,7 @@ Every env-step is ONE CUDA kernel launch (csrc/dsim_kernels.cu::step_kernel).  T
 """
 import ctypes as C
 import types
+import warnings
 
 import numpy as np
 
@@ -124,7 +125,17 @@ class BaseDroneEnv(_VectorEnv):
         self._inputs_ready = bool(g('inputs_ready', False))
         # floor contact (env_gen.py:14-21,97): off by default - the floor is out of reach in the training configs (z = 15 m,
         # truncation at 4 m) and would-be contacts are only counted (episode_stats()['n_near_ground']); on: simulated
-        self.ground_contact = bool(g('ground_contact', False))
+        gc = g('ground_contact', None)
+        if gc is None:
+            # not asked for: off (the specialised in-air kernels run), but say so when a drone could get down to the floor before it
+            # is truncated - lowest setpoint (control_reference clips the joystick setpoint to start_pos[2] - 6, :167-170) minus
+            # max_distance, against the longest drone (pendulum tip <= 2.5 m below the body).  BASELINE configs: 15 - 6 - 4 = 5 m.
+            lowest = min(float(self._reference[2]), float(self.start_pos[2]) - (6.0 if (self.controlled or self.per_env_reference) else 0.0)) - float(self.max_distance)
+            if lowest < 2.5:
+                warnings.warn("the floor (z = 0) is within reach of this configuration but 'ground_contact' is not set: floor contacts are "
+                              "only COUNTED (episode_stats()['n_near_ground']), not simulated; pass ground_contact=True to simulate them", stacklevel=2)
+            gc = False
+        self.ground_contact = bool(gc)
         self._regen_epoch = 0
         # seed: reference uses config.get('worker_index', -1) + 1 + seed (BaseDroneEnv.py:113, Q5)
         self.seed_value = int(g('worker_index', -1) + 1 + g('seed', 1))

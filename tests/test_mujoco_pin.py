@@ -51,6 +51,26 @@ def test_oracle_matches_frozen_mujoco_outputs(oracle):
                     assert (np.abs(a - b) <= tol * (1 + np.abs(b))).all(), (tag, i, nstep, name)
 
 
+def test_oracle_contact_matches_frozen_mujoco_outputs(oracle):
+    if not os.path.exists(GOLD):
+        pytest.skip("contact parity vs MuJoCo UNPINNED: tests/golden/mjstep.npz has never been generated (mujoco unavailable so far)")
+    g = np.load(GOLD)
+    if "ground_pend_qpos" not in g:
+        pytest.skip("tests/golden/mjstep.npz predates the floor-contact leg of tools/mujoco_diff.py")
+    freq = float(g["frequency"])
+    for tag, pend in (("ground_pend", True), ("ground_nopend", False)):
+        qpos, qvel, act, ctrl, params = (g[f"{tag}_{k}"] for k in ("qpos", "qvel", "act", "ctrl", "params"))
+        for i in range(len(qpos)):
+            m = oracle.compile_model(params[i], pend, freq, True, ground=True)
+            f = oracle.forward_contact(m, qpos[i], qvel[i], act[i], ctrl[i])
+            assert (np.abs(f["qacc"] - g[f"{tag}_fwd_qacc"][i]) <= 1e-6 * (1 + np.abs(g[f"{tag}_fwd_qacc"][i]))).all()
+            for nstep in (1, 2, 3):
+                o = oracle.step(m, qpos[i], qvel[i], act[i], ctrl[i], nstep)
+                for a, name in zip(o, ("qpos", "qvel", "act", "sens")):
+                    b = g[f"{tag}_step{nstep}_{name}"][i]
+                    assert (np.abs(a - b) <= 1e-6 * (1 + np.abs(b))).all(), (tag, i, nstep, name)
+
+
 def test_harness_inputs_are_the_parity_test_inputs():
     """the harness steps MuJoCo on exactly the states test_substep_matches_oracle feeds the CUDA kernel"""
     rng = np.random.default_rng(7)
@@ -61,5 +81,13 @@ def test_harness_inputs_are_the_parity_test_inputs():
     qpos = np.concatenate([pos, q, rng.normal(size=(n, 2)) * 0.6], axis=1)
     got = mujoco_diff.seeded_cases(n, 7, True)
     assert np.array_equal(got[0], qpos)
+    # ... and, for the floor-contact leg, the states test_contact_step_matches_oracle feeds it
+    rng = np.random.default_rng(11)
+    n = 256
+    q = rng.normal(size=(n, 4))
+    q[: n // 4] = [1, 0, 0, 0] + 0.05 * rng.normal(size=(n // 4, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    pos = np.stack([rng.normal(size=n), rng.normal(size=n), rng.uniform(0.0, 1.5, size=n)], axis=1)
+    assert np.array_equal(mujoco_diff.near_floor_cases(n, 11, True)[0][:, :7], np.concatenate([pos, q], axis=1))
     ok, why = mujoco_diff.probe("/nonexistent")
     assert not ok and why

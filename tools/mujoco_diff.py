@@ -14,7 +14,9 @@ What it does when it can run
      (drone-major qpos[9i:9i+9], qvel[8i:8i+8], act[4i:4i+4]: BaseDroneEnv.py:367-375), calls mujoco.mj_forward and then
      mujoco.mj_step(model, data, nstep=frame_skip) (mujoco_vecenv.py:404-407) and compares qacc / sensordata (forward) and
      qpos / qvel / act / sensordata (after 1, 2, 3 and 100 steps) with oracle.forward / oracle.step: tolerance 1e-10;
-  4. with --write-golden freezes MuJoCo's outputs into tests/golden/mjstep.npz, after which tests/test_mujoco_pin.py pins the
+  4. repeats 3 (1, 2, 3 steps) on near-floor states - the inputs of tests/test_gpu_ground_contact.py - against oracle models with
+     ground=True: contact count, qacc / sensordata, stepped state; tolerance 1e-6 (MuJoCo's Newton solver stops at 1e-8);
+  5. with --write-golden freezes MuJoCo's outputs into tests/golden/mjstep.npz, after which tests/test_mujoco_pin.py pins the
      oracle against them on every box (no mujoco needed any more).
 
 Probe outcomes so far are recorded in DESIGN.md §3 (build container and the gpurun B200 box: ModuleNotFoundError for both
@@ -57,6 +59,25 @@ def seeded_cases(n=192, seed=7, pend=True):
     pos = np.array([0, 0, 15.0]) + rng.normal(size=(n, 3))
     qpos = np.concatenate([pos, q] + ([rng.normal(size=(n, 2)) * 0.6] if pend else []), axis=1)
     qvel = rng.normal(size=(n, 8 if pend else 6))
+    act = rng.uniform(0, 1, size=(n, 4))
+    actions = rng.uniform(0, 1, size=(n, 4))
+    params = NOMINAL * rng.uniform(0.85, 1.15, size=(n, 6))
+    if not pend:
+        params[:, 4:] = 0
+    return qpos, qvel, act, actions, params
+
+
+def near_floor_cases(n=256, seed=11, pend=True):
+    """the inputs of tests/test_gpu_ground_contact.py::test_contact_step_matches_oracle (same generator, same seed): random
+    attitudes at heights where the drone's geoms reach the floor plane"""
+    rng = np.random.default_rng(seed)
+    zmax = 1.5 if pend else 0.3
+    q = rng.normal(size=(n, 4))
+    q[: n // 4] = [1, 0, 0, 0] + 0.05 * rng.normal(size=(n // 4, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    pos = np.stack([rng.normal(size=n), rng.normal(size=n), rng.uniform(0.0, zmax, size=n)], axis=1)
+    qpos = np.concatenate([pos, q] + ([rng.normal(size=(n, 2)) * 0.5] if pend else []), axis=1)
+    qvel = rng.normal(size=(n, 8 if pend else 6)) * 0.5
     act = rng.uniform(0, 1, size=(n, 4))
     actions = rng.uniform(0, 1, size=(n, 4))
     params = NOMINAL * rng.uniform(0.85, 1.15, size=(n, 6))
@@ -138,7 +159,51 @@ def run(reference_root="/root/reference", write_golden=False, n=192, frequency=1
             report["checks"][f"mj_step_x{nstep}_{tag}"] = worst_s
             for name, arr in zip(("qpos", "qvel", "act", "sens"), out):
                 gold[f"{tag}_step{nstep}_{name}"] = arr
-    report["pass_1e-10"] = {k: bool(v <= (1e-10 if "x100" not in k else 1e-6)) for k, v in report["checks"].items()}
+    # ---- 4. floor contact: the same comparison on states whose geoms reach the floor, oracle models with
+    # ground=True.  MuJoCo's Newton solver stops at tolerance 1e-8, so these legs are held to 1e-6, not 1e-10.
+    for pend in (True, False):
+        qpos, qvel, act, actions, params = near_floor_cases(256, 11, pend)
+        n2 = len(qpos)
+        nq, nv = (9, 8) if pend else (7, 6)
+        model = build_mujoco_model(reference_root, params, frequency)
+        data = mujoco.MjData(model)
+        ctrl = 0.1 + 0.9 * actions
+        tag = "ground_pend" if pend else "ground_nopend"
+
+        def load2():
+            mujoco.mj_resetData(model, data)
+            data.qpos[:] = qpos.ravel(); data.qvel[:] = qvel.ravel(); data.act[:] = act.ravel(); data.ctrl[:] = ctrl.ravel()
+        load2()
+        mujoco.mj_forward(model, data)
+        report[f"{tag}_mujoco_ncon"] = int(data.ncon)
+        mj_qacc, mj_sens = data.qacc.reshape(n2, nv).copy(), data.sensordata.reshape(n2, 3).copy()
+        worst_f, ncon_oracle = 0.0, 0
+        for i in range(n2):
+            m = O.compile_model(params[i], pend, frequency, True, ground=True)
+            f = O.forward_contact(m, qpos[i], qvel[i], act[i], ctrl[i])
+            ncon_oracle += f["ncon"]
+            worst_f = max(worst_f, (np.abs(f["qacc"] - mj_qacc[i]) / (1 + np.abs(mj_qacc[i]))).max(),
+                          (np.abs(f["sensordata"] - mj_sens[i]) / (1 + np.abs(mj_sens[i]))).max())
+        report[f"{tag}_oracle_ncon"] = ncon_oracle
+        report["checks"][f"contact_count_{tag}"] = float(abs(ncon_oracle - int(data.ncon)))
+        report["checks"][f"contact_forward_qacc_sensordata_{tag}"] = worst_f
+        gold[f"{tag}_qpos"], gold[f"{tag}_qvel"], gold[f"{tag}_act"], gold[f"{tag}_ctrl"], gold[f"{tag}_params"] = qpos, qvel, act, ctrl, params
+        gold[f"{tag}_fwd_qacc"], gold[f"{tag}_fwd_sens"] = mj_qacc, mj_sens
+        for nstep in (1, 2, 3):
+            load2()
+            mujoco.mj_step(model, data, nstep=nstep)
+            out = (data.qpos.reshape(n2, nq).copy(), data.qvel.reshape(n2, nv).copy(), data.act.reshape(n2, 4).copy(), data.sensordata.reshape(n2, 3).copy())
+            worst_s = 0.0
+            for i in range(n2):
+                m = O.compile_model(params[i], pend, frequency, True, ground=True)
+                o = O.step(m, qpos[i], qvel[i], act[i], ctrl[i], nstep)
+                for a, b in zip(o, (out[0][i], out[1][i], out[2][i], out[3][i])):
+                    worst_s = max(worst_s, (np.abs(a - b) / (1 + np.abs(b))).max())
+            report["checks"][f"contact_mj_step_x{nstep}_{tag}"] = worst_s
+            for name, arr in zip(("qpos", "qvel", "act", "sens"), out):
+                gold[f"{tag}_step{nstep}_{name}"] = arr
+    report["pass_1e-10"] = {k: bool(v <= (1e-6 if ("x100" in k or "contact_" in k) else 1e-10)) if "contact_count" not in k else bool(v == 0)
+                            for k, v in report["checks"].items()}
     if write_golden:
         path = os.path.join(ROOT, "tests", "golden", "mjstep.npz")
         np.savez_compressed(path, mujoco_version=np.array(mujoco.__version__), frequency=np.array(float(frequency)), **gold)
