@@ -178,24 +178,41 @@ template <typename T> DSIM_DEV void dense_mass(const EnvConsts<T> &c, bool pend,
     } else { M[6 * 8 + 6] = T(1); M[7 * 8 + 7] = T(1); }
     for (int i = 0; i < 8; i++) for (int j = 0; j < i; j++) M[i * 8 + j] = M[j * 8 + i];
 }
-// in-place Cholesky (lower triangle) and solve, 8 x 8
+// in-place Cholesky (lower triangle) and solve, 8 x 8.  Every loop is fully unrolled so that a caller's matrix with
+// compile-time indices stays in registers (the slow path is bound by the latency of its local-memory arrays)
 template <typename T> DSIM_DEV void chol8(T *A) {
+    #pragma unroll
     for (int j = 0; j < 8; j++) {
         T d = A[j * 8 + j];
+        #pragma unroll
         for (int k = 0; k < j; k++) d -= A[j * 8 + k] * A[j * 8 + k];
         d = sqrt_(max_(d, T(1e-30)));
         A[j * 8 + j] = d;
         const T id = T(1) / d;
+        #pragma unroll
         for (int i = j + 1; i < 8; i++) {
             T s = A[i * 8 + j];
+            #pragma unroll
             for (int k = 0; k < j; k++) s -= A[i * 8 + k] * A[j * 8 + k];
             A[i * 8 + j] = s * id;
         }
     }
 }
 template <typename T> DSIM_DEV void chol8_solve(const T *L, T *b) {
-    for (int i = 0; i < 8; i++) { T s = b[i]; for (int k = 0; k < i; k++) s -= L[i * 8 + k] * b[k]; b[i] = s / L[i * 8 + i]; }
-    for (int i = 7; i >= 0; i--) { T s = b[i]; for (int k = i + 1; k < 8; k++) s -= L[k * 8 + i] * b[k]; b[i] = s / L[i * 8 + i]; }
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+        T s = b[i];
+        #pragma unroll
+        for (int k = 0; k < i; k++) s -= L[i * 8 + k] * b[k];
+        b[i] = s / L[i * 8 + i];
+    }
+    #pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        T s = b[i];
+        #pragma unroll
+        for (int k = i + 1; k < 8; k++) s -= L[k * 8 + i] * b[k];
+        b[i] = s / L[i * 8 + i];
+    }
 }
 // Jacobian row of direction d (body axes) at body point p moving with `body`: J x = d . (a + al x p + hinge terms)
 template <typename T> DSIM_DEV void contact_row(V3<T> d, V3<T> p, int body, V3<T> yc, T *J) {
@@ -287,8 +304,7 @@ __device__ DSIM_CONTACT_CALL int contact_solve(ContactIO<T> &io, const EnvConsts
     for (int k = 0; k < 8; k++) x[k] = io.x[k];
     // Newton converges quadratically once the active set is right: the iteration whose step falls below the precision's
     // resolution of x was the last useful one.  FP32: the gradient carries ~1e-6 of rounding noise per newton of force, so the
-    // tolerances sit just above that floor and the iteration cap does the rest (measured: a cap of 16 costs nothing - the
-    // slow path is bound by the latency of its local-memory arrays, the L1 being almost entirely carved out as shared memory)
+    // tolerances sit just above that floor and the iteration cap does the rest (measured: 10x looser tolerances buy 10 %)
     T trace = T(0);
     for (int k = 0; k < 8; k++) trace += M[k * 8 + k];
     const bool f32 = sizeof(T) == 4;
@@ -296,6 +312,7 @@ __device__ DSIM_CONTACT_CALL int contact_solve(ContactIO<T> &io, const EnvConsts
     #pragma unroll 1
     for (int it = 0; it < (f32 ? 16 : 40); it++) {
         for (int k = 0; k < 8; k++) { T s = -io.q[k]; for (int j = 0; j < 8; j++) s += M[k * 8 + j] * x[j]; gq[k] = s; grad[k] = s; }
+        #pragma unroll
         for (int k = 0; k < 64; k++) L[k] = M[k];
         #pragma unroll 1
         for (int i = 0; i < cs.n; i++)
@@ -304,13 +321,17 @@ __device__ DSIM_CONTACT_CALL int contact_solve(ContactIO<T> &io, const EnvConsts
                 T J[8];
                 const T aref = row(i, r, J);
                 T jar = -aref;
+                #pragma unroll
                 for (int k = 0; k < 8; k++) jar += J[k] * x[k];
                 jar_[4 * i + r] = jar;
                 if (jar >= T(0)) continue;
                 const T D = cs.D[i];
+                #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     grad[k] += D * jar * J[k];
-                    for (int j = 0; j <= k; j++) L[k * 8 + j] += D * J[k] * J[j];
+                    const T dj = D * J[k];
+                    #pragma unroll
+                    for (int j = 0; j <= k; j++) L[k * 8 + j] += dj * J[j];
                 }
             }
         T gn = T(0);
