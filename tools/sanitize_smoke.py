@@ -3,7 +3,7 @@
 buffer of a handle is allocated at its EXACT size between two 4 KB canary regions and `guard_check()` counts overwritten
 canary bytes (out-of-bounds device writes: bulk stores of ragged last pages, the observation block, per-env scalars).
 Also usable under compute-sanitizer (memcheck / racecheck / synccheck) where that is allowed.  Ragged batch sizes through every step-kernel
-instantiation (specialised C2 / C3 / C4, generic, FP64, no pendulum), in-kernel resets, evaluate, host entry point, both
+instantiation (specialised C2 / C3 / C4, generic, FP64, no pendulum, floor contact), in-kernel resets, evaluate, host entry point, both
 dependency modes, the auxiliary kernels and the two policy kernels.      compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
 import os
 import sys
@@ -21,10 +21,15 @@ cases = [(W.LocalFrameRPYParamsEnv, M.rewards.distance_energy_reward, dict(param
          (M.BaseDroneEnv, M.rewards.default_reward_fcn, dict(), 97),
          (W.LocalFrameRmParamsEnv, M.rewards.reward_2, dict(skip_steps=2), 65),
          (M.BaseDroneEnv, M.rewards.default_reward_fcn, dict(precision="fp64"), 70),
-         (M.BaseDroneEnv, M.rewards.default_reward_fcn, dict(pendulum=False), 33)]
+         (M.BaseDroneEnv, M.rewards.default_reward_fcn, dict(pendulum=False), 33),
+         # floor contact: the instantiations with the slow path, every drone within reach of the floor (z = 1 m, 1.2 m pendulum)
+         (W.LocalFrameRPYParamsEnv, M.rewards.distance_energy_reward, dict(ground_contact=True, start_pos=[0, 0, 1.0, 0], reference=[0, 0, 1.0, 0], max_distance=100.0), 1000 + 5),
+         (M.BaseDroneEnv, M.rewards.default_reward_fcn, dict(ground_contact=True, precision="fp64", start_pos=[0, 0, 1.0, 0], reference=[0, 0, 1.0, 0], max_distance=100.0), 70),
+         (M.BaseDroneEnv, M.rewards.default_reward_fcn, dict(ground_contact=True, pendulum=False, start_pos=[0, 0, 0.1, 0], reference=[0, 0, 0.1, 0], max_distance=100.0), 33)]
 for ready in (False, True):
     for cls, rew, extra, n in cases:
-        cfg = dict(M.base_config, num_drones=n, reward_fcn=rew, auto_reset=True, max_steps=3, max_distance=1.0, inputs_ready=ready, **extra)
+        cfg = dict(M.base_config, num_drones=n, reward_fcn=rew, auto_reset=True, max_steps=3, max_distance=1.0, inputs_ready=ready)
+        cfg.update(extra)
         envs = [cls(dict(cfg, env_id_offset=k * n)) for k in range(2)]
         dt = torch.float64 if extra.get("precision") == "fp64" else torch.float32
         for e in envs:
