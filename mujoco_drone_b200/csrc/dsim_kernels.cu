@@ -177,6 +177,18 @@ __global__ void trajectory_kernel(int n, T *refp, int kind, double t, double pha
     T *col = refp + page_elem(REF_ROWS, 0, i);
     col[0] = (T)(r[0] - st0); col[kTile] = (T)(r[1] - st1); col[2 * kTile] = (T)(r[2] - st2); col[3 * kTile] = (T)r[3];
 }
+// qpos0 of the freshly built model: every drone sits on env_gen.make_sim's spawn grid (env_gen.py:114-122: sz = ceil(sqrt(N)),
+// pitch 0.5 m, centred, z = 0.15 m; drone i at column i % sz, row i / sz of numpy's default 'xy' meshgrid), quaternion
+// identity, hinges 0 - what MjData holds until the first vector_reset
+template <typename T> __global__ void spawn_grid_kernel(int n, T *rw, double sx, double sy, double sz_) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int side = (int)ceil(sqrt((double)n));
+    const double x = ((i % side) - 0.5 * (side - 1)) * 0.5, y = ((i / side) - 0.5 * (side - 1)) * 0.5;
+    T *col = rw + page_elem(RW_ROWS, 0, i);
+    col[0 * kTile] = (T)(x - sx); col[1 * kTile] = (T)(y - sy); col[2 * kTile] = (T)(0.15 - sz_);
+    col[S_QUAT * kTile] = T(1);
+}
 // one row of a paged buffer := value, for the first n envs
 template <typename T> __global__ void fill_row_kernel(int n, T *base, int page_rows, int row, T value) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -382,13 +394,13 @@ extern "C" int dsim_create(const DsimConfig *cfg, int device, DsimHandle **out) 
     double chw[12];
     for (int k = 0; k < 6; k++) { chw[k] = cfg->param_center[k]; chw[6 + k] = cfg->param_halfwidth[k]; }
     CK(cudaMemcpy(h->center_hw, chw, sizeof chw, cudaMemcpyHostToDevice));
-    // quaternion rows start as identity (MjData qpos0 of a free joint), per-env reference = shared reference
-    for (int k = 0; k < 5; k++) {
-        const int is_ref = k < 4;
-        const double v = !is_ref ? 1.0 : (k < 3 ? cfg->reference[k] - cfg->start_pos[k] : cfg->reference[3]);
-        void *base = is_ref ? h->refp : h->rw;
-        const int rows = is_ref ? (int)REF_ROWS : (int)RW_ROWS, row = is_ref ? k : (int)S_QUAT;
-        if (h->rs == 4) fill_row<float>(h, base, rows, row, v); else fill_row<double>(h, base, rows, row, v);
+    // MjData qpos0: spawn grid, identity quaternions; per-env reference = shared reference
+    if (h->rs == 4) spawn_grid_kernel<float><<<(h->n + 255) / 256, 256>>>(h->n, (float *)h->rw, cfg->start_pos[0], cfg->start_pos[1], cfg->start_pos[2]);
+    else spawn_grid_kernel<double><<<(h->n + 255) / 256, 256>>>(h->n, (double *)h->rw, cfg->start_pos[0], cfg->start_pos[1], cfg->start_pos[2]);
+    h->launches++;
+    for (int k = 0; k < 4; k++) {
+        const double v = k < 3 ? cfg->reference[k] - cfg->start_pos[k] : cfg->reference[3];
+        if (h->rs == 4) fill_row<float>(h, h->refp, REF_ROWS, k, v); else fill_row<double>(h, h->refp, REF_ROWS, k, v);
     }
     CK(cudaGetLastError());
     rc = dsim_regen_params(h, 0, nullptr);

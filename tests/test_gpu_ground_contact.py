@@ -198,3 +198,24 @@ def test_many_drones_land_and_stay_on_the_floor():
     st = env.episode_stats()
     assert st["n_nonfinite"] == 0
     env.close()
+
+
+def test_before_the_first_reset_the_drones_sit_on_the_spawn_grid():
+    """SURVEY Q17 (env_gen.py:114-124): MjData starts at qpos0 = make_sim's spawn grid, 0.15 m above the floor; a vector_step issued
+    there (RLlib never does: it resets first) sends the pendulum into the floor and truncates every drone at once."""
+    import torch
+    import mujoco_drone_b200 as M
+    n = 70
+    env = M.BaseDroneEnv(dict(M.base_config, num_drones=n, ground_contact=True))
+    qp, qv, ac, sens, ns = env.get_state()
+    sz = int(np.ceil(np.sqrt(n)))
+    steps = (np.arange(sz) - (sz - 1) / 2) * 0.5
+    xpos, ypos, zpos = np.meshgrid(steps, steps, [0.15])
+    want = np.stack([xpos.flat[:n], ypos.flat[:n], zpos.flat[:n]], axis=1)
+    assert np.abs(qp[:, :3] - want).max() < 2e-6                   # FP32 offsets from start_pos z = 15
+    assert np.array_equal(qp[:, 3:], np.tile([1, 0, 0, 0, 0, 0], (n, 1))) and not qv.any() and not ac.any()
+    obs, rew, trunc = env.step_tensor(torch.rand((n, 4), device="cuda"))
+    assert trunc.all().item() and torch.isfinite(obs).all().item() and torch.isfinite(rew).all().item()
+    qp2 = env.get_state()[0]
+    assert (qp2[:, 2] > 0.15).all()                                 # the floor pushed them up (the weight starts 1.1 m under it)
+    env.close()
