@@ -233,3 +233,100 @@ def test_friction_stops_a_sliding_drone():
     for _ in range(100):
         qp, qv, ac, _ = O.step(m, qp, qv, ac, np.zeros(4))
     assert np.abs(qp - rest).max() < 1e-9
+
+
+def test_contact_stage_against_an_autograd_restatement():
+    """Third statement of the constraint stage, sharing no code with the oracle's (C, cdof Jacobians) or the kernel's (body-frame
+    rows): the Lagrangian model of tests/test_lagrangian_pin.py supplies M = d2T/dqdot2 and, by forward-mode autodiff of
+    `body origin + R_body(q) p_local`, the Jacobian of every contact point; body_invweight0, impedance, regulariser and
+    reference acceleration are written out again from MuJoCo's formulas; the convex problem is minimised by a damped Newton
+    iteration on autograd derivatives of the cost.  Only the contact LISTS are taken from the oracle (their geometry is held by
+    test_contact_lists_against_brute_force_depth)."""
+    import torch
+    import test_lagrangian_pin as LP
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        rng = np.random.default_rng(4)
+        worst, done = 0.0, 0
+        while done < 12:
+            pend = done % 3 != 2
+            params = np.array(PEND) * rng.uniform(0.8, 1.2, size=6)
+            if not pend:
+                params[4:] = 0
+            nq, nv = (9, 8) if pend else (7, 6)
+            qpos = np.concatenate([rng.normal(size=2), [rng.uniform(0, 1.3 if pend else 0.2)], _quat(rng.normal(size=3) * [1, 1, 3]), rng.normal(size=nq - 7) * 0.6])
+            qvel, act, ctrl = rng.normal(size=nv), rng.uniform(0, 1, 4), rng.uniform(0, 1, 4)
+            m = O.compile_model(params, pend, 100.0, True, ground=True)
+            cons = O.collide(m, qpos)
+            if not cons:
+                continue
+            got = O.forward_contact(m, qpos, qvel, act, ctrl)
+            free = O.forward(O.compile_model(params, pend, 100.0, True), qpos, qvel, act, ctrl)
+            mod = LP.Model(m, pend)
+            R0 = torch.tensor(LP._quat_to_mat(qpos[3:7]))
+            q = torch.zeros(nv); q[0:3] = torch.tensor(qpos[0:3])
+            if pend:
+                q[6:8] = torch.tensor(qpos[7:9])
+            qd = torch.tensor(qvel)
+            M, _ = mod.mass_and_bias(q, qd, R0)
+
+            def body_frame(qq, b, R_=R0):                    # (origin, rotation) of MuJoCo body b = 2 core, 3 link, 4 pendulum
+                p, th = qq[0:3], qq[3:6]
+                R = R_ @ torch.linalg.matrix_exp(LP._hat(th))
+                if b == 2:
+                    return p, R
+                o = p + R @ mod.pos_c
+                Rc = R @ LP._rx(qq[6])
+                if b == 3:
+                    return o, Rc
+                return o + Rc @ mod.pos_d, Rc @ LP._ry(qq[7])
+
+            def point_jac(qq, b, world, R_=R0):
+                o, Rb = body_frame(qq, b, R_)
+                local = (Rb.T @ (torch.tensor(world) - o)).detach()
+                return torch.func.jacfwd(lambda z: body_frame(z, b, R_)[0] + body_frame(z, b, R_)[1] @ local)(qq)
+
+            # body_invweight0 at qpos0 (identity attitude, hinges 0)
+            q0, I3 = torch.zeros(nv), torch.eye(3)
+            M0, _ = mod.mass_and_bias(q0, torch.zeros(nv), I3)
+            tran = {}
+            for k, b in enumerate([2, 3, 4] if pend else [2]):
+                com0 = mod.frames(q0, I3)[0][k][1].detach().numpy()
+                J0 = point_jac(q0, b, com0, I3)
+                tran[b] = torch.trace(J0 @ torch.linalg.solve(M0, J0.T)) / 3
+            tc, dmax, mu = max(0.02, 2 * m.timestep), 0.95, 1.0
+            K, B = 1 / (dmax * tc) ** 2, 2 / (dmax * tc)
+            rows, aref, D = [], [], []
+            for c in cons:
+                J = point_jac(q, c["body"], c["pos"])
+                d = _impedance(c["dist"])
+                Rr = 2 * mu * mu * (1 - d) / d * (1 + mu * mu) * tran[c["body"]]
+                for e in ([0, 1, 1], [0, -1, 1], [-1, 0, 1], [1, 0, 1]):
+                    r = torch.tensor(e, dtype=torch.float64) @ J
+                    rows.append(r); aref.append(-B * (r @ qd) - K * d * c["dist"]); D.append(1 / Rr)
+            Jm, ar, Dv = torch.stack(rows), torch.stack(aref), torch.stack(D)
+            a0 = torch.tensor(free["qacc"])
+
+            def cost(x):
+                res = torch.clamp(Jm @ x - ar, max=0.0)
+                return 0.5 * (x - a0) @ M @ (x - a0) + 0.5 * (Dv * res * res).sum()
+            x = a0.clone()
+            for _ in range(60):                              # damped Newton on the autograd gradient / generalised Hessian
+                g = torch.func.grad(cost)(x)
+                if g.abs().max() < 1e-11 * (1 + (M @ a0).abs().max()):
+                    break
+                act_rows = (Jm @ x - ar) < 0
+                H = M + (Jm[act_rows].T * Dv[act_rows]) @ Jm[act_rows]
+                dx = -torch.linalg.solve(H, g)
+                t, c0 = 1.0, cost(x)
+                while cost(x + t * dx) > c0 + 1e-4 * t * (g @ dx) and t > 1e-10:
+                    t *= 0.5
+                x = x + t * dx
+            err = (np.abs(x.numpy() - got["qacc"]) / (1 + np.abs(got["qacc"]))).max()
+            worst = max(worst, err)
+            done += 1
+        print("contact stage, oracle vs autograd restatement: max relative deviation of qacc", worst)
+        assert worst < 1e-8, worst
+    finally:
+        torch.set_default_dtype(old)
