@@ -83,8 +83,9 @@ def test_contact_step_matches_oracle(oracle, precision, frame_skip, pend):
     prm = env.drone_params
     # FP32: a contact force is K d(r) r / R with r the penetration (~1e-4 .. 1e-2 m) computed from a height of ~1 m: its
     # relative error is eps * 1 m / r, i.e. up to 1e-3 where the penetration is shallow, times h / m on the velocity
-    # measured (B200, this seed): FP64 2e-14 / 1e-12 / 7e-13; FP32 3e-6 (hinge angles) / 3.3e-5 / 1.1e-4
-    tol = dict(pos=1e-11, vel=1e-9, acc=1e-7) if precision == "fp64" else dict(pos=1e-5, vel=2e-4, acc=1e-3)
+    # measured maxima over 8 seeds x 256 states (tools/gpu_ground_seeds.py, profiles/r02d_ground_contact.txt): FP64 1.8e-14 /
+    # 1.0e-12 / 4.2e-13; FP32 8.3e-6 (hinge angles) / 5.5e-5 / 9.5e-5 -> FP32 tolerances 3-4x those
+    tol = dict(pos=1e-11, vel=1e-9, acc=1e-7) if precision == "fp64" else dict(pos=3e-5, vel=2e-4, acc=3e-4)
     touching = 0
     worst = dict(pos=0.0, vel=0.0, acc=0.0)
     for i in range(n):
