@@ -6,11 +6,12 @@
 // (~1e-3 on the logits, and its FP32-sized weights do not fit either).  This kernel is the faithful mode: the whole network
 // fused on the FP32 pipe, activations in shared memory, weights streamed through L1 from their 363 KB L2-resident blob.
 //
-//   tile = 64 rows per CTA pass, 512 threads = 16 warps: warp w owns rows 8 (w % 8) .. +7 and the column half w / 8 (every A
-//   operand is a warp-wide broadcast read of the transposed activation tile At[k][row]; lane l owns output columns l, l+32,
-//   ... of its half, so every W operand is a coalesced 128-byte line of the transposed weights Wt[k][n], shared by eight
-//   warps through L1): 32 FFMA per 2 LDS.128 + 4 LDG at N = 256.  Layers ping-pong between two activation tiles; BatchNorm
-//   (eval) is folded into its two consumers on the host.  tanh(x) = 1 - 2 / (exp(2x) + 1) on the MUFU exp2 / rcp (abs. error
+//   tile = 128 rows per CTA pass, 512 threads = 16 warps: warp w owns rows 8 w .. +7 and ALL output columns (every A operand
+//   is a warp-wide broadcast read of the transposed activation tile At[k][row]; lane l owns columns l, l+32, ..., so every W
+//   operand is a coalesced 128-byte line of the transposed weights Wt[k][n], shared by the sixteen warps through L1):
+//   64 FFMA per 2 LDS.128 + 8 LDG at N = 256, 32 per 2 + 4 at N = 128 (the 64-row tile with the columns split over two warp
+//   groups had 32 / 16: it was bound by operand fetches, 3.06 ms per 524 288 rows).  Layers ping-pong between a 256-deep and
+//   a 128-deep activation tile (203 KB); BatchNorm (eval) is folded into its two consumers on the host.  tanh(x) = 1 - 2 / (exp(2x) + 1) on the MUFU exp2 / rcp (abs. error
 //   ~2e-7: the logits stay within 1e-6 of the torch FP32 module, tests/test_policy_reference.py).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,7 +24,7 @@
 namespace {
 
 constexpr int S_DIM = 16, P_DIM = 6, A_DIM = 4, E_DIM = 8, OBS_DIM = S_DIM + P_DIM, ENC_H = 32, K1 = S_DIM + A_DIM + E_DIM;   // 28
-constexpr int TM = 64, LDT = TM + 4;       // rows per tile; row pitch of the transposed tiles (68: conflict-free 16-byte stores)
+constexpr int TM = 128, LDT = TM + 4;      // rows per tile; row pitch of the transposed tiles (132 = 4 mod 32: conflict-free 16-byte stores)
 // fp32 blob (float offsets): transposed weights Wt[k][n] then bias, per layer
 constexpr int F_W1 = 0, F_B1 = F_W1 + K1 * 256;                 // 28 -> 256
 constexpr int F_W2 = F_B1 + 256, F_B2 = F_W2 + 256 * 128;       // 256 -> 128
@@ -34,7 +35,7 @@ constexpr int F_V3 = F_B4 + 8, F_C3 = F_V3 + 128;               // 128 -> 1
 constexpr int F_E1 = F_C3 + 1, F_E1B = F_E1 + ENC_H * P_DIM;    // encoder 6 -> 32 ([j][k])
 constexpr int F_E2 = F_E1B + ENC_H, F_E2B = F_E2 + E_DIM * ENC_H;   // 32 -> 8 ([e][j])
 constexpr int F_ELEMS = F_E2B + E_DIM;
-constexpr int SMEM_BYTES = 2 * 256 * LDT * 4;                   // two activation tiles [256][68] fp32 = 139 264 B
+constexpr int SMEM_BYTES = (256 + 128) * LDT * 4;               // activation tiles A [256][132] and B [128][132] fp32 = 202 752 B
 
 struct P32 {
     const float *w, *obs, *prev_action;
@@ -49,13 +50,11 @@ __device__ __forceinline__ float tanh_acc(float x) {
     const float e = __expf(2.0f * x);
     return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
-// Ot[n][row] = act(bias[n] + sum_k Wt[k][n] * At[k][row]) for the 64 rows of the tile; N a multiple of 64
+// Ot[n][row] = act(bias[n] + sum_k Wt[k][n] * At[k][row]) for the 128 rows of the tile; N a multiple of 32
 template <int K, int N, bool TANH>
-__device__ __forceinline__ void dense(const float *__restrict__ Wt_, const float *__restrict__ bias_, const float *At, float *Ot_) {
-    constexpr int CN = N / 64;
-    const int tx = threadIdx.x & 31, wp = threadIdx.x >> 5, ty = wp & 7, half = wp >> 3;
-    const float *Wt = Wt_ + half * (N / 2), *bias = bias_ + half * (N / 2);
-    float *Ot = Ot_ + half * (N / 2) * LDT;
+__device__ __forceinline__ void dense(const float *__restrict__ Wt, const float *__restrict__ bias, const float *At, float *Ot) {
+    constexpr int CN = N / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     float acc[8][CN];
     #pragma unroll
     for (int j = 0; j < CN; j++) {
@@ -65,7 +64,7 @@ __device__ __forceinline__ void dense(const float *__restrict__ Wt_, const float
     }
     // software pipeline over k in blocks of KB: the W and A operands of block b + 1 are fetched while block b is multiplied
     // (an unpipelined loop sat 28 % of its time on the first FFMA of every block waiting for the L1 / L2 round trip)
-    constexpr int KB = 2;
+    constexpr int KB = CN >= 8 ? 1 : 2;                                       // 64 accumulators leave room for one operand block in flight
     static_assert(K % KB == 0, "K must be a multiple of the pipeline block");
     const float *wq = Wt + tx;
     const float *ap = At + ty * 8;
@@ -112,7 +111,7 @@ __device__ __forceinline__ void dense(const float *__restrict__ Wt_, const float
 
 __global__ void __launch_bounds__(NT, 1) rma_full_forward_fp32_kernel(const P32 p) {
     extern __shared__ __align__(16) float sm[];
-    float *A = sm, *B = sm + 256 * LDT;
+    float *A = sm, *B = sm + 256 * LDT;                              // A: up to 256 activation rows deep, B: up to 128
     const int tid = threadIdx.x;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -155,9 +154,9 @@ __global__ void __launch_bounds__(NT, 1) rma_full_forward_fp32_kernel(const P32 
         dense<128, 256, true>(p.w + F_W3, p.w + F_B3, B, A);         // [l1 | v1] -> A
         __syncthreads();
         dense<128, 128, true>(p.w + F_V2, p.w + F_C2, A + 128 * LDT, B);   // v2 = tanh(V2 v1 + c2) -> B
-        // logits = W4 l1 + b4: 64 rows x 8 outputs, thread -> (row, output pair)
-        if (tid < 256) {
-            const int row = tid & 63, o2 = (tid >> 6) * 2;
+        // logits = W4 l1 + b4: 128 rows x 8 outputs, thread -> (row, output pair)
+        {
+            const int row = tid & (TM - 1), o2 = (tid >> 7) * 2;
             float x0 = __ldg(p.w + F_B4 + o2), x1 = __ldg(p.w + F_B4 + o2 + 1);
             #pragma unroll 8
             for (int k = 0; k < 128; k++) {
