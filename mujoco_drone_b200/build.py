@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdronesim_b200.so")
 SOURCES = ["dsim_kernels.cu", "dsim_policy_mlp.cu", "dsim_policy_fp32.cu"]
-HEADERS = ["dsim_device.cuh", "dsim_obs_reward.cuh", "dsim_params.cuh", "dsim_step.cuh", "dsim_contact.cuh", "dsim_policy.cuh", os.path.join("..", "..", "include", "dronesim_b200.h")]
+HEADERS = ["dsim_device.cuh", "dsim_obs_reward.cuh", "dsim_params.cuh", "dsim_step.cuh", "dsim_step_x2.cuh", "dsim_packed.cuh", "dsim_contact.cuh", "dsim_policy.cuh", os.path.join("..", "..", "include", "dronesim_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -227,6 +227,39 @@ template <typename T> DSIM_DEV V3<T> ldl3_solve(const Ldl3<T> &f, V3<T> b) {
     return mk(z0, z1, z2);
 }
 
+// mju_normalize4 of the free-joint quaternion: a (near-)zero quaternion becomes identity
+template <typename T> DSIM_DEV void quat_unit(T sw, T sx, T sy, T sz, T &qw, T &qx, T &qy, T &qz) {
+    const T qn = sw * sw + sx * sx + sy * sy + sz * sz;
+    const bool qok = qn >= T(1e-30);
+    const T qi = rsqrt_(qn);
+    qw = qok ? sw * qi : T(1); qx = qok ? sx * qi : T(0); qy = qok ? sy * qi : T(0); qz = qok ? sz * qi : T(0);
+}
+// mju_quatIntegrate: the rotation quaternion of one step, [rw, kq * w] = [cos(a), sin(a) / |w| * w] with a = h |w| / 2 and
+// w2 = |w|^2.  FP32: even Taylor series in z = a^2 (no square root, no division, exact identity for w = 0 like MuJoCo's
+// |w| < mjMINVAL branch); relative error < 1e-7 for a <= 0.8, i.e. |w| <= 160 rad/s at 100 Hz; polynomial sincos beyond.
+template <typename T> DSIM_DEV void quat_step(T h, T w2, T &rw, T &kq) {
+    rw = T(1); kq = T(0);
+    if constexpr (std::is_same<T, float>::value) {
+        const float z = (0.25f * h * h) * w2;
+        if (z <= 0.64f) {
+            float ps = fmaf(z, 2.7557319e-6f, -1.9841270e-4f); ps = fmaf(ps, z, 8.3333333e-3f); ps = fmaf(ps, z, -1.6666667e-1f);
+            kq = (0.5f * h) * fmaf(ps, z, 1.0f);
+            float pc = fmaf(z, -2.7557319e-7f, 2.4801587e-5f); pc = fmaf(pc, z, -1.3888889e-3f); pc = fmaf(pc, z, 4.1666667e-2f); pc = fmaf(pc, z, -0.5f);
+            rw = fmaf(pc, z, 1.0f);
+        } else {
+            const float iw = rsqrt_(w2), wn = w2 * iw;
+            float sh;
+            sincos_hinge(0.5f * h * wn, &sh, &rw);                          // branch-free polynomial (7e-8): no libm slow path in the kernel image
+            kq = sh * iw;
+        }
+    } else if (w2 >= T(1e-30)) {
+        const T wn = sqrt_(w2);
+        T sh;
+        sincos_(T(0.5) * h * wn, &sh, &rw);
+        kq = sh / wn;
+    }
+}
+
 // ------------------------------------------------------------------ one mj_step (Euler, implicit hinge damping)
 // ADVANCE=false evaluates only the forward part (mj_forward: accelerometer refresh after set_state).
 // GROUND: floor contacts (dsim_contact.cuh) for drones whose bounding sphere reaches the floor; `g` is only read then.
@@ -239,10 +272,8 @@ template <typename T> __device__ DSIM_CONTACT_CALL int contact_solve(ContactIO<T
 template <typename T, bool PEND, bool ADVANCE, bool GROUND = false>
 DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T h, const GroundCtx<T> *g = nullptr) {
     // -- kinematics (mj_kinematics normalises the free-joint quaternion)
-    const T qn = s.qw * s.qw + s.qx * s.qx + s.qy * s.qy + s.qz * s.qz;
-    const bool qok = qn >= T(1e-30);                                         // mju_normalize4: a (near-)zero quaternion becomes identity
-    const T qi = rsqrt_(qn);
-    const T qw = qok ? s.qw * qi : T(1), qx = qok ? s.qx * qi : T(0), qy = qok ? s.qy * qi : T(0), qz = qok ? s.qz * qi : T(0);
+    T qw, qx, qy, qz;
+    quat_unit(s.qw, s.qx, s.qy, s.qz, qw, qx, qy, qz);
     const M3<T> R = quat_to_mat(qw, qx, qy, qz);
     const V3<T> vb = tmul(R, s.vel);                                         // origin velocity, body coords
     const V3<T> gb = mk(T(-kGravity) * R.m[6], T(-kGravity) * R.m[7], T(-kGravity) * R.m[8]);   // R^T g
@@ -417,26 +448,8 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
         // FP32: even Taylor series in z = a^2 (no square root, no division, exact identity for w = 0 like MuJoCo's
         // |w| < mjMINVAL branch); relative error < 1e-7 for a <= 0.8, i.e. |w| <= 160 rad/s at 100 Hz; libm beyond.
         const T w2 = dot(s.om, s.om);
-        T rw = T(1), kq = T(0);
-        if constexpr (std::is_same<T, float>::value) {
-            const float z = (0.25f * h * h) * w2;
-            if (z <= 0.64f) {
-                float ps = fmaf(z, 2.7557319e-6f, -1.9841270e-4f); ps = fmaf(ps, z, 8.3333333e-3f); ps = fmaf(ps, z, -1.6666667e-1f);
-                kq = (0.5f * h) * fmaf(ps, z, 1.0f);
-                float pc = fmaf(z, -2.7557319e-7f, 2.4801587e-5f); pc = fmaf(pc, z, -1.3888889e-3f); pc = fmaf(pc, z, 4.1666667e-2f); pc = fmaf(pc, z, -0.5f);
-                rw = fmaf(pc, z, 1.0f);
-            } else {
-                const float iw = rsqrt_(w2), wn = w2 * iw;
-                float sh;
-                sincos_hinge(0.5f * h * wn, &sh, &rw);                      // branch-free polynomial (7e-8): no libm slow path in the kernel image
-                kq = sh * iw;
-            }
-        } else if (w2 >= T(1e-30)) {
-            const T wn = sqrt_(w2);
-            T sh;
-            sincos_(T(0.5) * h * wn, &sh, &rw);
-            kq = sh / wn;
-        }
+        T rw, kq;
+        quat_step(h, w2, rw, kq);
         const T rx_ = kq * s.om.x, ry_ = kq * s.om.y, rz_ = kq * s.om.z;
         s.qw = qw * rw - qx * rx_ - qy * ry_ - qz * rz_;
         s.qx = qw * rx_ + qx * rw + qy * rz_ - qz * ry_;

@@ -17,6 +17,7 @@
 #include "dsim_obs_reward.cuh"
 #include "dsim_params.cuh"
 #include "dsim_contact.cuh"
+#include "dsim_packed.cuh"
 #include "dsim_policy.cuh"
 
 using namespace dsim;
@@ -26,6 +27,7 @@ namespace {
 constexpr int kBlock = 128;
 
 #include "dsim_step.cuh"
+#include "dsim_step_x2.cuh"
 
 // mj_forward after set_state (mujoco_vecenv.py:396-402): refresh sensordata (+ obs) from the current state
 template <typename T, bool PEND>
@@ -608,6 +610,24 @@ template <typename T> static cudaError_t launch_step(DsimHandle *h, const KParam
 #endif
         const int o = kp.obs_id, r = kp.reward_id;
         const int cfg = (kp.per_env_consts ? 1 : 0) | (kp.refp ? 2 : 0) | (kp.frame_skip == 1 ? 4 : 0);
+        if constexpr (std::is_same<T, float>::value) {
+            // two envs per lane on the packed FP32 pipe (dsim_step_x2.cuh) while a warp has at most two page pairs
+            static const int x2 = getenv("DSIM_X2") ? atoi(getenv("DSIM_X2")) : 0;
+            if (x2 && !kp.timeline) {
+                const int npairs = (pages + 1) / 2;
+                const unsigned smem2 = kp.smem_per_slot * kX2Slots * kStepWarps;
+                cudaError_t e2 = cudaSuccess;
+                auto try_x2 = [&](auto kernel) {
+                    int cap = 0;
+                    if (step_fn_capacity((const void *)kernel, h->device, smem2, &cap) != cudaSuccess) { cudaGetLastError(); return false; }
+                    if (npairs > 2 * cap * kStepWarps) return false;
+                    e2 = launch_one(h, kernel, smem2, st, &kp, npairs);
+                    return true;
+                };
+                if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2 && cfg == 5 && try_x2(step_kernel_x2<DSIM_OBS_LOCAL_RPY_PARAMS, 2, 5>)) return e2;
+                if (o == DSIM_OBS_LOCAL_RPY && r == 1 && cfg == 6 && try_x2(step_kernel_x2<DSIM_OBS_LOCAL_RPY, 1, 6>)) return e2;
+            }
+        }
         // BASELINE configs 4 / 5 (per-env randomised parameters), 3 (moving per-env setpoints, one parameter set), 2 (base_config: per-env parameters, raw 33-float rows)
         if (o == DSIM_OBS_LOCAL_RPY_PARAMS && r == 2 && cfg == 5) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY_PARAMS, 2, 5>, smem, st, &kp, pages);
         if (o == DSIM_OBS_LOCAL_RPY && r == 1 && cfg == 6) return launch_one(h, step_kernel<float, true, DSIM_OBS_LOCAL_RPY, 1, 6>, smem, st, &kp, pages);

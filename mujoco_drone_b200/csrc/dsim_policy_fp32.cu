@@ -9,8 +9,8 @@
 //   tile = 128 rows per CTA pass, 512 threads = 16 warps: warp w owns rows 8 w .. +7 and ALL output columns (every A operand
 //   is a warp-wide broadcast read of the transposed activation tile At[k][row]; lane l owns columns l, l+32, ..., so every W
 //   operand is a coalesced 128-byte line of the transposed weights Wt[k][n], shared by the sixteen warps through L1):
-//   64 FFMA per 2 LDS.128 + 8 LDG at N = 256, 32 per 2 + 4 at N = 128 (the 64-row tile with the columns split over two warp
-//   groups had 32 / 16: it was bound by operand fetches, 3.06 ms per 524 288 rows).  Layers ping-pong between a 256-deep and
+//   32 packed FFMA2 (64 FMAs) per 2 LDS.128 + 8 LDG at N = 256, 16 per 2 + 4 at N = 128 (the 64-row tile with the columns
+//   split over two warp groups and scalar FFMAs: 3.06 ms per 524 288 rows; 128-row tile 2.77 ms; FFMA2 2.31 ms).  Layers ping-pong between a 256-deep and
 //   a 128-deep activation tile (203 KB); BatchNorm (eval) is folded into its two consumers on the host.  tanh(x) = 1 - 2 / (exp(2x) + 1) on the MUFU exp2 / rcp (abs. error
 //   ~2e-7: the logits stay within 1e-6 of the torch FP32 module, tests/test_policy_reference.py).
 #include <cuda_runtime.h>
@@ -50,17 +50,25 @@ __device__ __forceinline__ float tanh_acc(float x) {
     const float e = __expf(2.0f * x);
     return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
+// Blackwell's packed FP32 FMA: two IEEE fma.rn per lane and instruction (SASS FFMA2).  A three-register FFMA issues every other
+// cycle per scheduler (register read ports), so a scalar-FFMA kernel tops out at half the FP32 peak (measured: FMA pipe 50 %
+// active, 34 TFLOP/s, with eligible warps held at dispatch); FFMA2 moves 64-bit operands through the same ports.  Results are
+// bit-identical to fmaf.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(u64 &d, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
 // Ot[n][row] = act(bias[n] + sum_k Wt[k][n] * At[k][row]) for the 128 rows of the tile; N a multiple of 32
 template <int K, int N, bool TANH>
 __device__ __forceinline__ void dense(const float *__restrict__ Wt, const float *__restrict__ bias, const float *At, float *Ot) {
     constexpr int CN = N / 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    float acc[8][CN];
+    u64 acc[4][CN];                                                           // [row pair][column]: rows (2 rp, 2 rp + 1) of this warp's eight
     #pragma unroll
     for (int j = 0; j < CN; j++) {
         const float b = __ldg(bias + tx + 32 * j);
         #pragma unroll
-        for (int r = 0; r < 8; r++) acc[r][j] = b;
+        for (int r = 0; r < 4; r++) acc[r][j] = pack2(b, b);
     }
     // software pipeline over k in blocks of KB: the W and A operands of block b + 1 are fetched while block b is multiplied
     // (an unpipelined loop sat 28 % of its time on the first FFMA of every block waiting for the L1 / L2 round trip)
@@ -91,18 +99,26 @@ __device__ __forceinline__ void dense(const float *__restrict__ Wt, const float 
         }
         #pragma unroll
         for (int u = 0; u < KB; u++) {
-            const float av[8] = {a[cur][u][0].x, a[cur][u][0].y, a[cur][u][0].z, a[cur][u][0].w, a[cur][u][1].x, a[cur][u][1].y, a[cur][u][1].z, a[cur][u][1].w};
+            // row pairs come packed out of the 16-byte activation loads; the weight of a column is duplicated into both halves
+            const u64 av[4] = {pack2(a[cur][u][0].x, a[cur][u][0].y), pack2(a[cur][u][0].z, a[cur][u][0].w),
+                               pack2(a[cur][u][1].x, a[cur][u][1].y), pack2(a[cur][u][1].z, a[cur][u][1].w)};
             #pragma unroll
-            for (int r = 0; r < 8; r++)
+            for (int j = 0; j < CN; j++) {
+                const u64 ww = pack2(w[cur][u][j], w[cur][u][j]);
                 #pragma unroll
-                for (int j = 0; j < CN; j++) acc[r][j] = fmaf(av[r], w[cur][u][j], acc[r][j]);
+                for (int r = 0; r < 4; r++) ffma2(acc[r][j], av[r], ww);
+            }
         }
     }
     #pragma unroll
     for (int j = 0; j < CN; j++) {
         float v[8];
         #pragma unroll
-        for (int r = 0; r < 8; r++) v[r] = TANH ? tanh_acc(acc[r][j]) : acc[r][j];
+        for (int r = 0; r < 4; r++) unpack2(acc[r][j], v[2 * r], v[2 * r + 1]);
+        if (TANH) {
+            #pragma unroll
+            for (int r = 0; r < 8; r++) v[r] = tanh_acc(v[r]);
+        }
         float *o = Ot + (tx + 32 * j) * LDT + ty * 8;
         *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4 *>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
