@@ -2,7 +2,7 @@
 """Static evidence about the built kernels, for profiles/: `nvcc -Xptxas -v` resource usage per kernel (registers, spills,
 stack, shared memory) and per-kernel counts of the SASS mnemonics that prove the hardware paths (cuobjdump -sass of the
 in-tree libdronesim_b200.so): UTCHMMA / UTCBAR / LDTM / STTM (tcgen05 MMA, commit, tensor-memory load / store), UBLKCP
-(cp.async.bulk = TMA 1D bulk copy), SYNCS (mbarrier), ACQBULK / PREEXIT (programmatic dependent launch), FFMA / FMUL / FADD.
+(cp.async.bulk = TMA 1D bulk copy), SYNCS (mbarrier), ACQBULK / PREEXIT (programmatic dependent launch), FFMA / FMUL / FADD and their packed two-per-lane forms FFMA2 / FMUL2 / FADD2.
 
     python tools/build_evidence.py > profiles/r02_build_evidence.txt
 """
@@ -51,7 +51,7 @@ for line in sass.splitlines():
         if m.group(1) in ("UBLKCP", "SYNCS", "LDTM", "STTM"):
             counts[cur][m.group(1) + m.group(2)] += 1
 dm = demangle(list(counts))
-KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UBLKCP.S.G", "UBLKCP.G.S", "SYNCS", "ACQBULK", "PREEXIT", "FFMA", "FMUL", "FADD", "MUFU", "DFMA", "DADD", "DMUL"]
+KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UBLKCP.S.G", "UBLKCP.G.S", "SYNCS", "ACQBULK", "PREEXIT", "FFMA", "FMUL", "FADD", "FFMA2", "FMUL2", "FADD2", "MUFU", "DFMA", "DADD", "DMUL"]
 print("\n## SASS mnemonic counts per kernel (cuobjdump -sass mujoco_drone_b200/libdronesim_b200.so; static instruction counts)")
 print("  " + "kernel".ljust(66) + " ".join(k.rjust(10) for k in KEYS) + "     total")
 for fn, c in counts.items():
