@@ -171,6 +171,10 @@ template <typename T> DSIM_DEV M3<T> rpy_to_mat(T roll, T pitch, T yaw) {
     return R;
 }
 
+}  // namespace dsim
+#include "dsim_packed.cuh"     // F2: two FP32 values per register pair on the packed FP32 pipe (needs the scalar helpers and V3 above)
+namespace dsim {
+
 // ------------------------------------------------------------------ per-env state held in registers
 template <typename T> struct EnvState {
     V3<T> pos;            // OFFSET from start_pos
@@ -260,6 +264,32 @@ template <typename T> DSIM_DEV void quat_step(T h, T w2, T &rw, T &kq) {
     }
 }
 
+// free-joint quaternion: normalisation and the per-step rotation, packed where it is plain arithmetic
+DSIM_DEV void quat_unit(F2 sw, F2 sx, F2 sy, F2 sz, F2 &qw, F2 &qx, F2 &qy, F2 &qz) {
+    const F2 qn = sw * sw + sx * sx + sy * sy + sz * sz;
+    const F2 qi = rsqrt_(qn);
+    qw = sw * qi; qx = sx * qi; qy = sy * qi; qz = sz * qi;
+    const bool ok0 = qn.lo() >= 1e-30f, ok1 = qn.hi() >= 1e-30f;
+    if (!(ok0 && ok1)) {                                            // (near-)zero quaternion -> identity, per half
+        qw = F2(ok0 ? qw.lo() : 1.f, ok1 ? qw.hi() : 1.f); qx = F2(ok0 ? qx.lo() : 0.f, ok1 ? qx.hi() : 0.f);
+        qy = F2(ok0 ? qy.lo() : 0.f, ok1 ? qy.hi() : 0.f); qz = F2(ok0 ? qz.lo() : 0.f, ok1 ? qz.hi() : 0.f);
+    }
+}
+DSIM_DEV void quat_step(F2 h, F2 w2, F2 &rw, F2 &kq) {
+    const F2 z = (F2(0.25f) * h * h) * w2;
+    if (z.lo() <= 0.64f && z.hi() <= 0.64f) {                       // both envs in the Taylor range (|w| <= 160 rad/s at 100 Hz)
+        F2 ps = fma2(z, F2(2.7557319e-6f), F2(-1.9841270e-4f)); ps = fma2(ps, z, F2(8.3333333e-3f)); ps = fma2(ps, z, F2(-1.6666667e-1f));
+        kq = (F2(0.5f) * h) * fma2(ps, z, F2(1.0f));
+        F2 pc = fma2(z, F2(-2.7557319e-7f), F2(2.4801587e-5f)); pc = fma2(pc, z, F2(-1.3888889e-3f)); pc = fma2(pc, z, F2(4.1666667e-2f)); pc = fma2(pc, z, F2(-0.5f));
+        rw = fma2(pc, z, F2(1.0f));
+    } else {
+        float r0, k0, r1, k1;
+        quat_step(h.lo(), w2.lo(), r0, k0); quat_step(h.hi(), w2.hi(), r1, k1);
+        rw = F2(r0, r1); kq = F2(k0, k1);
+    }
+}
+
+
 // ------------------------------------------------------------------ one mj_step (Euler, implicit hinge damping)
 // ADVANCE=false evaluates only the forward part (mj_forward: accelerometer refresh after set_state).
 // GROUND: floor contacts (dsim_contact.cuh) for drones whose bounding sphere reaches the floor; `g` is only read then.
@@ -283,7 +313,14 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
     const T mh = mC + mD, mtot = c.mB + mh, inv_m = rcp_(mtot);
 
     T sx = 0, cx = 1, sy = 0, cy = 1;
-    if (PEND) { sincos_hinge(s.hx, &sx, &cx); sincos_hinge(s.hy, &sy, &cy); }
+    if (PEND) {
+        if constexpr (std::is_same<T, float>::value) {
+            // the two hinge angles through ONE packed evaluation (FP32 scalar issues every other cycle; FFMA2 carries both)
+            F2 S, C;
+            sincos_hinge(F2(s.hx, s.hy), &S, &C);
+            sx = S.lo(); sy = S.hi(); cx = C.lo(); cy = C.hi();
+        } else { sincos_hinge(s.hx, &sx, &cx); sincos_hinge(s.hy, &sy, &cy); }
+    }
     const V3<T> yc = mk(T(0), cx, sx);                                       // hinge-y axis (C frame y) in body coords
     const V3<T> n = mk(sy, -sx * cy, cx * cy);                               // pendulum axis (D frame z)
     const V3<T> xd = mk(cy, sx * sy, -cx * sy);                              // D frame x
@@ -337,7 +374,10 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
     V3<T> flin = mk(T(0), T(0), c.F * ((a0 + a1) + (a2 + a3)));
     V3<T> fang = mk(c.Fs * ((a1 + a2) - (a0 + a3)), c.Fs * ((a2 + a3) - (a0 + a1)), c.kq * ((a0 + a2) - (a1 + a3)));
     T f_x = 0, f_y = 0;
-    {   // body B: principal frame == body frame (4-fold symmetry)
+    // bodies B and D run the same inertia-box arithmetic on different numbers: FP32 with a pendulum evaluates both in one packed
+    // pass (B | D) further down
+    constexpr bool kFluidPair = PEND && std::is_same<T, float>::value;
+    if constexpr (!kFluidPair) {   // body B: principal frame == body frame (4-fold symmetry)
         const FluidBox<T> fb = fluid_box(c.mB, c.IBx, c.IBy, c.IBz);
         V3<T> f, t;
         fluid_apply(fb, om, vb + mk(om.y * c.cz, -om.x * c.cz, T(0)), f, t);
@@ -363,10 +403,22 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
             f_x += t.x;
         }
         {   // body D: frame axes (xd, yc, n), COM at hinge + rho
-            const FluidBox<T> fb = fluid_box(mD, c.IDx, c.IDx, c.IDz);
             const V3<T> vD = vh + cross(omD, rho);
             V3<T> fl, tl;
-            fluid_apply(fb, mk(dot(xd, omD), dot(yc, omD), dot(n, omD)), mk(dot(xd, vD), dot(yc, vD), dot(n, vD)), fl, tl);
+            if constexpr (kFluidPair) {
+                const FluidBox<F2> fb = fluid_box(F2(c.mB, mD), F2(c.IBx, c.IDx), F2(c.IBy, c.IDx), F2(c.IBz, c.IDz));
+                const V3<T> vB = vb + mk(om.y * c.cz, -om.x * c.cz, T(0));
+                V3<F2> f2, t2;
+                fluid_apply(fb, mk(F2(om.x, dot(xd, omD)), F2(om.y, dot(yc, omD)), F2(om.z, dot(n, omD))),
+                            mk(F2(vB.x, dot(xd, vD)), F2(vB.y, dot(yc, vD)), F2(vB.z, dot(n, vD))), f2, t2);
+                const V3<T> fB = mk(f2.x.lo(), f2.y.lo(), f2.z.lo()), tB = mk(t2.x.lo(), t2.y.lo(), t2.z.lo());
+                flin = flin + fB;
+                fang = fang + tB + mk(-c.cz * fB.y, c.cz * fB.x, T(0));
+                fl = mk(f2.x.hi(), f2.y.hi(), f2.z.hi()); tl = mk(t2.x.hi(), t2.y.hi(), t2.z.hi());
+            } else {
+                const FluidBox<T> fb = fluid_box(mD, c.IDx, c.IDx, c.IDz);
+                fluid_apply(fb, mk(dot(xd, omD), dot(yc, omD), dot(n, omD)), mk(dot(xd, vD), dot(yc, vD), dot(n, vD)), fl, tl);
+            }
             const V3<T> f = fl.x * xd + fl.y * yc + fl.z * n;
             const V3<T> W = tl.x * xd + tl.y * yc + tl.z * n + cross(rho, f);
             flin = flin + f;
@@ -390,26 +442,60 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
         const V3<T> px = (-mu * cy) * yc, py = mu * xd;                      // linear momentum per unit hinge rate
         const V3<T> Lx = mk(IC + P + QmP * n.x * n.x, QmP * n.x * n.y, QmP * n.x * n.z) + mk(dl * px.y, -dl * px.x, T(0));
         const V3<T> Ly = P * yc + mk(dl * py.y, -dl * py.x, T(0));
-        const V3<T> alx = ldl3_solve(L, Lx - cross(com, px)), acx = inv_m * px + cross(com, alx);
-        const V3<T> aly = ldl3_solve(L, Ly - cross(com, py)), acy = inv_m * py + cross(com, aly);
-        const T Sxx = (IC + P + QmP * n.x * n.x) - (dot(px, acx) + dot(Lx, alx));
-        const T Sxy = -(dot(px, acy) + dot(Lx, aly));
-        const T Syy = P - (dot(py, acy) + dot(Ly, aly));
-        const T r1 = rx - (dot(px, ac0) + dot(Lx, al0)), r2 = ry - (dot(py, ac0) + dot(Ly, al0));
-        {   // explicit (qacc of mj_fwdAcceleration): feeds the accelerometer
-            const T idet = rcp_(Sxx * Syy - Sxy * Sxy);
-            const T hax = (Syy * r1 - Sxy * r2) * idet, hay = (Sxx * r2 - Sxy * r1) * idet;
-            a_e = ac0 - hax * acx - hay * acy;
-            al_e = al0 - hax * alx - hay * aly;
-            hax_e = hax; hay_e = hay;
+        V3<T> alx, acx, aly, acy;
+        T Sxx, Syy, r1, r2;
+        if constexpr (std::is_same<T, float>::value) {
+            // the hinge-x and hinge-y columns are the same arithmetic on different right-hand sides: one packed pass (x | y)
+            const V3<F2> pp = mk(F2(px.x, py.x), F2(px.y, py.y), F2(px.z, py.z)), LL = mk(F2(Lx.x, Ly.x), F2(Lx.y, Ly.y), F2(Lx.z, Ly.z));
+            const V3<F2> com2 = mk(F2(com.x), F2(com.y), F2(com.z));
+            Ldl3<F2> L2;
+            L2.l10 = F2(L.l10); L2.l20 = F2(L.l20); L2.l21 = F2(L.l21); L2.id0 = F2(L.id0); L2.id1 = F2(L.id1); L2.id2 = F2(L.id2);
+            const V3<F2> al = ldl3_solve(L2, LL - cross(com2, pp));
+            const V3<F2> ac = F2(inv_m) * pp + cross(com2, al);
+            alx = mk(al.x.lo(), al.y.lo(), al.z.lo()); aly = mk(al.x.hi(), al.y.hi(), al.z.hi());
+            acx = mk(ac.x.lo(), ac.y.lo(), ac.z.lo()); acy = mk(ac.x.hi(), ac.y.hi(), ac.z.hi());
+            const F2 dg = dot(pp, ac) + dot(LL, al);                         // (px.acx + Lx.alx | py.acy + Ly.aly)
+            Sxx = (IC + P + QmP * n.x * n.x) - dg.lo(); Syy = P - dg.hi();
+            const F2 rr = F2(rx, ry) - (dot(pp, mk(F2(ac0.x), F2(ac0.y), F2(ac0.z))) + dot(LL, mk(F2(al0.x), F2(al0.y), F2(al0.z))));
+            r1 = rr.lo(); r2 = rr.hi();
+        } else {
+            alx = ldl3_solve(L, Lx - cross(com, px)); acx = inv_m * px + cross(com, alx);
+            aly = ldl3_solve(L, Ly - cross(com, py)); acy = inv_m * py + cross(com, aly);
+            Sxx = (IC + P + QmP * n.x * n.x) - (dot(px, acx) + dot(Lx, alx));
+            Syy = P - (dot(py, acy) + dot(Ly, aly));
+            r1 = rx - (dot(px, ac0) + dot(Lx, al0)); r2 = ry - (dot(py, ac0) + dot(Ly, al0));
         }
-        if (ADVANCE) {  // implicit in joint damping (mj_EulerSkip): (M + h diag(B)) qacc = qfrc_smooth
+        const T Sxy = -(dot(px, acy) + dot(Lx, aly));
+        if constexpr (ADVANCE && std::is_same<T, float>::value) {
+            // the explicit solution (accelerometer) and the implicit-damping one (integration) differ only in the diagonal of the
+            // 2 x 2 Schur block: one packed pass (explicit | implicit)
             const T hb = h * T(kHingeDamping);
-            const T Sxx2 = Sxx + hb, Syy2 = Syy + hb;
-            const T idet = rcp_(Sxx2 * Syy2 - Sxy * Sxy);
-            hax_i = (Syy2 * r1 - Sxy * r2) * idet; hay_i = (Sxx2 * r2 - Sxy * r1) * idet;
-            a_i = ac0 - hax_i * acx - hay_i * acy;
-            al_i = al0 - hax_i * alx - hay_i * aly;
+            const F2 Sx2(Sxx, Sxx + hb), Sy2(Syy, Syy + hb), Sxy2(Sxy), r12(r1), r22(r2);
+            const F2 idet = rcp_(Sx2 * Sy2 - Sxy2 * Sxy2);
+            const F2 hax = F2(Sy2 * r12 - Sxy2 * r22) * idet, hay = F2(Sx2 * r22 - Sxy2 * r12) * idet;
+            const V3<F2> acx2 = mk(F2(acx.x), F2(acx.y), F2(acx.z)), acy2 = mk(F2(acy.x), F2(acy.y), F2(acy.z));
+            const V3<F2> alx2 = mk(F2(alx.x), F2(alx.y), F2(alx.z)), aly2 = mk(F2(aly.x), F2(aly.y), F2(aly.z));
+            const V3<F2> a2 = mk(F2(ac0.x), F2(ac0.y), F2(ac0.z)) - hax * acx2 - hay * acy2;
+            const V3<F2> l2 = mk(F2(al0.x), F2(al0.y), F2(al0.z)) - hax * alx2 - hay * aly2;
+            a_e = mk(a2.x.lo(), a2.y.lo(), a2.z.lo()); a_i = mk(a2.x.hi(), a2.y.hi(), a2.z.hi());
+            al_e = mk(l2.x.lo(), l2.y.lo(), l2.z.lo()); al_i = mk(l2.x.hi(), l2.y.hi(), l2.z.hi());
+            hax_e = hax.lo(); hay_e = hay.lo(); hax_i = hax.hi(); hay_i = hay.hi();
+        } else {
+            {   // explicit (qacc of mj_fwdAcceleration): feeds the accelerometer
+                const T idet = rcp_(Sxx * Syy - Sxy * Sxy);
+                const T hax = (Syy * r1 - Sxy * r2) * idet, hay = (Sxx * r2 - Sxy * r1) * idet;
+                a_e = ac0 - hax * acx - hay * acy;
+                al_e = al0 - hax * alx - hay * aly;
+                hax_e = hax; hay_e = hay;
+            }
+            if (ADVANCE) {  // implicit in joint damping (mj_EulerSkip): (M + h diag(B)) qacc = qfrc_smooth
+                const T hb = h * T(kHingeDamping);
+                const T Sxx2 = Sxx + hb, Syy2 = Syy + hb;
+                const T idet = rcp_(Sxx2 * Syy2 - Sxy * Sxy);
+                hax_i = (Syy2 * r1 - Sxy * r2) * idet; hay_i = (Sxx2 * r2 - Sxy * r1) * idet;
+                a_i = ac0 - hax_i * acx - hay_i * acy;
+                al_i = al0 - hax_i * alx - hay_i * aly;
+            }
         }
     }
 
@@ -466,7 +552,21 @@ DSIM_DEV void substep(EnvState<T> &s, const EnvConsts<T> &c, const T ctrl[4], T 
 // scipy Rotation.as_euler('ZYX')[::-1] (quaternion algorithm, gimbal-lock branches, eps 1e-7)
 template <typename T> DSIM_DEV void quat_to_rpy(T w, T x, T y, T z, T &roll, T &pitch, T &yaw) {
     const T a = w - y, b = x + z, c = y + w, d = z - x;
-    const T hs = atan2_(b, a), hd = atan2_(d, c);
+    T hs, hd;
+    if constexpr (std::is_same<T, float>::value) {
+        // the two half-angle arctangents through one packed evaluation: atan(t) = t P(t^2) on (hs | hd), fix-ups per half
+        const float ax0 = fabsf(a), ay0 = fabsf(b), ax1 = fabsf(c), ay1 = fabsf(d);
+        const F2 mx(fmaxf(ax0, ay0), fmaxf(ax1, ay1)), mn(fminf(ax0, ay0), fminf(ax1, ay1));
+        const F2 t = mn * rcp_(max_(mx, F2(1e-37f))), s2 = t * t;
+        F2 r(2.8340642988e-03f);
+        r = fma2(r, s2, F2(-1.6005030503e-02f)); r = fma2(r, s2, F2(4.2587607465e-02f)); r = fma2(r, s2, F2(-7.4954454434e-02f));
+        r = fma2(r, s2, F2(1.0636754098e-01f)); r = fma2(r, s2, F2(-1.4202570512e-01f)); r = fma2(r, s2, F2(1.9992483579e-01f));
+        r = fma2(r, s2, F2(-3.3333066781e-01f)); r = fma2(r, s2, F2(9.9999998424e-01f));
+        r = r * t;
+        float r0 = r.lo(), r1 = r.hi();
+        r0 = ay0 > ax0 ? 1.57079632679f - r0 : r0; r0 = a < 0.f ? 3.14159265359f - r0 : r0; hs = copysignf(r0, b);
+        r1 = ay1 > ax1 ? 1.57079632679f - r1 : r1; r1 = c < 0.f ? 3.14159265359f - r1 : r1; hd = copysignf(r1, d);
+    } else { hs = atan2_(b, a); hd = atan2_(d, c); }
     T a1 = T(2) * atan2_sqrt(c * c + d * d, a * a + b * b);
     const bool case1 = abs_(a1) <= T(1e-7), case2 = abs_(a1 - T(kPi)) <= T(1e-7);
     T a0, a2;

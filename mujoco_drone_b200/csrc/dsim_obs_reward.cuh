@@ -146,7 +146,15 @@ DSIM_DEV void emit_obs(int id, const EnvState<T> &s, const PostState<T> &p, V3<T
     if (id == 0) { emit_state_row<T, PEND>(s, p, start, ref_off, prm, out); return; }
     const T hd = wrap_pi(p.ref_yaw - p.yaw);                               // (ref_yaw - yaw + pi) % 2pi - pi
     const V3<T> gerr = T(-1) * p.err;                                      // reference[:3] - xyz
-    const V3<T> lerr = tmul(p.R, gerr), lvel = tmul(p.R, s.vel);
+    V3<T> lerr, lvel;
+    if constexpr (std::is_same<T, float>::value) {
+        // R^T applied to the position error and to the velocity: one packed pass (err | vel)
+        const V3<F2> v2 = mk(F2(gerr.x, s.vel.x), F2(gerr.y, s.vel.y), F2(gerr.z, s.vel.z));
+        const F2 lx = F2(p.R.m[0]) * v2.x + F2(p.R.m[3]) * v2.y + F2(p.R.m[6]) * v2.z;
+        const F2 ly = F2(p.R.m[1]) * v2.x + F2(p.R.m[4]) * v2.y + F2(p.R.m[7]) * v2.z;
+        const F2 lz = F2(p.R.m[2]) * v2.x + F2(p.R.m[5]) * v2.y + F2(p.R.m[8]) * v2.z;
+        lerr = mk(lx.lo(), ly.lo(), lz.lo()); lvel = mk(lx.hi(), ly.hi(), lz.hi());
+    } else { lerr = tmul(p.R, gerr); lvel = tmul(p.R, s.vel); }
     // the wrappers index the 33-layout: [12:14] pendulum_rp, [14:16] pendulum_ang_vel, [16:19] acc, [19:23] act.
     // Without a pendulum the 29-layout shifts: [12:15] acc, [15:19] act -> NoPend variants read act[1:4] as "acc" (Q11).
     const T s12 = PEND ? s.hx : s.acc.x, s13 = PEND ? s.hy : s.acc.y, s14 = PEND ? s.hvx : s.acc.z, s15 = PEND ? s.hvy : s.act[0];

@@ -9,8 +9,8 @@
 // whole templated physics (substep<T>, V3<T>, ...) instantiates for T = F2 unchanged.  nvcc does not contract or vectorise
 // across inline asm, so products stay unevaluated (F2Mul) until they meet their addend: a * b + c, c - a * b,
 // a * b - c * d become one FFMA2 like the scalar code's FFMA.
+// Included by dsim_device.cuh (after the scalar helpers and V3, before the physics that uses it); not a stand-alone header.
 #pragma once
-#include "dsim_device.cuh"
 
 namespace dsim {
 
@@ -106,31 +106,6 @@ DSIM_DEV void sincos_hinge(F2 a, F2 *s, F2 *c) {
     const float ss0 = (q0 & 1) ? cs0 : sn0, cc0 = (q0 & 1) ? sn0 : cs0, ss1 = (q1 & 1) ? cs1 : sn1, cc1 = (q1 & 1) ? sn1 : cs1;
     *s = F2(__int_as_float(__float_as_int(ss0) ^ ((q0 & 2) << 30)), __int_as_float(__float_as_int(ss1) ^ ((q1 & 2) << 30)));
     *c = F2(__int_as_float(__float_as_int(cc0) ^ (((q0 + 1) & 2) << 30)), __int_as_float(__float_as_int(cc1) ^ (((q1 + 1) & 2) << 30)));
-}
-
-// free-joint quaternion: normalisation and the per-step rotation, packed where it is plain arithmetic
-DSIM_DEV void quat_unit(F2 sw, F2 sx, F2 sy, F2 sz, F2 &qw, F2 &qx, F2 &qy, F2 &qz) {
-    const F2 qn = sw * sw + sx * sx + sy * sy + sz * sz;
-    const F2 qi = rsqrt_(qn);
-    qw = sw * qi; qx = sx * qi; qy = sy * qi; qz = sz * qi;
-    const bool ok0 = qn.lo() >= 1e-30f, ok1 = qn.hi() >= 1e-30f;
-    if (!(ok0 && ok1)) {                                            // (near-)zero quaternion -> identity, per half
-        qw = F2(ok0 ? qw.lo() : 1.f, ok1 ? qw.hi() : 1.f); qx = F2(ok0 ? qx.lo() : 0.f, ok1 ? qx.hi() : 0.f);
-        qy = F2(ok0 ? qy.lo() : 0.f, ok1 ? qy.hi() : 0.f); qz = F2(ok0 ? qz.lo() : 0.f, ok1 ? qz.hi() : 0.f);
-    }
-}
-DSIM_DEV void quat_step(F2 h, F2 w2, F2 &rw, F2 &kq) {
-    const F2 z = (F2(0.25f) * h * h) * w2;
-    if (z.lo() <= 0.64f && z.hi() <= 0.64f) {                       // both envs in the Taylor range (|w| <= 160 rad/s at 100 Hz)
-        F2 ps = fma2(z, F2(2.7557319e-6f), F2(-1.9841270e-4f)); ps = fma2(ps, z, F2(8.3333333e-3f)); ps = fma2(ps, z, F2(-1.6666667e-1f));
-        kq = (F2(0.5f) * h) * fma2(ps, z, F2(1.0f));
-        F2 pc = fma2(z, F2(-2.7557319e-7f), F2(2.4801587e-5f)); pc = fma2(pc, z, F2(-1.3888889e-3f)); pc = fma2(pc, z, F2(4.1666667e-2f)); pc = fma2(pc, z, F2(-0.5f));
-        rw = fma2(pc, z, F2(1.0f));
-    } else {
-        float r0, k0, r1, k1;
-        quat_step(h.lo(), w2.lo(), r0, k0); quat_step(h.hi(), w2.hi(), r1, k1);
-        rw = F2(r0, r1); kq = F2(k0, k1);
-    }
 }
 
 }  // namespace dsim
