@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[3]: RMA domain randomisation, 1M envs over 8 GPUs = 131072 per GPU (train_RMA.py:66-75)
     "c4": dict(cls="LocalFrameRPYParamsEnv", reward="distance_energy_reward", envs_per_gpu=131072, alg_bytes=104 + 94 + 88 + 24,
-               traffic=24.50e6 + 24.86e6, traffic_src=("profiles/r02c_dram_steady_state.csv: dram__bytes_read.sum (24.50 MB) + dram__bytes_write.sum (24.86 MB) per launch, mean over the "
+               traffic=24.50e6 + 24.66e6, traffic_src=("profiles/r02f_dram_steady_state.csv: dram__bytes_read.sum (24.50 MB) + dram__bytes_write.sum (24.66 MB) per launch, mean over the "
                                                        "18 device-resident launches of a single-pass ncu run of this workload WITHOUT cache control (--cache-control none) after the 1500-step "
                                                        "pre-roll, 8 replicas round-robin: the write-backs of earlier launches are evicted while later ones run, so the steady-state "
                                                        "write traffic is visible (an ncu --set full capture flushes the caches and sees reads only)"),
