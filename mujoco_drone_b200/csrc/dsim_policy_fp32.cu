@@ -24,7 +24,10 @@
 namespace {
 
 constexpr int S_DIM = 16, P_DIM = 6, A_DIM = 4, E_DIM = 8, OBS_DIM = S_DIM + P_DIM, ENC_H = 32, K1 = S_DIM + A_DIM + E_DIM;   // 28
-constexpr int TM = 128, LDT = TM + 4;      // rows per tile; row pitch of the transposed tiles (132 = 4 mod 32: conflict-free 16-byte stores)
+#ifndef DSIM_P32_TM
+#define DSIM_P32_TM 128
+#endif
+constexpr int TM = DSIM_P32_TM, LDT = TM + 4;      // rows per tile; row pitch of the transposed tiles (132 = 4 mod 32: conflict-free 16-byte stores)
 // fp32 blob (float offsets): transposed weights Wt[k][n] then bias, per layer
 constexpr int F_W1 = 0, F_B1 = F_W1 + K1 * 256;                 // 28 -> 256
 constexpr int F_W2 = F_B1 + 256, F_B2 = F_W2 + 256 * 128;       // 256 -> 128
@@ -44,7 +47,8 @@ struct P32 {
     int n, ntiles;
 };
 
-constexpr int NT = 512;                    // threads per CTA
+constexpr int NT = TM * 4;                 // threads per CTA: one warp per 8 rows
+constexpr int kCtasPerSm = TM == 128 ? 1 : 2;
 __device__ __forceinline__ float tanh_acc(float x) {
     // 1 - 2 / (e^{2x} + 1): exact limits for |x| large (e -> inf: 1; e -> 0: -1), no cancellation near 0 beyond 1 ulp of 1
     const float e = __expf(2.0f * x);
@@ -125,7 +129,7 @@ __device__ __forceinline__ void dense(const float *__restrict__ Wt, const float 
     }
 }
 
-__global__ void __launch_bounds__(NT, 1) rma_full_forward_fp32_kernel(const P32 p) {
+__global__ void __launch_bounds__(NT, kCtasPerSm) rma_full_forward_fp32_kernel(const P32 p) {
     extern __shared__ __align__(16) float sm[];
     float *A = sm, *B = sm + 256 * LDT;                              // A: up to 256 activation rows deep, B: up to 128
     const int tid = threadIdx.x;
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(NT, 1) rma_full_forward_fp32_kernel(const P32 
         dense<128, 128, true>(p.w + F_V2, p.w + F_C2, A + 128 * LDT, B);   // v2 = tanh(V2 v1 + c2) -> B
         // logits = W4 l1 + b4: 128 rows x 8 outputs, thread -> (row, output pair)
         {
-            const int row = tid & (TM - 1), o2 = (tid >> 7) * 2;
+            const int row = tid & (TM - 1), o2 = (tid / TM) * 2;
             float x0 = __ldg(p.w + F_B4 + o2), x1 = __ldg(p.w + F_B4 + o2 + 1);
             #pragma unroll 8
             for (int k = 0; k < 128; k++) {
@@ -242,7 +246,7 @@ extern "C" int dsim_policy32_forward(DsimPolicy32 *h, const float *obs_dev, cons
     p.n = n; p.ntiles = (n + TM - 1) / TM;
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof lc);
-    lc.gridDim = dim3(p.ntiles < h->sms ? p.ntiles : h->sms); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = SMEM_BYTES; lc.stream = (cudaStream_t)stream;
+    lc.gridDim = dim3(p.ntiles < kCtasPerSm * h->sms ? p.ntiles : kCtasPerSm * h->sms); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = SMEM_BYTES; lc.stream = (cudaStream_t)stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
