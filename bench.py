@@ -599,7 +599,11 @@ def main():
     st = {k: sum(e.episode_stats()[k] for e in envs) for k in ddist.STAT_KEYS}
     stats = ddist.allreduce_episode_stats(st, device=dev)     # the path's only collective
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank_ms = None
     if world > 1:
+        allms = [torch.zeros_like(tmax) for _ in range(world)]
+        dist.all_gather(allms, tmax)                         # reported next to the max: which GPU of the box set the pace
+        per_rank_ms = [float(t.item()) / timed_steps for t in allms]
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
     value = world * n * timed_steps / (ms * 1e-3)
@@ -764,6 +768,8 @@ def main():
         "clocks": clocks,
         "episode_stats": {k: stats[k] for k in ("n_episodes", "mean_return", "mean_length", "n_nonfinite", "n_near_ground")},
     }
+    if per_rank_ms:
+        line["per_rank_ms_per_step"] = per_rank_ms                 # `ms_per_step` is their maximum
     if extras:
         line["extras"] = extras
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
